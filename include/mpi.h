@@ -1,0 +1,72 @@
+/* pnfft-b200 mini-MPI: the control-plane subset of MPI that PNFFT and its callers use.
+ *
+ * PNFFT's public header includes <mpi.h> (reference api/pnfft.h:28) and every entry point
+ * takes an MPI_Comm.  The target image has no MPI, so the library ships this stand-in:
+ * one process per GPU, started by any launcher that exports RANK / WORLD_SIZE /
+ * LOCAL_RANK / MASTER_ADDR / MASTER_PORT (torchrun does), rendezvous over TCP on
+ * MASTER_PORT+PNFFT_B200_PORT_OFFSET, host-side collectives through rank 0, and the
+ * data plane (halo exchange, FFT transposes) on NCCL over NVLink.  A build against a
+ * real MPI only has to replace this header and pnfft_b200/csrc/minimpi.cpp.
+ *
+ * Handles are small integers (MPICH style) so they pass through ctypes/FFI unchanged.
+ */
+#ifndef PNFFT_B200_MINI_MPI_H
+#define PNFFT_B200_MINI_MPI_H 1
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int MPI_Comm;
+typedef int MPI_Datatype;
+typedef int MPI_Op;
+typedef int MPI_Fint;
+
+#define MPI_SUCCESS 0
+#define MPI_ERR_OTHER 15
+
+#define MPI_COMM_NULL  0
+#define MPI_COMM_WORLD 1
+#define MPI_COMM_SELF  2
+
+#define MPI_CHAR        1
+#define MPI_INT         2
+#define MPI_UNSIGNED    3
+#define MPI_LONG        4
+#define MPI_FLOAT       5
+#define MPI_DOUBLE      6
+#define MPI_LONG_DOUBLE 7
+#define MPI_BYTE        8
+
+#define MPI_SUM 1
+#define MPI_MAX 2
+#define MPI_MIN 3
+
+int MPI_Init(int *argc, char ***argv);
+int MPI_Initialized(int *flag);
+int MPI_Finalize(void);
+int MPI_Abort(MPI_Comm comm, int errorcode);
+int MPI_Comm_rank(MPI_Comm comm, int *rank);
+int MPI_Comm_size(MPI_Comm comm, int *size);
+int MPI_Comm_dup(MPI_Comm comm, MPI_Comm *newcomm);
+int MPI_Comm_free(MPI_Comm *comm);
+int MPI_Cart_create(MPI_Comm comm, int ndims, const int *dims, const int *periods,
+                    int reorder, MPI_Comm *comm_cart);
+int MPI_Cartdim_get(MPI_Comm comm, int *ndims);
+int MPI_Cart_get(MPI_Comm comm, int maxdims, int *dims, int *periods, int *coords);
+int MPI_Cart_coords(MPI_Comm comm, int rank, int maxdims, int *coords);
+int MPI_Cart_rank(MPI_Comm comm, const int *coords, int *rank);
+int MPI_Barrier(MPI_Comm comm);
+int MPI_Bcast(void *buf, int count, MPI_Datatype type, int root, MPI_Comm comm);
+int MPI_Reduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype type,
+               MPI_Op op, int root, MPI_Comm comm);
+int MPI_Allreduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype type,
+                  MPI_Op op, MPI_Comm comm);
+double MPI_Wtime(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

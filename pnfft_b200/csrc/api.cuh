@@ -1,0 +1,374 @@
+// extern "C" entry points of libpnfft_b200.so for one precision.  Included twice (api_d.cu, api_f.cu) with
+//   PNX(name)  -> pnfft_##name / pnfftf_##name      RT -> double / float
+// Signatures are those of include/pnfft.h (= reference api/pnfft.h:51-288).
+#include <pnfft.h>
+
+#include "core.cuh"
+
+using pnb::INT;
+typedef pnb::Core<RT> CoreT;
+typedef pnb::Plan<RT> PlanT;
+typedef pnb::Nodes<RT> NodesT;
+typedef RT CT[2];
+
+#define AS_PLAN(p) (reinterpret_cast<PlanT *>(p))
+#define AS_NODES(p) (reinterpret_cast<NodesT *>(p))
+
+namespace {
+
+void local_size_impl(int d, const INT *N, const INT *n, const RT *x_max, int m, MPI_Comm comm, unsigned flags, bool c2r,
+                     INT *local_N, INT *local_N_start, RT *lo, RT *up) {
+  if (d != 3) { fprintf(stderr, "!!! Error in PNFFT Planer: d != 3 not yet implemented !!!\n"); return; }
+  pnb::Mesh mesh;
+  if (!pnb::get_mesh(comm, mesh)) return;
+  pnb::Layout L;
+  pnb::compute_layout<RT>(L, mesh, N, n, x_max, m, c2r, flags);
+  for (int t = 0; t < 3; t++) { local_N[t] = L.local_N[t]; local_N_start[t] = L.local_N_start[t]; }
+  pnb::node_borders<RT>(L, x_max, lo, up);
+}
+
+void adv_defaults(const INT *N, INT *n, RT *x_max, int *m) {
+  // reference api/api-adv.c:172-192
+  for (int t = 0; t < 3; t++) { n[t] = 2 * N[t]; x_max[t] = (RT)0.5; }
+  *m = 6;
+}
+
+}  // namespace
+
+extern "C" {
+
+int PNX(create_procmesh)(int rnk, MPI_Comm comm, const int *np, MPI_Comm *comm_cart) {
+  int periods[3] = {1, 1, 1}, size = 0, prod = 1;
+  MPI_Comm_size(comm, &size);
+  for (int t = 0; t < rnk; t++) prod *= np[t];
+  if (prod != size) return 1;
+  return MPI_Cart_create(comm, rnk, np, periods, 1, comm_cart);
+}
+int PNX(create_procmesh_2d)(MPI_Comm comm, int np0, int np1, MPI_Comm *comm_cart_2d) {
+  const int np[2] = {np0, np1};
+  return PNX(create_procmesh)(2, comm, np, comm_cart_2d);
+}
+
+void PNX(local_size_guru)(int d, const INT *N, const INT *n, const RT *x_max, int m, MPI_Comm comm_cart, unsigned pnfft_flags,
+                          INT *local_N, INT *local_N_start, RT *lo, RT *up) {
+  local_size_impl(d, N, n, x_max, m, comm_cart, pnfft_flags, false, local_N, local_N_start, lo, up);
+}
+void PNX(local_size_guru_c2r)(int d, const INT *N, const INT *n, const RT *x_max, int m, MPI_Comm comm_cart, unsigned pnfft_flags,
+                              INT *local_N, INT *local_N_start, RT *lo, RT *up) {
+  local_size_impl(d, N, n, x_max, m, comm_cart, pnfft_flags, true, local_N, local_N_start, lo, up);
+}
+void PNX(local_size_adv)(int d, const INT *N, MPI_Comm comm_cart, unsigned pnfft_flags, INT *local_N, INT *local_N_start, RT *lo, RT *up) {
+  INT n[3]; RT x_max[3]; int m;
+  adv_defaults(N, n, x_max, &m);
+  local_size_impl(d, N, n, x_max, m, comm_cart, pnfft_flags, false, local_N, local_N_start, lo, up);
+}
+void PNX(local_size_adv_c2r)(int d, const INT *N, MPI_Comm comm_cart, unsigned pnfft_flags, INT *local_N, INT *local_N_start, RT *lo, RT *up) {
+  INT n[3]; RT x_max[3]; int m;
+  adv_defaults(N, n, x_max, &m);
+  local_size_impl(d, N, n, x_max, m, comm_cart, pnfft_flags, true, local_N, local_N_start, lo, up);
+}
+void PNX(local_size_3d)(const INT *N, MPI_Comm comm_cart, unsigned pnfft_flags, INT *local_N, INT *local_N_start, RT *lo, RT *up) {
+  PNX(local_size_adv)(3, N, comm_cart, pnfft_flags, local_N, local_N_start, lo, up);
+}
+void PNX(local_size_3d_c2r)(const INT *N, MPI_Comm comm_cart, unsigned pnfft_flags, INT *local_N, INT *local_N_start, RT *lo, RT *up) {
+  PNX(local_size_adv_c2r)(3, N, comm_cart, pnfft_flags, local_N, local_N_start, lo, up);
+}
+
+PNX(plan) PNX(init_guru)(int d, const INT *N, const INT *n, const RT *x_max, int m, unsigned pnfft_flags, unsigned fftw_flags, MPI_Comm comm_cart) {
+  if (d != 3) { fprintf(stderr, "!!! Error in PNFFT Planer: d != 3 not yet implemented !!!\n"); return nullptr; }
+  return reinterpret_cast<PNX(plan)>(CoreT::init(N, n, x_max, m, pnfft_flags, fftw_flags, comm_cart, false));
+}
+PNX(plan) PNX(init_guru_c2r)(int d, const INT *N, const INT *n, const RT *x_max, int m, unsigned pnfft_flags, unsigned fftw_flags, MPI_Comm comm_cart) {
+  if (d != 3) { fprintf(stderr, "!!! Error in PNFFT Planer: d != 3 not yet implemented !!!\n"); return nullptr; }
+  return reinterpret_cast<PNX(plan)>(CoreT::init(N, n, x_max, m, pnfft_flags, fftw_flags, comm_cart, true));
+}
+PNX(plan) PNX(init_adv)(int d, const INT *N, unsigned pnfft_flags, unsigned fftw_flags, MPI_Comm comm_cart) {
+  INT n[3]; RT x_max[3]; int m;
+  adv_defaults(N, n, x_max, &m);
+  return PNX(init_guru)(d, N, n, x_max, m, pnfft_flags, fftw_flags, comm_cart);
+}
+PNX(plan) PNX(init_adv_c2r)(int d, const INT *N, unsigned pnfft_flags, unsigned fftw_flags, MPI_Comm comm_cart) {
+  INT n[3]; RT x_max[3]; int m;
+  adv_defaults(N, n, x_max, &m);
+  return PNX(init_guru_c2r)(d, N, n, x_max, m, pnfft_flags, fftw_flags, comm_cart);
+}
+PNX(plan) PNX(init_3d)(const INT *N, MPI_Comm comm_cart) { return PNX(init_adv)(3, N, PNFFT_MALLOC_F_HAT, 0, comm_cart); }
+PNX(plan) PNX(init_3d_c2r)(const INT *N, MPI_Comm comm_cart) { return PNX(init_adv_c2r)(3, N, PNFFT_MALLOC_F_HAT, 0, comm_cart); }
+void PNX(finalize)(PNX(plan) ths, unsigned flags) { CoreT::finalize(AS_PLAN(ths), flags); }
+
+PNX(nodes) PNX(init_nodes)(INT local_M, unsigned malloc_flags) { return reinterpret_cast<PNX(nodes)>(CoreT::init_nodes(local_M, malloc_flags)); }
+void PNX(free_nodes)(PNX(nodes) ths, unsigned flags) { CoreT::free_nodes(AS_NODES(ths), flags); }
+void PNX(precompute_psi)(PNX(plan) ths, PNX(nodes) nodes, unsigned precompute_flags) { CoreT::precompute_psi(AS_PLAN(ths), AS_NODES(nodes), precompute_flags); }
+
+void PNX(set_f)(CT *f, PNX(nodes) nodes) { AS_NODES(nodes)->f = (RT *)f; }
+void PNX(set_grad_f)(CT *grad_f, PNX(nodes) nodes) { AS_NODES(nodes)->grad_f = (RT *)grad_f; }
+void PNX(set_hessian_f)(CT *h, PNX(nodes) nodes) { AS_NODES(nodes)->hessian_f = (RT *)h; }
+void PNX(set_f_real)(RT *f, PNX(nodes) nodes) { AS_NODES(nodes)->f = f; }
+void PNX(set_grad_f_real)(RT *grad_f, PNX(nodes) nodes) { AS_NODES(nodes)->grad_f = grad_f; }
+void PNX(set_hessian_f_real)(RT *h, PNX(nodes) nodes) { AS_NODES(nodes)->hessian_f = h; }
+void PNX(set_x)(RT *x, PNX(nodes) nodes) { AS_NODES(nodes)->x = x; AS_NODES(nodes)->binned = false; AS_NODES(nodes)->d_x_bound = nullptr; }
+void PNX(set_f_hat)(CT *f_hat, PNX(plan) ths) { AS_PLAN(ths)->f_hat = (PlanT::C *)f_hat; }
+void PNX(set_f_hat_real)(RT *f_hat, PNX(plan) ths) { AS_PLAN(ths)->f_hat = (PlanT::C *)f_hat; }
+void PNX(set_b)(RT b0, RT b1, RT b2, PNX(plan) ths) {
+  // reference api/api-basic.c:587-596: new shape parameters, window tables recomputed
+  PlanT *p = AS_PLAN(ths);
+  p->b[0] = b0; p->b[1] = b1; p->b[2] = b2;
+  CoreT::upload_window_tables(p);
+}
+CT *PNX(get_f)(const PNX(nodes) nodes) { return (CT *)AS_NODES(nodes)->f; }
+CT *PNX(get_grad_f)(const PNX(nodes) nodes) { return (CT *)AS_NODES(nodes)->grad_f; }
+CT *PNX(get_hessian_f)(const PNX(nodes) nodes) { return (CT *)AS_NODES(nodes)->hessian_f; }
+RT *PNX(get_f_real)(const PNX(nodes) nodes) { return AS_NODES(nodes)->f; }
+RT *PNX(get_grad_f_real)(const PNX(nodes) nodes) { return AS_NODES(nodes)->grad_f; }
+RT *PNX(get_hessian_f_real)(const PNX(nodes) nodes) { return AS_NODES(nodes)->hessian_f; }
+RT *PNX(get_x)(const PNX(nodes) nodes) { return AS_NODES(nodes)->x; }
+CT *PNX(get_f_hat)(const PNX(plan) ths) { return (CT *)AS_PLAN(ths)->f_hat; }
+RT *PNX(get_f_hat_real)(const PNX(plan) ths) { return (RT *)AS_PLAN(ths)->f_hat; }
+int PNX(get_d)(const PNX(plan)) { return 3; }
+int PNX(get_m)(const PNX(plan) ths) { return AS_PLAN(ths)->L.m; }
+void PNX(get_x_max)(const PNX(plan) ths, RT *x_max) { for (int t = 0; t < 3; t++) x_max[t] = AS_PLAN(ths)->x_max[t]; }
+void PNX(get_N)(const PNX(plan) ths, INT *N) { for (int t = 0; t < 3; t++) N[t] = AS_PLAN(ths)->L.N[t]; }
+void PNX(get_n)(const PNX(plan) ths, INT *n) { for (int t = 0; t < 3; t++) n[t] = AS_PLAN(ths)->L.n[t]; }
+unsigned PNX(get_pnfft_flags)(const PNX(plan) ths) { return AS_PLAN(ths)->pnfft_flags; }
+unsigned PNX(get_pfft_flags)(const PNX(plan) ths) { return AS_PLAN(ths)->pfft_flags; }
+void PNX(get_b)(const PNX(plan) ths, RT *b0, RT *b1, RT *b2) { *b0 = AS_PLAN(ths)->b[0]; *b1 = AS_PLAN(ths)->b[1]; *b2 = AS_PLAN(ths)->b[2]; }
+
+void PNX(trafo)(PNX(plan) ths, PNX(nodes) nodes, unsigned compute_flags) { CoreT::trafo(AS_PLAN(ths), AS_NODES(nodes), compute_flags); }
+void PNX(adj)(PNX(plan) ths, PNX(nodes) nodes, unsigned compute_flags) { CoreT::adj(AS_PLAN(ths), AS_NODES(nodes), compute_flags); }
+
+void PNX(init)(void) { int f = 0; MPI_Initialized(&f); if (!f) MPI_Init(nullptr, nullptr); }
+void PNX(cleanup)(void) {}
+
+void *PNX(malloc)(size_t n) {
+  void *p = nullptr;
+  if (n == 0) n = 1;
+  if (cudaHostAlloc(&p, n, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    fprintf(stderr, "pnfft-b200: page-locked allocation of %zu bytes failed (no CUDA device?)\n", n);
+    return nullptr;
+  }
+  return p;
+}
+RT *PNX(alloc_real)(size_t n) { return (RT *)PNX(malloc)(sizeof(RT) * n); }
+CT *PNX(alloc_complex)(size_t n) { return (CT *)PNX(malloc)(2 * sizeof(RT) * n); }
+void PNX(free)(void *p) { if (p) cudaFreeHost(p); }
+
+// PFFT's generator is not available; the formula is the one of reference tests/check_vs_pfft.c:167-181
+void PNX(init_f_hat_3d)(const INT *N, const INT *local_N, const INT *local_N_start, unsigned, CT *data) {
+  INT m = 0;
+  for (INT k0 = local_N_start[0]; k0 < local_N_start[0] + local_N[0]; k0++)
+    for (INT k1 = local_N_start[1]; k1 < local_N_start[1] + local_N[1]; k1++)
+      for (INT k2 = local_N_start[2]; k2 < local_N_start[2] + local_N[2]; k2++, m++) {
+        const INT g = ((k0 + N[0] / 2) * N[1] + (k1 + N[1] / 2)) * N[2] + (k2 + N[2] / 2);
+        data[m][0] = (RT)(1000.0 / (double)(2 * g + 1));
+        data[m][1] = (RT)(1000.0 / (double)(2 * g + 2));
+      }
+}
+void PNX(init_f)(INT local_M, CT *data) {
+  for (INT j = 0; j < local_M; j++) {
+    data[j][0] = (RT)100.0 * (RT)rand() / (RT)RAND_MAX;
+    data[j][1] = (RT)100.0 * (RT)rand() / (RT)RAND_MAX;
+  }
+}
+void PNX(init_x_3d_adv)(const RT *lo, const RT *up, const RT *x_max, INT loc_M, RT *x) {
+  for (int t = 0; t < 3; t++) if (lo[t] < -x_max[t] || x_max[t] < up[t]) return;
+  for (INT j = 0; j < loc_M; j++)
+    for (int t = 0; t < 3; t++) {
+      RT tmp;
+      do {
+        RT r;
+        do { r = (RT)rand() / (RT)RAND_MAX; } while (r >= (RT)1.0);
+        tmp = (up[t] - lo[t]) * r + lo[t];
+      } while (tmp < -x_max[t] || x_max[t] <= tmp);
+      x[3 * j + t] = tmp;
+    }
+}
+void PNX(init_x_3d)(const RT *lo, const RT *up, INT loc_M, RT *x) {
+  const RT x_max[3] = {(RT)0.5, (RT)0.5, (RT)0.5};
+  PNX(init_x_3d_adv)(lo, up, x_max, loc_M, x);
+}
+void PNX(zero_f_hat)(PNX(plan) ths) {
+  PlanT *p = AS_PLAN(ths);
+  if (!p || !p->f_hat) return;
+  const size_t bytes = sizeof(PlanT::C) * (size_t)CoreT::local_N_total(p);
+  if (pnb::is_device_ptr(p->f_hat)) cudaMemset(p->f_hat, 0, bytes); else memset(p->f_hat, 0, bytes);
+}
+
+RT PNX(inv_phi_hat)(const PNX(plan) ths, int dim, INT k) {
+  const PlanT *p = AS_PLAN(ths);
+  return pnb::phi_hat_any<RT>(p->kind, (long)k, (long)p->L.n[dim], p->b[dim], p->L.m, true);
+}
+RT PNX(phi_hat)(const PNX(plan) ths, int dim, INT k) {
+  const PlanT *p = AS_PLAN(ths);
+  return pnb::phi_hat_any<RT>(p->kind, (long)k, (long)p->L.n[dim], p->b[dim], p->L.m, false);
+}
+// psi(x), dpsi(x): window at offset x (reference kernel/ndft-parallel.c:2288-2316)
+RT PNX(psi)(const PNX(plan) ths, int dim, RT x) {
+  const PlanT *p = AS_PLAN(ths);
+  const RT n = (RT)p->L.n[dim];
+  if (p->kind == pnb::WIN_BSPLINE) return pnb::bspline<RT>(2 * p->L.m, n * x + (RT)p->L.m);
+  RT psi, d;
+  pnb::window_tap<RT>(p->kind, n * x, n, p->b[dim], p->L.m, false, &psi, &d);
+  return psi;
+}
+RT PNX(dpsi)(const PNX(plan) ths, int dim, RT x) {
+  const PlanT *p = AS_PLAN(ths);
+  const RT n = (RT)p->L.n[dim];
+  const int m = p->L.m;
+  if (p->kind == pnb::WIN_BSPLINE) return n * (pnb::bspline<RT>(2 * m - 1, n * x + (RT)m) - pnb::bspline<RT>(2 * m - 1, n * x + (RT)m - (RT)1));
+  RT psi, d;
+  // window_tap takes y = l - n x, i.e. z = -y = n x
+  pnb::window_tap<RT>(p->kind, -(n * x), n, p->b[dim], m, true, &psi, &d);
+  return d;
+}
+
+void PNX(vpr_complex)(CT *data, INT N, const char *name, MPI_Comm comm) {
+  int rank = 0; MPI_Comm_rank(comm, &rank);
+  if (rank) return;
+  printf("%s:", name);
+  for (INT k = 0; k < N; k++) { if (k % 4 == 0) printf("\n%4td.", k / 4); printf(" %.2e+%.2ei,", (double)data[k][0], (double)data[k][1]); }
+  printf("\n");
+}
+void PNX(vpr_real)(RT *data, INT N, const char *name, MPI_Comm comm) {
+  int rank = 0; MPI_Comm_rank(comm, &rank);
+  if (rank) return;
+  printf("%s:", name);
+  for (INT k = 0; k < N; k++) { if (k % 8 == 0) printf("\n%4td.", k / 8); printf(" %.2e,", (double)data[k]); }
+  printf("\n");
+}
+
+double *PNX(get_timer_trafo)(PNX(plan) ths) { return PNX(timer_copy)(AS_PLAN(ths)->timer_trafo); }
+double *PNX(get_timer_adj)(PNX(plan) ths) { return PNX(timer_copy)(AS_PLAN(ths)->timer_adj); }
+void PNX(timer_average)(double *t) { if (t[0] > 0) for (int i = 1; i < PNFFT_TIMER_LENGTH; i++) t[i] /= t[0]; t[0] = t[0] > 0 ? 1 : 0; }
+double *PNX(timer_copy)(const double *orig) {
+  double *c = (double *)malloc(sizeof(double) * PNFFT_TIMER_LENGTH);
+  for (int i = 0; i < PNFFT_TIMER_LENGTH; i++) c[i] = orig[i];
+  return c;
+}
+double *PNX(timer_reduce_max)(MPI_Comm comm, double *timer) {
+  double *r = (double *)malloc(sizeof(double) * PNFFT_TIMER_LENGTH);
+  MPI_Reduce(timer, r, PNFFT_TIMER_LENGTH, MPI_DOUBLE, MPI_MAX, 0, comm);
+  return r;
+}
+double *PNX(timer_add)(const double *a, const double *b) {
+  double *c = (double *)malloc(sizeof(double) * PNFFT_TIMER_LENGTH);
+  for (int i = 0; i < PNFFT_TIMER_LENGTH; i++) c[i] = a[i] + b[i];
+  return c;
+}
+void PNX(timer_free)(double *t) { free(t); }
+void PNX(reset_timer)(PNX(plan) ths) {
+  memset(AS_PLAN(ths)->timer_trafo, 0, sizeof(double) * PNFFT_TIMER_LENGTH);
+  memset(AS_PLAN(ths)->timer_adj, 0, sizeof(double) * PNFFT_TIMER_LENGTH);
+}
+void PNX(print_average_timer)(const PNX(plan) ths, MPI_Comm comm) {
+  static const char *names[] = {"iter", "whole", "loop_b", "sort_nodes", "gcells", "matrix_b", "matrix_f", "matrix_d", "shift_input", "shift_output"};
+  for (int dir = 0; dir < 2; dir++) {
+    double t[PNFFT_TIMER_LENGTH], mx[PNFFT_TIMER_LENGTH];
+    for (int i = 0; i < PNFFT_TIMER_LENGTH; i++) t[i] = dir ? AS_PLAN(ths)->timer_adj[i] : AS_PLAN(ths)->timer_trafo[i];
+    PNX(timer_average)(t);
+    MPI_Reduce(t, mx, PNFFT_TIMER_LENGTH, MPI_DOUBLE, MPI_MAX, 0, comm);
+    int rank = 0; MPI_Comm_rank(comm, &rank);
+    if (rank == 0) for (int i = 1; i < 8; i++) printf("pnfft_%s_%s = %.3e;\n", dir ? "adj" : "trafo", names[i], mx[i]);
+  }
+}
+void PNX(print_average_timer_adv)(const PNX(plan) ths, MPI_Comm comm) { PNX(print_average_timer)(ths, comm); }
+
+// ---------------------------------------------------------------------------------------------
+// extensions
+// ---------------------------------------------------------------------------------------------
+void PNX(b200_get_local_no)(const PNX(plan) ths, INT *local_no, INT *local_no_start, INT *no) {
+  const PlanT *p = AS_PLAN(ths);
+  for (int t = 0; t < 3; t++) { local_no[t] = p->L.local_no[t]; local_no_start[t] = p->L.local_no_start[t]; no[t] = p->L.no[t]; }
+}
+
+static void grid_io(PlanT *p, RT *compact, bool set) {
+  const pnb::Layout &L = p->L;
+  const int nc = L.c2r ? 1 : 2;
+  const size_t cnt = (size_t)L.local_no[0] * L.local_no[1] * L.local_no[2] * nc;
+  RT *d = nullptr;
+  const bool dev = pnb::is_device_ptr(compact);
+  if (dev) d = compact;
+  else {
+    PNB_CUDA(cudaMalloc((void **)&d, sizeof(RT) * (cnt ? cnt : 1)));
+    if (set) PNB_CUDA(cudaMemcpyAsync(d, compact, sizeof(RT) * cnt, cudaMemcpyHostToDevice, p->stream));
+  }
+  pnb::BoxMap bm = pnb::dense_map(L.local_no[0], L.local_no[1], L.local_no[2], L.ngc[1], L.pitch2, L.gcb[0], L.gcb[1], L.gcb[2], 0);
+  if (L.c2r) pnb::box_copy<RT>(p->stream, (RT *)p->d_grid, d, bm, set ? pnb::BOX_C2A : pnb::BOX_A2C, false, nullptr);
+  else pnb::box_copy<PlanT::C>(p->stream, (PlanT::C *)p->d_grid, (PlanT::C *)d, bm, set ? pnb::BOX_C2A : pnb::BOX_A2C, false, nullptr);
+  if (!dev) {
+    if (!set) PNB_CUDA(cudaMemcpyAsync(compact, d, sizeof(RT) * cnt, cudaMemcpyDeviceToHost, p->stream));
+    PNB_CUDA(cudaStreamSynchronize(p->stream));
+    cudaFree(d);
+  } else PNB_CUDA(cudaStreamSynchronize(p->stream));
+}
+void PNX(b200_set_grid)(PNX(plan) ths, const RT *compact_grid) { grid_io(AS_PLAN(ths), const_cast<RT *>(compact_grid), true); }
+void PNX(b200_get_grid)(PNX(plan) ths, RT *compact_grid) { grid_io(AS_PLAN(ths), compact_grid, false); }
+
+void PNX(b200_set_g1)(PNX(plan) ths, const CT *g1) {
+  PlanT *p = AS_PLAN(ths);
+  PNB_CUDA(cudaMemcpy(p->d_g1, g1, sizeof(PlanT::C) * (size_t)CoreT::local_N_total(p), cudaMemcpyDefault));
+}
+void PNX(b200_get_g1)(PNX(plan) ths, CT *g1) {
+  PlanT *p = AS_PLAN(ths);
+  PNB_CUDA(cudaMemcpy(g1, p->d_g1, sizeof(PlanT::C) * (size_t)CoreT::local_N_total(p), cudaMemcpyDefault));
+}
+
+void PNX(b200_node_grid_index)(PNX(plan) ths, PNX(nodes) nodes, INT *u_and_m0) {
+  PlanT *p = AS_PLAN(ths); NodesT *nd = AS_NODES(nodes);
+  const size_t M = (size_t)nd->local_M;
+  if (!M) return;
+  const RT *dx = CoreT::dev_in(p, nd->x, &nd->d_x, &nd->cap_x, 3 * M, true);
+  long long *d = nullptr;
+  PNB_CUDA(cudaMalloc((void **)&d, sizeof(long long) * 4 * M));
+  pnb::k_node_grid_index<RT><<<(unsigned)((M + 255) / 256), 256, 0, p->stream>>>(CoreT::geom(p), dx, (int)M, d);
+  PNB_CUDA(cudaMemcpyAsync(u_and_m0, d, sizeof(long long) * 4 * M, cudaMemcpyDeviceToHost, p->stream));
+  PNB_CUDA(cudaStreamSynchronize(p->stream));
+  cudaFree(d);
+}
+
+void PNX(b200_sort_nodes)(PNX(plan) ths, PNX(nodes) nodes, INT *keys, INT *perm) {
+  PlanT *p = AS_PLAN(ths); NodesT *nd = AS_NODES(nodes);
+  const size_t M = (size_t)nd->local_M;
+  if (!M) return;
+  const RT *dx = CoreT::dev_in(p, nd->x, &nd->d_x, &nd->cap_x, 3 * M, true);
+  unsigned long long *k_in = nullptr, *k_out = nullptr;
+  int *i_in = nullptr, *i_out = nullptr;
+  PNB_CUDA(cudaMalloc((void **)&k_in, 8 * M)); PNB_CUDA(cudaMalloc((void **)&k_out, 8 * M));
+  PNB_CUDA(cudaMalloc((void **)&i_in, 4 * M)); PNB_CUDA(cudaMalloc((void **)&i_out, 4 * M));
+  pnb::k_sort_keys<RT><<<(unsigned)((M + 255) / 256), 256, 0, p->stream>>>(CoreT::geom(p), p->L.n[0], p->L.n[1], p->L.n[2], dx, (int)M, k_in, i_in);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, i_in, i_out, (int)M, 0, 64, p->stream);
+  void *d_tmp = nullptr;
+  PNB_CUDA(cudaMalloc(&d_tmp, tmp ? tmp : 1));
+  // LSD radix sort is stable: equal keys keep their original order, like the reference's radix_lsdf (util/util.c:206-277)
+  cub::DeviceRadixSort::SortPairs(d_tmp, tmp, k_in, k_out, i_in, i_out, (int)M, 0, 64, p->stream);
+  std::vector<unsigned long long> hk(M);
+  std::vector<int> hi(M);
+  PNB_CUDA(cudaMemcpyAsync(hk.data(), k_out, 8 * M, cudaMemcpyDeviceToHost, p->stream));
+  PNB_CUDA(cudaMemcpyAsync(hi.data(), i_out, 4 * M, cudaMemcpyDeviceToHost, p->stream));
+  PNB_CUDA(cudaStreamSynchronize(p->stream));
+  for (size_t i = 0; i < M; i++) { keys[i] = (INT)hk[i]; perm[i] = (INT)hi[i]; }
+  cudaFree(k_in); cudaFree(k_out); cudaFree(i_in); cudaFree(i_out); cudaFree(d_tmp);
+}
+
+void PNX(b200_window_tensor)(PNX(plan) ths, PNX(nodes) nodes, RT *psi, RT *dpsi) {
+  PlanT *p = AS_PLAN(ths); NodesT *nd = AS_NODES(nodes);
+  const size_t M = (size_t)nd->local_M;
+  if (!M) return;
+  const size_t cnt = M * 3 * (size_t)p->L.cutoff;
+  const RT *dx = CoreT::dev_in(p, nd->x, &nd->d_x, &nd->cap_x, 3 * M, true);
+  RT *d_psi = nullptr, *d_dpsi = nullptr;
+  PNB_CUDA(cudaMalloc((void **)&d_psi, sizeof(RT) * cnt));
+  if (dpsi) PNB_CUDA(cudaMalloc((void **)&d_dpsi, sizeof(RT) * cnt));
+  pnb::k_window_tensor<RT><<<(unsigned)((M * 32 + 255) / 256), 256, 0, p->stream>>>(CoreT::geom(p), dx, (int)M, d_psi, d_dpsi);
+  PNB_CUDA(cudaMemcpyAsync(psi, d_psi, sizeof(RT) * cnt, cudaMemcpyDeviceToHost, p->stream));
+  if (dpsi) PNB_CUDA(cudaMemcpyAsync(dpsi, d_dpsi, sizeof(RT) * cnt, cudaMemcpyDeviceToHost, p->stream));
+  PNB_CUDA(cudaStreamSynchronize(p->stream));
+  cudaFree(d_psi); cudaFree(d_dpsi);
+}
+
+void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant) { AS_PLAN(ths)->kernel_variant = variant; }
+void PNX(b200_get_stage_ms)(PNX(plan) ths, int adjoint, double *ms8) { for (int i = 0; i < 8; i++) ms8[i] = AS_PLAN(ths)->stage_ms[adjoint ? 1 : 0][i]; }
+long long PNX(b200_kernel_launches)(PNX(plan) ths) { return AS_PLAN(ths)->launches; }
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// Host-side state behind the opaque pnfft_plan / pnfft_nodes handles
+// (the reference's plan_s / nodes_s, kernel/ipnfft.h:160-256, re-thought for a device-resident pipeline).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <mpi.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "window.h"
+
+namespace pnb {
+
+typedef ptrdiff_t INT;
+
+#define PNB_CUDA(call)                                                                            \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      fprintf(stderr, "pnfft-b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__), __FILE__, \
+              __LINE__, cudaGetErrorString(e__));                                                 \
+      abort();                                                                                    \
+    }                                                                                             \
+  } while (0)
+
+#define PNB_CUFFT(call)                                                                           \
+  do {                                                                                            \
+    cufftResult r__ = (call);                                                                     \
+    if (r__ != CUFFT_SUCCESS) {                                                                   \
+      fprintf(stderr, "pnfft-b200: cuFFT error %d at %s:%d\n", (int)r__, __FILE__, __LINE__);     \
+      abort();                                                                                    \
+    }                                                                                             \
+  } while (0)
+
+template <class R> struct Vec2;
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
+
+// ---------------------------------------------------------------------------------------------
+// Block decomposition (reference kernel/ndft-parallel.c:788-822 via PFFT's default blocks:
+// block = ceil(n/P), rank c owns [c*block, min(n,(c+1)*block)), shifted by -n/2).
+// ---------------------------------------------------------------------------------------------
+inline void block_1d(INT n, int p, int c, INT *len, INT *start) {
+  const INT blk = (n + p - 1) / p;
+  INT s = (INT)c * blk;
+  INT l = n - s;
+  if (l > blk) l = blk;
+  if (l <= 0) { l = 0; s = 0; }
+  *len = l;
+  *start = s;
+}
+
+struct Mesh {
+  int np[2] = {1, 1};   // process mesh p0 x p1 over grid dims 0 and 1
+  int co[2] = {0, 0};   // my coordinates
+  int rank = 0, size = 1;
+  int rank_of(int c0, int c1) const { return ((c0 % np[0] + np[0]) % np[0]) * np[1] + ((c1 % np[1] + np[1]) % np[1]); }
+};
+
+// Everything integer about a plan: sizes, local blocks, padded-grid geometry.
+struct Layout {
+  INT N[3], n[3], no[3];
+  int m, cutoff;
+  bool c2r;
+  INT Nc2;                 // stored extent of f_hat's last dim: N[2] or N[2]/2+1
+  INT local_N[3], local_N_start[3];
+  INT local_no[3], local_no_start[3];
+  INT gcb[3], gca[3];      // ghost cells below / above (reference get_size_gcells :1550-1561)
+  INT ngc[3];              // padded extents local_no + gcb + gca (reference local_array_size :1575-1582)
+  INT pitch2;              // row pitch (cells) of the device padded grid, >= ngc[2], 16-byte aligned rows
+  INT o_off[3];            // first kept index of the length-n FFT output (shifted storage): n/2 - no/2
+};
+
+// ---------------------------------------------------------------------------------------------
+// Device-side description handed to the gridding kernels by value
+// ---------------------------------------------------------------------------------------------
+template <class R> struct GridGeom {
+  int m, cutoff;
+  int kind;                // WindowKind
+  int fast_gauss;
+  R n[3];                  // (R) n_t
+  R b[3];
+  int los[3];              // local_no_start
+  int lno[3];              // local_no
+  int ngc[3];              // padded extents
+  long long pitch1;        // = pitch2 (cells per y-row)
+  long long pitch0;        // = ngc[1] * pitch2 (cells per x-plane)
+  const R *exp_const;      // fast Gaussian table [3][cutoff] (device)
+};
+
+
+// ---------------------------------------------------------------------------------------------
+// Strided 3-d box map (see boxcopy.cuh) and the description of the pencil-FFT re-distributions
+// (see fftpipe.cuh)
+// ---------------------------------------------------------------------------------------------
+struct BoxMap {
+  long long dims[3];
+  long long a_off, a_str[3];
+  long long c_off, c_str[3];
+  int parity;   // used by the sign variant: factor (-1)^(i0+i1+i2+parity)
+};
+
+struct Transfer {
+  int peer;
+  long long send_elems = 0, recv_elems = 0;  // complex elements
+  long long send_off = 0, recv_off = 0;      // offsets inside the chunk buffers
+  std::vector<BoxMap> send_maps, recv_maps;  // source array <-> send chunk ; destination array <-> recv chunk
+  bool send_sign = false;
+};
+
+struct Stage {
+  std::vector<Transfer> tr;
+  long long src_elems = 0, dst_elems = 0, send_total = 0, recv_total = 0;
+  long long zero_off = 0, zero_len = 0;      // contiguous gap of the destination array (forward direction)
+  bool zero_all = false;
+};
+
+struct PipeGeom {
+  Stage st[3];
+  long long L1_elems, L3_elems, L4_elems;   // complex elements
+  long long S1, S3;                          // strides of the x / y passes
+  INT z0len, z1len, n2z;                     // n2z: complex row length of L4 (n2 or n2/2+1)
+  long long buf_elems;                       // complex elements each work buffer needs
+};
+
+template <class R> struct Nodes;
+
+template <class R> struct Plan {
+  typedef typename Vec2<R>::type C;
+
+  Layout L;
+  Mesh mesh;
+  MPI_Comm comm = MPI_COMM_NULL;
+  unsigned pnfft_flags = 0, pfft_flags = 0;
+  R x_max[3], sigma[3], b[3];
+  int kind = WIN_KAISER_BESSEL;
+
+  // user-visible f_hat (host or device pointer); owned iff PNFFT_MALLOC_F_HAT
+  C *f_hat = nullptr;
+  bool owns_f_hat = false;
+
+  // device state
+  cudaStream_t stream = nullptr;
+  C *d_f_hat = nullptr;          // staging copy when the user's f_hat is a host pointer
+  R *d_invphi[3] = {nullptr, nullptr, nullptr};  // 1/phi_hat tables incl. the (-1)^k fft-shift sign, [local_N[t]]
+  R *d_invphi_plain[3] = {nullptr, nullptr, nullptr};  // without the sign (for OMIT_FFT paths)
+  R *d_exp_const = nullptr;      // [3][cutoff] for FAST_GAUSSIAN
+  void *d_grid = nullptr;        // padded grid [ngc0][ngc1][pitch2] of C (c2c) or R (c2r)
+  void *d_work[2] = {nullptr, nullptr};  // ping-pong FFT stage buffers
+  size_t work_bytes = 0, grid_bytes = 0;
+  C *d_g1 = nullptr;             // compact FFT-input-side array (local_N block) used with OMIT_* flags / ik
+  C *d_g1_buffer = nullptr;      // ik differentiation buffer
+
+  PipeGeom pipe;
+  // FFT plans
+  cufftHandle fft_x = 0, fft_y = 0, fft_z_fwd = 0, fft_z_bwd = 0;
+  bool fft_ready = false;
+
+  // timers (seconds), reference slots api/pnfft.h:407-418
+  double timer_trafo[10], timer_adj[10];
+  double stage_ms[2][8];
+  long long launches = 0;
+  int kernel_variant = 0;
+
+  cudaEvent_t ev[16];
+
+  // scratch for binning (grown on demand)
+  void *d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+};
+
+template <class R> struct Nodes {
+  typedef typename Vec2<R>::type C;
+  INT local_M = 0;
+  unsigned malloc_flags = 0;
+  R *x = nullptr;
+  R *f = nullptr;          // C[M] (c2c) or R[M] (c2r), user pointer (host or device)
+  R *grad_f = nullptr;     // 3 per node
+  R *hessian_f = nullptr;  // accepted, never computed
+  unsigned precompute_flags = 0;
+
+  // device mirrors (allocated when the user arrays live on the host)
+  R *d_x = nullptr, *d_f = nullptr, *d_grad_f = nullptr;
+  size_t cap_x = 0, cap_f = 0, cap_grad = 0;
+
+  // binning state
+  int *d_tile = nullptr;       // tile id per node
+  int *d_tile_sorted = nullptr;
+  int *d_perm = nullptr;       // sorted position -> node index
+  int *d_idx = nullptr;        // identity
+  int *d_tile_count = nullptr; // [ntiles+1]
+  int *d_tile_start = nullptr; // [ntiles+1]
+  int *d_item = nullptr;       // work items: 3 ints each (tile, begin, end)
+  int *d_nitems = nullptr;
+  size_t cap_nodes = 0, cap_tiles = 0, cap_items = 0;
+  bool binned = false;         // valid for the current x (only kept across calls after precompute_psi)
+  const R *d_x_bound = nullptr; // device x the binning / tables were computed from
+  long long max_items = 0;     // launch bound for the tiled kernels
+
+  // PNFFT_PRE_PSI tables in sorted order (reference kernel/ndft-parallel.c:1184-1240)
+  R *d_pre_psi = nullptr, *d_pre_dpsi = nullptr;
+};
+
+}  // namespace pnb

@@ -1,0 +1,242 @@
+// Window functions of the PNFFT B matrix and their Fourier coefficients (D matrix), written once for
+// host and device.  Formulas restate SURVEY.md Appendix A, i.e. reference
+//   kernel/ndft-parallel.c:1678-1797 (psi per tap), :1850-1953 (dpsi per tap), :2195-2269 (1-d windows),
+//   kernel/matrix_D.c:30-132 (1/phi_hat), kernel/bspline.c:45-91 (cardinal B-spline), kernel/sinc.c:26-53.
+// Everything is expressed in grid units: tap s of a node sits at y_s = floor(n x) - n x - m + s.
+#pragma once
+#include <cmath>
+#include <cfloat>
+
+#if defined(__CUDACC__)
+#define PNB_HD __host__ __device__ __forceinline__
+#else
+#define PNB_HD inline
+#endif
+
+namespace pnb {
+
+enum WindowKind { WIN_KAISER_BESSEL = 0, WIN_GAUSSIAN = 1, WIN_BSPLINE = 2, WIN_SINC_POWER = 3, WIN_BESSEL_I0 = 4 };
+
+constexpr int kMaxM = 16;               // 2m+1 <= 33 taps per axis
+constexpr int kMaxCutoff = 2 * kMaxM + 1;
+
+// math wrappers so that one template body serves float and double
+PNB_HD double m_sqrt(double v) { return sqrt(v); }
+PNB_HD float m_sqrt(float v) { return sqrtf(v); }
+PNB_HD double m_exp(double v) { return exp(v); }
+PNB_HD float m_exp(float v) { return expf(v); }
+PNB_HD double m_sinh(double v) { return sinh(v); }
+PNB_HD float m_sinh(float v) { return sinhf(v); }
+PNB_HD double m_cosh(double v) { return cosh(v); }
+PNB_HD float m_cosh(float v) { return coshf(v); }
+PNB_HD double m_sin(double v) { return sin(v); }
+PNB_HD float m_sin(float v) { return sinf(v); }
+PNB_HD double m_cos(double v) { return cos(v); }
+PNB_HD float m_cos(float v) { return cosf(v); }
+PNB_HD double m_tan(double v) { return tan(v); }
+PNB_HD float m_tan(float v) { return tanf(v); }
+PNB_HD double m_floor(double v) { return floor(v); }
+PNB_HD float m_floor(float v) { return floorf(v); }
+PNB_HD double m_fabs(double v) { return fabs(v); }
+PNB_HD float m_fabs(float v) { return fabsf(v); }
+template <class R> PNB_HD R m_eps();
+template <> PNB_HD double m_eps<double>() { return DBL_EPSILON; }
+template <> PNB_HD float m_eps<float>() { return FLT_EPSILON; }
+
+template <class R> PNB_HD R m_pi() { return (R)3.14159265358979323846; }
+
+// x^(2m) for integer m >= 0 (the reference calls pow(x, 2.0*m); the exponent is always an even integer)
+template <class R> PNB_HD R pow_2m(R x, int m) {
+  R x2 = x * x, r = (R)1;
+  int e = m;
+  while (e) { if (e & 1) r *= x2; x2 *= x2; e >>= 1; }
+  return r;
+}
+
+// sinc with the Taylor branch near 0 (reference kernel/sinc.c:26-53)
+template <class R> PNB_HD R sinc(R x) {
+  const R b = m_eps<R>();
+  const R bs = m_sqrt(b), bs2 = m_sqrt(bs);
+  const R ax = m_fabs(x);
+  if (ax >= bs2) return m_sin(x) / x;
+  R r = (R)1;
+  if (ax >= b) {
+    const R x2 = x * x;
+    r -= x2 / (R)6;
+    if (ax >= bs) r += (x2 * x2) / (R)120;
+  }
+  return r;
+}
+
+// Modified Bessel functions I0, I1 by their (all-positive) power series; the reference forwards to GSL
+// (kernel/bessel_i0.c:375, kernel/bessel_i1.c:570).  Arguments on this path are <= m*b ~ 50.
+template <class R> PNB_HD R bessel_i(int nu, R x) {
+  const double ax = fabs((double)x);
+  if (ax > 60.0) {  // asymptotic expansion, never reached by valid window parameters
+    const double mu = 4.0 * nu * nu;
+    double term = 1.0, sum = 1.0;
+    for (int k = 1; k < 60; k++) {
+      const double t = term * -(mu - (2.0 * k - 1.0) * (2.0 * k - 1.0)) / (8.0 * k * ax);
+      if (fabs(t) >= fabs(term)) break;
+      term = t; sum += term;
+    }
+    const double v = exp(ax) / sqrt(2.0 * 3.14159265358979323846 * ax) * sum;
+    return (R)((nu && x < 0) ? -v : v);
+  }
+  const double q = 0.25 * ax * ax;
+  double term = 1.0, sum = 1.0;
+  for (int k = 1; k < 400; k++) {
+    term *= q / ((double)k * (double)(k + nu));
+    sum += term;
+    if (term < 1e-17 * sum) break;
+  }
+  double v = nu ? 0.5 * ax * sum : sum;
+  if (nu && x < 0) v = -v;
+  return (R)v;
+}
+
+// Cardinal B-spline of order k (degree k-1, support [0,k]) at x -- scalar, O(k^2); the reference's
+// de Boor scheme kernel/bspline.c:45-91 evaluates the same function.
+template <class R> PNB_HD R bspline(int k, R x) {
+  if (!(x > (R)0 && x < (R)k)) return (R)0;
+  if ((R)k - x < x) x = (R)k - x;  // symmetry
+  int r = (int)ceil((double)x) - 1;  // x in (r, r+1]
+  const R v = x - (R)r;              // in (0,1]
+  // a[j] = B_q(v + j), j = 0..q-1
+  R a[2 * kMaxM + 2];
+  for (int j = 0; j <= k; j++) a[j] = (R)0;
+  a[0] = (R)1;
+  for (int q = 2; q <= k; q++) {
+    const R inv = (R)1 / (R)(q - 1);
+    for (int j = q - 1; j >= 0; j--) {
+      const R t = v + (R)j;
+      const R lo = j > 0 ? a[j - 1] : (R)0;
+      a[j] = (t * a[j] + ((R)q - t) * lo) * inv;
+    }
+  }
+  return a[r];
+}
+
+// All 2m+1 taps of the B-spline window of one axis at once.  frac = n x - floor(n x) in [0,1).
+// psi[s] = B_{2m}(s - frac); dpsi[s] = n (B_{2m-1}(s-1-frac) - B_{2m-1}(s-frac))  (= -n B'_{2m}(s-frac))
+// (reference kernel/ndft-parallel.c:1716-1742, :1867-1893)
+template <class R> PNB_HD void bspline_taps(int m, R frac, R n, R *psi, R *dpsi) {
+  const int k = 2 * m;
+  const R v = (R)1 - frac;  // in (0,1]
+  R a[2 * kMaxM + 2];
+  for (int j = 0; j <= k; j++) a[j] = (R)0;
+  a[0] = (R)1;
+  for (int q = 2; q <= k; q++) {
+    if (q == k && dpsi) {
+      // a[j] = B_{k-1}(v + j), j = 0..k-2.  tap s (>=1) sits at s - frac = v + (s-1)
+      dpsi[0] = (R)0;  // B_{k-1}(-1-frac) - B_{k-1}(-frac) = 0
+      for (int s = 1; s <= k; s++) {
+        const R hi = (s - 1 <= k - 2) ? a[s - 1] : (R)0;  // B_{k-1}(s - frac)   = a[s-1]
+        const R lo = (s - 2 >= 0) ? a[s - 2] : (R)0;      // B_{k-1}(s-1-frac)  = a[s-2]
+        dpsi[s] = n * (lo - hi);
+      }
+    }
+    const R inv = (R)1 / (R)(q - 1);
+    for (int j = q - 1; j >= 0; j--) {
+      const R t = v + (R)j;
+      const R lo = j > 0 ? a[j - 1] : (R)0;
+      a[j] = (t * a[j] + ((R)q - t) * lo) * inv;
+    }
+  }
+  psi[0] = (R)0;
+  for (int s = 1; s <= k; s++) psi[s] = a[s - 1];
+  if (k == 1 && dpsi) { dpsi[0] = dpsi[1] = (R)0; }
+}
+
+// One tap of a point-wise window: y = l - n x (grid units), z = -y.  want_d: also the AD gradient weight.
+template <class R> PNB_HD void window_tap(int kind, R y, R n, R b, int m, bool want_d, R *psi_out, R *dpsi_out) {
+  const R pi = m_pi<R>();
+  R psi = (R)0, dpsi = (R)0;
+  const R z = -y;
+  switch (kind) {
+    case WIN_GAUSSIAN: {
+      psi = m_exp(-(y * y) / b) / m_sqrt(pi * b);
+      if (want_d) dpsi = (R)(-2.0) * n / b * z * psi;
+    } break;
+    case WIN_SINC_POWER: {
+      psi = pow_2m(sinc(pi * y / b), m) / b;
+      if (want_d) {
+        const R w = pi * z / b;
+        dpsi = (m_fabs(w) > m_eps<R>()) ? (R)2 * (R)m * pi * n / b * ((R)1 / m_tan(w) - (R)1 / w) * psi : (R)0;
+      }
+    } break;
+    case WIN_BESSEL_I0: {
+      const R d = (R)m * (R)m - y * y;
+      if (d < 0) { psi = (R)0; dpsi = (R)0; }
+      else {
+        const R r = m_sqrt(d);
+        psi = (R)0.5 * bessel_i<R>(0, b * r);
+        if (want_d) dpsi = (d > 0) ? (R)(-0.5) * b * n * z * bessel_i<R>(1, b * r) / r : -((R)0.25 * b * b * n) * z;
+      }
+    } break;
+    default: {  // Kaiser-Bessel
+      const R d = (R)m * (R)m - y * y;
+      const R r = m_sqrt(m_fabs(d));
+      if (d < 0) {
+        psi = m_sin(b * r) / (pi * r);
+        if (want_d) dpsi = n * z / d * (psi - b * m_cos(b * r) / pi);
+      } else if (d > 0) {
+        psi = m_sinh(b * r) / (pi * r);
+        if (want_d) dpsi = n * z / d * (psi - b * m_cosh(b * r) / pi);
+      } else {
+        psi = b / pi;
+        if (want_d) dpsi = -n * (R)m * b * b * b / ((R)3 * pi);
+      }
+    } break;
+  }
+  *psi_out = psi;
+  if (want_d) *dpsi_out = dpsi;
+}
+
+// ---- Fourier coefficients of the window (host only in practice: 3 tables per plan) ----
+template <class R> inline R phi_hat_any(int kind, long k, long n, R b, int m, bool inverse) {
+  const R pi = m_pi<R>();
+  switch (kind) {
+    case WIN_GAUSSIAN: {
+      const R e = (pi * (R)k / (R)n) * (pi * (R)k / (R)n) * b;
+      return inverse ? m_exp(e) : m_exp(-e);
+    }
+    case WIN_BSPLINE: {
+      const R s = sinc<R>((R)k * pi / (R)n);
+      return (R)std::pow((double)s, (inverse ? -2.0 : 2.0) * m);
+    }
+    case WIN_SINC_POWER: {
+      const R d = m_fabs((R)k * b / (R)n);
+      if (inverse) return (d < (R)m) ? (R)1 / bspline<R>(2 * m, d + (R)m) : (R)0;
+      return bspline<R>(2 * m, d + (R)m);
+    }
+    case WIN_BESSEL_I0: {
+      const R t = (R)2 * pi * (R)k / (R)n;
+      const R d = b * b - t * t;
+      const R r = m_sqrt(m_fabs(d));
+      if (d < 0) return inverse ? r / m_sin((R)m * r) : m_sin((R)m * r) / r;
+      if (d > 0) return inverse ? r / m_sinh((R)m * r) : m_sinh((R)m * r) / r;
+      return inverse ? (R)1 / (R)m : (R)m;
+    }
+    default: {
+      const R t = (R)2 * pi * (R)k / (R)n;
+      const R d = b * b - t * t;
+      if (d < 0) return (R)0;
+      if (d > 0) { const R v = bessel_i<R>(0, (R)m * m_sqrt(d)); return inverse ? (R)1 / v : v; }
+      return (R)1;
+    }
+  }
+}
+
+// window shape parameter b (reference kernel/ndft-parallel.c:1013-1064)
+template <class R> inline R window_shape(int kind, int m, R sigma) {
+  const R pi = m_pi<R>();
+  switch (kind) {
+    case WIN_GAUSSIAN: return ((R)m / pi) * (R)2 * sigma / ((R)2 * sigma - (R)1);
+    case WIN_BSPLINE: return (R)0;
+    case WIN_SINC_POWER: return (R)m * ((R)2 * sigma) / ((R)2 * sigma - (R)1);
+    default: return pi * ((R)2 - (R)1 / sigma);
+  }
+}
+
+}  // namespace pnb

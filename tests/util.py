@@ -1,0 +1,71 @@
+"""Shared helpers of the parity tests: seeded inputs and single-rank runs through the C ABI."""
+import numpy as np
+
+from pnfft_b200 import api as A
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).ravel()
+    b = np.asarray(b).ravel()
+    d = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / (d if d > 0 else 1.0))
+
+
+def make_inputs(N, M, seed, c2r=False, single=False, lo=-0.5, up=0.5):
+    rng = np.random.default_rng(seed)
+    rdt = np.float32 if single else np.float64
+    x = rng.uniform(lo, up, (M, 3)).astype(rdt)
+    x = np.clip(x, -0.5, np.nextafter(rdt(0.5), rdt(0)))
+    Nc = (N[0], N[1], N[2] // 2 + 1) if c2r else tuple(N)
+    fh = (rng.uniform(-1, 1, Nc) + 1j * rng.uniform(-1, 1, Nc)).astype(np.complex64 if single else np.complex128)
+    if c2r:
+        f = rng.uniform(-1, 1, M).astype(rdt)
+        g = rng.uniform(-1, 1, (M, 3)).astype(rdt)
+    else:
+        cdt = np.complex64 if single else np.complex128
+        f = (rng.uniform(-1, 1, M) + 1j * rng.uniform(-1, 1, M)).astype(cdt)
+        g = (rng.uniform(-1, 1, (M, 3)) + 1j * rng.uniform(-1, 1, (M, 3))).astype(cdt)
+    return x, fh, f, g
+
+
+class Run1:
+    """One-rank plan + node set with host (numpy) arrays."""
+
+    def __init__(self, N, x, n=None, m=6, flags=0, c2r=False, single=False, x_max=(0.5, 0.5, 0.5), variant=0):
+        self.N = tuple(N)
+        self.n = tuple(n) if n is not None else tuple(2 * v for v in N)
+        self.c2r, self.single, self.m = c2r, single, m
+        self.rdt = np.float32 if single else np.float64
+        self.cdt = np.complex64 if single else np.complex128
+        self.comm = A.create_procmesh_2d(1, 1)
+        self.plan = A.Plan.init_guru(self.N, self.n, x_max, m, flags, self.comm, c2r=c2r, single=single)
+        self.plan.set_kernel_variant(variant)
+        self.M = x.shape[0]
+        self.x = np.ascontiguousarray(x, self.rdt)
+        self.nodes = A.Nodes(self.M, 0, single=single)
+        self.nodes.set_x(self.x)
+        ft = self.rdt if c2r else self.cdt
+        self.f = np.zeros(self.M, ft)
+        self.g = np.zeros((self.M, 3), ft)
+        self.nodes.set_f(self.f)
+        self.nodes.set_grad_f(self.g)
+        Nc = (N[0], N[1], N[2] // 2 + 1) if c2r else self.N
+        self.f_hat = np.zeros(Nc, self.cdt)
+        self.plan.set_f_hat(self.f_hat)
+
+    def trafo(self, f_hat, cf):
+        self.f_hat[...] = f_hat
+        self.plan.trafo(self.nodes, cf)
+        return self.f.copy(), self.g.copy()
+
+    def adj(self, f, g, cf):
+        if f is not None:
+            self.f[...] = f
+        if g is not None:
+            self.g[...] = g
+        self.plan.adj(self.nodes, cf)
+        return self.f_hat.copy()
+
+    def close(self):
+        self.nodes.free(0)
+        self.plan.finalize(0)
