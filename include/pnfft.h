@@ -160,8 +160,10 @@ typedef float pnfftf_complex[2];
   void PNX(b200_sort_nodes)(PNX(plan) ths, PNX(nodes) nodes, ptrdiff_t *keys /* [M] */, ptrdiff_t *perm /* [M] */); \
   /* 3*(2m+1) window values (and derivatives, may be NULL) per node as the kernels evaluate them */ \
   void PNX(b200_window_tensor)(PNX(plan) ths, PNX(nodes) nodes, R *psi /* [M][3][2m+1] */, R *dpsi); \
-  /* select gridding kernels: 0 = tiled shared-memory kernels (default), 1 = generic global-memory kernels */ \
+  /* select kernels: bit 0 = generic global-memory gridding kernels instead of the tiled ones;      \
+   * bit 1 = exact window evaluation instead of the per-tap polynomials fitted at plan time */ \
   void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant);                                    \
+  int PNX(b200_get_poly_degree)(PNX(plan) ths);                                                     \
   /* device time (ms) of the last trafo/adj stages: [0]=B gather/scatter kernel only,              \
    * [1]=binning, [2]=halo, [3]=F, [4]=D, [5]=H2D, [6]=D2H, [7]=whole */                            \
   void PNX(b200_get_stage_ms)(PNX(plan) ths, int adjoint, double *ms8);                             \

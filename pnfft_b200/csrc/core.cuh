@@ -153,6 +153,8 @@ template <class R> struct Core {
     g.pitch1 = p->L.pitch2;
     g.pitch0 = (long long)p->L.ngc[1] * p->L.pitch2;
     g.exp_const = p->d_exp_const;
+    g.poly = (p->use_poly && p->poly_deg >= 0) ? p->d_poly : nullptr;
+    g.poly_deg = p->poly_deg;
     return g;
   }
 
@@ -177,6 +179,73 @@ template <class R> struct Core {
       if (!p->d_exp_const) PNB_CUDA(cudaMalloc(&p->d_exp_const, sizeof(R) * h.size()));
       PNB_CUDA(cudaMemcpy(p->d_exp_const, h.data(), sizeof(R) * h.size(), cudaMemcpyHostToDevice));
     }
+    fit_window_polys(p);
+  }
+
+
+  // Per-tap polynomial form of the window (the kernels' on-the-fly evaluation): tap s of axis t as a function
+  // of frac = n x - floor(n x) in [0,1) is analytic for every supported window, so a Chebyshev interpolant of
+  // modest degree reproduces it to rounding.  Fitted here in double from the exact formulas of window.h, the
+  // degree is raised until the neglected Chebyshev tail is below 2e-17 (double) / 1e-9 (float) of the window
+  // maximum; if degree 24 is not enough the kernels keep the exact evaluation.
+  static void fit_window_polys(P *p) {
+    const Layout &L = p->L;
+    const int c = L.cutoff, nv = 3 * c, m = L.m;
+    const int NP = 48;
+    const double pi = 3.14159265358979323846;
+    std::vector<double> ck((size_t)nv * NP);
+    double vmax = 0;
+    for (int v = 0; v < nv; v++) {
+      const int t = v / c, s = v - t * c;
+      double f[NP];
+      for (int j = 0; j < NP; j++) {
+        const double u = cos(pi * (j + 0.5) / NP), frac = 0.5 * (u + 1.0);
+        double psi, d;
+        window_tap<double>(p->kind, (double)s - (double)m - frac, (double)L.n[t], (double)p->b[t], m, false, &psi, &d);
+        f[j] = psi;
+        vmax = std::max(vmax, fabs(psi));
+      }
+      for (int k = 0; k < NP; k++) {
+        long double acc = 0;
+        for (int j = 0; j < NP; j++) acc += (long double)f[j] * cosl((long double)pi * k * (j + 0.5L) / NP);
+        ck[(size_t)v * NP + k] = (double)(acc * 2.0L / NP * (k == 0 ? 0.5L : 1.0L));
+      }
+    }
+    const double tol = (sizeof(R) == 8 ? 2e-17 : 1e-9) * vmax;
+    int deg = -1;
+    for (int D = 2; D <= kMaxPolyCoef - 1; D++) {
+      double worst = 0;
+      for (int v = 0; v < nv; v++) {
+        double tail = 0;
+        for (int k = D + 1; k < NP - 8; k++) tail += fabs(ck[(size_t)v * NP + k]);
+        worst = std::max(worst, tail);
+      }
+      if (worst <= tol) { deg = D; break; }
+    }
+    p->poly_deg = deg;
+    if (deg < 0) return;
+    // Chebyshev -> monomial coefficients in u
+    std::vector<R> h((size_t)(deg + 1) * nv);
+    std::vector<long double> Tkm1((size_t)deg + 1), Tk((size_t)deg + 1), Tn((size_t)deg + 1), a((size_t)deg + 1);
+    for (int v = 0; v < nv; v++) {
+      std::fill(a.begin(), a.end(), 0.0L);
+      std::fill(Tkm1.begin(), Tkm1.end(), 0.0L);
+      std::fill(Tk.begin(), Tk.end(), 0.0L);
+      Tkm1[0] = 1.0L;                       // T_0
+      if (deg >= 1) Tk[1] = 1.0L;           // T_1
+      a[0] += ck[(size_t)v * NP] * Tkm1[0];
+      if (deg >= 1) a[1] += ck[(size_t)v * NP + 1];
+      for (int k = 2; k <= deg; k++) {
+        std::fill(Tn.begin(), Tn.end(), 0.0L);
+        for (int i = 0; i < deg; i++) Tn[(size_t)i + 1] += 2.0L * Tk[(size_t)i];
+        for (int i = 0; i <= deg; i++) Tn[(size_t)i] -= Tkm1[(size_t)i];
+        for (int i = 0; i <= deg; i++) a[(size_t)i] += (long double)ck[(size_t)v * NP + k] * Tn[(size_t)i];
+        Tkm1 = Tk; Tk = Tn;
+      }
+      for (int k = 0; k <= deg; k++) h[(size_t)k * nv + v] = (R)a[(size_t)k];
+    }
+    if (!p->d_poly) PNB_CUDA(cudaMalloc((void **)&p->d_poly, sizeof(R) * (size_t)kMaxPolyCoef * nv));
+    PNB_CUDA(cudaMemcpy(p->d_poly, h.data(), sizeof(R) * h.size(), cudaMemcpyHostToDevice));
   }
 
   static P *init(const INT *N, const INT *n, const R *x_max, int m, unsigned pnfft_flags, unsigned pfft_flags,
@@ -270,7 +339,7 @@ template <class R> struct Core {
     if (p->fft_z_bwd && p->fft_z_bwd != p->fft_z_fwd) cufftDestroy(p->fft_z_bwd);
     if (p->owns_f_hat && (flags & F_MALLOC_F_HAT) && p->f_hat) cudaFreeHost(p->f_hat);
     cudaFree(p->d_f_hat); cudaFree(p->d_g1); cudaFree(p->d_g1_buffer); cudaFree(p->d_grid);
-    cudaFree(p->d_work[0]); cudaFree(p->d_work[1]); cudaFree(p->d_exp_const); cudaFree(p->d_sort_tmp);
+    cudaFree(p->d_work[0]); cudaFree(p->d_work[1]); cudaFree(p->d_exp_const); cudaFree(p->d_sort_tmp); cudaFree(p->d_poly);
     for (int t = 0; t < 3; t++) cudaFree(p->d_invphi[t]);
     for (int i = 0; i < 16; i++) cudaEventDestroy(p->ev[i]);
     cudaStreamDestroy(p->stream);

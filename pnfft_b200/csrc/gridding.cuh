@@ -75,6 +75,32 @@ __device__ __forceinline__ void warp_window_eval(const GridGeom<R> &g, const R *
   }
 }
 
+// Same 3*(2m+1) values from the per-tap polynomials fitted at plan time (Core::fit_window_polys): tap s of
+// axis t is a smooth function of frac = n x - floor(n x) on [0,1); p(u), u = 2 frac - 1, reproduces it to
+// double rounding, and n * dp/dfrac is the AD-gradient weight (dpsi_s = -n g'(y_s), y_s = s - m - frac).
+// Nodes sitting exactly on a grid line (frac == 0) take the exact path: compactly supported windows jump there.
+template <class R>
+__device__ __forceinline__ void warp_window_eval_poly(const GridGeom<R> &g, const R *poly, const R *nx, const R *fl, int lane,
+                                                      R *psi_s, R *dpsi_s, bool want_d) {
+  const int c = g.cutoff, nv = 3 * c;
+  const R fr[3] = {nx[0] - fl[0], nx[1] - fl[1], nx[2] - fl[2]};
+  if (fr[0] == (R)0 || fr[1] == (R)0 || fr[2] == (R)0) { warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, want_d); return; }
+  for (int v = lane; v < nv; v += 32) {
+    const int t = v / c;
+    const R u = (R)2 * fr[t] - (R)1;
+    const R *a = poly + v;
+    R p = a[g.poly_deg * nv], dp = (R)0;
+    if (want_d) {
+      for (int k = g.poly_deg - 1; k >= 0; k--) { dp = dp * u + p; p = p * u + a[k * nv]; }
+      psi_s[v] = p;
+      dpsi_s[v] = (R)2 * g.n[t] * dp;
+    } else {
+      for (int k = g.poly_deg - 1; k >= 0; k--) p = p * u + a[k * nv];
+      psi_s[v] = p;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // binning
 // ------------------------------------------------------------------------------------------------
@@ -164,7 +190,8 @@ __global__ void k_window_tensor(GridGeom<R> g, const R *__restrict__ x, int M, R
   R xs[3] = {x[3 * (size_t)warp], x[3 * (size_t)warp + 1], x[3 * (size_t)warp + 2]}, nx[3], fl[3];
   int cell[3];
   project_node(g, xs, nx, fl, cell);
-  warp_window_eval(g, nx, fl, lane, psi + (size_t)warp * 3 * g.cutoff, dpsi ? dpsi + (size_t)warp * 3 * g.cutoff : nullptr, dpsi != nullptr);
+  if (g.poly) warp_window_eval_poly(g, g.poly, nx, fl, lane, psi + (size_t)warp * 3 * g.cutoff, dpsi ? dpsi + (size_t)warp * 3 * g.cutoff : nullptr, dpsi != nullptr);
+  else warp_window_eval(g, nx, fl, lane, psi + (size_t)warp * 3 * g.cutoff, dpsi ? dpsi + (size_t)warp * 3 * g.cutoff : nullptr, dpsi != nullptr);
 }
 
 // PNFFT_PRE_PSI tables, stored at the SORTED position p like the reference does (:1222-1240)
@@ -219,7 +246,8 @@ __global__ void __launch_bounds__(256) k_gather_generic(GridGeom<R> g, const R *
       if (want_d) dpsi_s[v] = na.pre_dpsi[(size_t)p * 3 * c + v];
     }
   } else {
-    warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, want_d);
+    if (g.poly) warp_window_eval_poly(g, g.poly, nx, fl, lane, psi_s, dpsi_s, want_d);
+    else warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, want_d);
   }
   __syncwarp();
   R af[2] = {0, 0}, a0[2] = {0, 0}, a1[2] = {0, 0}, a2[2] = {0, 0};
@@ -292,7 +320,8 @@ __global__ void __launch_bounds__(256) k_scatter_generic(GridGeom<R> g, R *__res
       if (want_d) dpsi_s[v] = na.pre_dpsi[(size_t)p * 3 * c + v];
     }
   } else {
-    warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, want_d);
+    if (g.poly) warp_window_eval_poly(g, g.poly, nx, fl, lane, psi_s, dpsi_s, want_d);
+    else warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, want_d);
   }
   __syncwarp();
   constexpr int NC = CPLX ? 2 : 1;
@@ -416,6 +445,7 @@ __device__ __forceinline__ double scale_cell(double w, double v) { return w * v;
 __device__ __forceinline__ float scale_cell(float w, float v) { return w * v; }
 
 constexpr int kGatherWarps = 16;
+constexpr int kMaxPolyCoef = 25;   // polynomial degree <= 24
 
 template <class R, bool CPLX, int M_, bool GRAD>
 __global__ void __launch_bounds__(kGatherWarps * 32, 1)
@@ -430,7 +460,8 @@ k_gather_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeom
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cell *box = reinterpret_cast<Cell *>(smem_raw);
   R *scratch = reinterpret_cast<R *>(smem_raw + Cfg::BOX_BYTES);
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw + Cfg::BOX_BYTES + kGatherWarps * 6 * C * sizeof(R));
+  R *poly_s = scratch + kGatherWarps * 6 * C;
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(poly_s + kMaxPolyCoef * 3 * C);
 
   const int tile = items[3 * blockIdx.x], begin = items[3 * blockIdx.x + 1], end = items[3 * blockIdx.x + 2];
   const int tz = tile % tg.nt[2], ty = (tile / tg.nt[2]) % tg.nt[1], tx = tile / (tg.nt[2] * tg.nt[1]);
@@ -442,6 +473,7 @@ k_gather_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeom
     mbar_expect_tx(bar, (unsigned)Cfg::BOX_BYTES);
     tma_load_3d(box, &tmap, o2 * NCOMP, o1, o0, bar);
   }
+  if (g.poly) for (int i = threadIdx.x; i < (g.poly_deg + 1) * 3 * C; i += kGatherWarps * 32) poly_s[i] = g.poly[i];
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -470,7 +502,8 @@ k_gather_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeom
         if (GRAD) dpsi_s[v] = na.pre_dpsi[(size_t)p * 3 * C + v];
       }
     } else {
-      warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, GRAD);
+      if (g.poly) warp_window_eval_poly(g, poly_s, nx, fl, lane, psi_s, dpsi_s, GRAD);
+      else warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, GRAD);
     }
     __syncwarp();
     if (!waited) { mbar_wait(bar, 0); waited = true; }
@@ -521,7 +554,7 @@ k_gather_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeom
 
 // scatter: C warps, warp w owns the box planes X with X == w (mod C); every node touches exactly one
 // owned plane per warp, so the read-modify-writes of different warps never meet.
-constexpr int kScatterBatch = 32;
+template <int M_> struct ScatterCfg { static constexpr int NB = (M_ <= 6) ? 32 : 16; };
 
 template <class R, bool CPLX, int M_, bool GRAD>
 __global__ void __launch_bounds__((2 * M_ + 1) * 32, 1)
@@ -532,7 +565,7 @@ k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeo
   constexpr int C = Cfg::C, BY = Cfg::BY, BZ = Cfg::BZ, NCH = Cfg::NCH;
   constexpr int NCOMP = CPLX ? 2 : 1;
   constexpr int NT = C * 32;
-  constexpr int NB = kScatterBatch;
+  constexpr int NB = ScatterCfg<M_>::NB;
   constexpr int WPN = GRAD ? 6 * C : 3 * C;   // weights per node
   if ((int)blockIdx.x >= *nitems) return;
 
@@ -541,6 +574,7 @@ k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeo
   R *wts = reinterpret_cast<R *>(smem_raw + Cfg::BOX_BYTES);           // [NB][WPN]
   Cell *vals = reinterpret_cast<Cell *>(wts + NB * WPN);                 // [NB][4]: f, g0, g1, g2
   int *hdr = reinterpret_cast<int *>(vals + NB * 4);                     // [NB][2]: box offset of tap (0,0,0); ux
+  R *poly_s = reinterpret_cast<R *>(hdr + NB * 2);
 
   const int tile = items[3 * blockIdx.x], begin = items[3 * blockIdx.x + 1], end = items[3 * blockIdx.x + 2];
   const int tz = tile % tg.nt[2], ty = (tile / tg.nt[2]) % tg.nt[1], tx = tile / (tg.nt[2] * tg.nt[1]);
@@ -550,6 +584,7 @@ k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeo
   {
     Cell z; zero_cell(z);
     for (int i = threadIdx.x; i < Cfg::BOX_CELLS; i += NT) box[i] = z;
+    if (g.poly) for (int i = threadIdx.x; i < (g.poly_deg + 1) * 3 * C; i += NT) poly_s[i] = g.poly[i];
   }
   int off[NCH], l1s[NCH], l2s[NCH];
 #pragma unroll
@@ -584,7 +619,7 @@ k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeo
         wts[i * WPN + r] = na.pre_psi[(size_t)(b0 + i) * 3 * C + r];
         if (GRAD) wts[i * WPN + 3 * C + r] = na.pre_dpsi[(size_t)(b0 + i) * 3 * C + r];
       }
-    } else if (g.kind == WIN_BSPLINE) {
+    } else if (g.kind == WIN_BSPLINE && !g.poly) {
       for (int v = threadIdx.x; v < nb * 3; v += NT) {
         const int i = v / 3, t = v - i * 3, j = na.perm[b0 + i];
         const R nxv = mul_rn(g.n[t], na.x[3 * (size_t)j + t]);
@@ -597,7 +632,14 @@ k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeo
         const R nxv = mul_rn(g.n[t], na.x[3 * (size_t)j + t]);
         const R flv = m_floor(nxv);
         R psi, dpsi = (R)0;
-        if (g.kind == WIN_GAUSSIAN && g.fast_gauss) {
+        const R fr = nxv - flv;
+        if (g.poly && fr != (R)0) {
+          const R u = (R)2 * fr - (R)1;
+          const R *a = poly_s + r;
+          psi = a[g.poly_deg * 3 * C];
+          for (int k = g.poly_deg - 1; k >= 0; k--) { if (GRAD) dpsi = dpsi * u + psi; psi = psi * u + a[k * 3 * C]; }
+          dpsi *= (R)2 * g.n[t];
+        } else if (g.kind == WIN_GAUSSIAN && g.fast_gauss) {
           const R d = nxv - (flv - (R)M_);
           const R e_sqr = m_exp(-(d * d) / g.b[t]), e_lin = m_exp((R)2 * d / g.b[t]);
           R tmp = e_sqr;
@@ -655,9 +697,12 @@ k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeo
 template <class R, bool CPLX, int M_, bool GRAD> struct TiledSmem {
   typedef typename CellT<R, CPLX>::type Cell;
   typedef TileCfg<M_, (int)sizeof(Cell)> Cfg;
-  static constexpr size_t gather = (size_t)Cfg::BOX_BYTES + (size_t)kGatherWarps * 6 * Cfg::C * sizeof(R) + 16;
-  static constexpr size_t scatter = (size_t)Cfg::BOX_BYTES + (size_t)kScatterBatch * (GRAD ? 6 : 3) * Cfg::C * sizeof(R) +
-                                    (size_t)kScatterBatch * 4 * sizeof(Cell) + (size_t)kScatterBatch * 2 * sizeof(int) + 16;
+  static constexpr size_t poly = (size_t)kMaxPolyCoef * 3 * Cfg::C * sizeof(R);
+  static constexpr size_t gather = (size_t)Cfg::BOX_BYTES + (size_t)kGatherWarps * 6 * Cfg::C * sizeof(R) + poly + 16;
+  static constexpr int NB = ScatterCfg<M_>::NB;
+  static constexpr size_t scatter = (size_t)Cfg::BOX_BYTES + (size_t)NB * (GRAD ? 6 : 3) * Cfg::C * sizeof(R) +
+                                    (size_t)NB * 4 * sizeof(Cell) + (size_t)NB * 2 * sizeof(int) + poly + 16;
+  static_assert(gather <= 232448 && scatter <= 232448, "shared-memory budget of one CTA exceeded");
 };
 
 }  // namespace pnb

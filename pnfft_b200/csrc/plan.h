@@ -90,6 +90,8 @@ template <class R> struct GridGeom {
   long long pitch1;        // = pitch2 (cells per y-row)
   long long pitch0;        // = ngc[1] * pitch2 (cells per x-plane)
   const R *exp_const;      // fast Gaussian table [3][cutoff] (device)
+  const R *poly;           // per-tap window polynomials [deg+1][3*cutoff] in u = 2 frac - 1 (device) or nullptr
+  int poly_deg;
 };
 
 
@@ -149,6 +151,9 @@ template <class R> struct Plan {
   R *d_invphi[3] = {nullptr, nullptr, nullptr};  // 1/phi_hat tables incl. the (-1)^k fft-shift sign, [local_N[t]]
   R *d_invphi_plain[3] = {nullptr, nullptr, nullptr};  // without the sign (for OMIT_FFT paths)
   R *d_exp_const = nullptr;      // [3][cutoff] for FAST_GAUSSIAN
+  R *d_poly = nullptr;           // window polynomials (see GridGeom::poly)
+  int poly_deg = -1;
+  int use_poly = 1;
   void *d_grid = nullptr;        // padded grid [ngc0][ngc1][pitch2] of C (c2c) or R (c2r)
   void *d_work[2] = {nullptr, nullptr};  // ping-pong FFT stage buffers
   size_t work_bytes = 0, grid_bytes = 0;

@@ -165,6 +165,10 @@ template <class R> PNB_HD void window_tap(int kind, R y, R n, R b, int m, bool w
         dpsi = (m_fabs(w) > m_eps<R>()) ? (R)2 * (R)m * pi * n / b * ((R)1 / m_tan(w) - (R)1 / w) * psi : (R)0;
       }
     } break;
+    case WIN_BSPLINE: {
+      psi = bspline<R>(2 * m, y + (R)m);
+      if (want_d) dpsi = n * (bspline<R>(2 * m - 1, y + (R)m - (R)1) - bspline<R>(2 * m - 1, y + (R)m));
+    } break;
     case WIN_BESSEL_I0: {
       const R d = (R)m * (R)m - y * y;
       if (d < 0) { psi = (R)0; dpsi = (R)0; }
