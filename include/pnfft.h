@@ -167,13 +167,21 @@ typedef float pnfftf_complex[2];
   /* device time (ms) of the last trafo/adj stages: [0]=B gather/scatter kernel only,              \
    * [1]=binning, [2]=halo, [3]=F, [4]=D, [5]=H2D, [6]=D2H, [7]=whole */                            \
   void PNX(b200_get_stage_ms)(PNX(plan) ths, int adjoint, double *ms8);                             \
-  long long PNX(b200_kernel_launches)(PNX(plan) ths);
+  /* kernels of this library launched so far / cuFFT, CUB and NCCL calls issued so far */        \
+  long long PNX(b200_kernel_launches)(PNX(plan) ths);                                               \
+  long long PNX(b200_library_calls)(PNX(plan) ths);                                                 \
+  /* the plan's cudaStream_t (all work of trafo/adj is issued on it; calls synchronise it on return) */ \
+  void *PNX(b200_get_stream)(PNX(plan) ths);
 
 #define PNFFT_B200_MANGLE_D(name) pnfft_##name
 #define PNFFT_B200_MANGLE_F(name) pnfftf_##name
 
 PNFFT_B200_API(PNFFT_B200_MANGLE_D, double, pnfft_complex)
 PNFFT_B200_API(PNFFT_B200_MANGLE_F, float, pnfftf_complex)
+
+/* FP64 FMA rate (TFLOP/s) of the current device, measured with independent DFMA chains on all SMs:
+ * the compute denominator of the gridding roofline (bench.py) */
+double pnfft_b200_measure_fp64_tflops(void);
 
 #ifndef PNFFT_PI
 #define PNFFT_PI 3.14159265358979323846

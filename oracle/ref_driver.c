@@ -284,3 +284,22 @@ void DRV(probe_sort)(const DRV(probe_cfg) *P, INT count, const R *x, INT *keys_a
 
 double DRV(bessel_i0)(double x) { return (double)PNX(bessel_i0)((R)x); }
 double DRV(bessel_i1)(double x) { return (double)PNX(bessel_i1)((R)x); }
+
+#if defined(PNFFT_PREC_SINGLE)
+/* The reference's float build still calls the double-mangled pnfft_get_args from
+ * pnfftf_check_init_parameters (api/api-basic.c:844-860, a name-mangling slip); the float oracle
+ * library is linked without the double objects, so the symbol is supplied here. */
+void pnfft_get_args(int argc, char **argv, const char *name, const int neededArgs, const unsigned type, void *parameter)
+{
+  PNX(get_args)(argc, argv, name, neededArgs, type, parameter);
+}
+/* likewise the un-mangled pfft_printf used by api/api-basic.c's parameter printer */
+#include <stdarg.h>
+void pfft_printf(MPI_Comm comm, const char *format, ...)
+{
+  int rank = 0;
+  MPI_Comm_rank(comm, &rank);
+  if (rank) return;
+  va_list ap; va_start(ap, format); vfprintf(stdout, format, ap); va_end(ap);
+}
+#endif

@@ -57,9 +57,17 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("libpnfft_b200.so is missing (%s): build it with `make -C pnfft_b200/csrc`; "
                                "there is no CPU fallback" % LIB_PATH)
-        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib = C.CDLL(LIB_PATH)
         _lib.MPI_Init(None, None)
     return _lib
+
+
+def measure_fp64_tflops():
+    """FP64 FMA rate of the current CUDA device in TFLOP/s (pnfft_b200_measure_fp64_tflops, include/pnfft.h)."""
+    f = lib().pnfft_b200_measure_fp64_tflops
+    f.restype = C.c_double
+    f.argtypes = []
+    return float(f())
 
 
 def _int3(v):
@@ -281,3 +289,10 @@ class Plan:
 
     def kernel_launches(self):
         return int(self.P.fn("b200_kernel_launches", C.c_longlong, [C.c_void_p])(self.h))
+
+    def library_calls(self):
+        return int(self.P.fn("b200_library_calls", C.c_longlong, [C.c_void_p])(self.h))
+
+    def stream(self):
+        """Raw cudaStream_t of the plan (everything trafo/adj launches goes to this stream)."""
+        return int(self.P.fn("b200_get_stream", C.c_void_p, [C.c_void_p])(self.h) or 0)

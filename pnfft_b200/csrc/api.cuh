@@ -372,5 +372,7 @@ void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant) { AS_PLAN(ths)->ke
 int PNX(b200_get_poly_degree)(PNX(plan) ths) { return AS_PLAN(ths)->poly_deg; }
 void PNX(b200_get_stage_ms)(PNX(plan) ths, int adjoint, double *ms8) { for (int i = 0; i < 8; i++) ms8[i] = AS_PLAN(ths)->stage_ms[adjoint ? 1 : 0][i]; }
 long long PNX(b200_kernel_launches)(PNX(plan) ths) { return AS_PLAN(ths)->launches; }
+long long PNX(b200_library_calls)(PNX(plan) ths) { return AS_PLAN(ths)->lib_launches; }
+void *PNX(b200_get_stream)(PNX(plan) ths) { return (void *)AS_PLAN(ths)->stream; }
 
 }  // extern "C"

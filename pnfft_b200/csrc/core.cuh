@@ -356,19 +356,19 @@ template <class R> struct Core {
     cudaStream_t st = p->stream;
     C *W0 = (C *)p->d_work[0], *W1 = (C *)p->d_work[1];
     run_stage_forward<C>(G.st[0], p->mesh, p->d_g1, W0, W1, st, &p->launches);       // L1 in W1
-    if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_FORWARD); p->launches++; }
+    if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_FORWARD); p->lib_launches++; }
     run_stage_forward<C>(G.st[1], p->mesh, W1, W1, W0, st, &p->launches);            // L3 in W0
-    if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_FORWARD); p->launches++; }
+    if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_FORWARD); p->lib_launches++; }
     run_stage_forward<C>(G.st[2], p->mesh, W0, W0, W1, st, &p->launches);            // L4 in W1
     const long long lno0 = L.local_no[0], lno1 = L.local_no[1];
     if (!L.c2r) {
-      if (p->fft_z_fwd) { FftType<R>::exec_c2c(p->fft_z_fwd, W1, CUFFT_FORWARD); p->launches++; }
+      if (p->fft_z_fwd) { FftType<R>::exec_c2c(p->fft_z_fwd, W1, CUFFT_FORWARD); p->lib_launches++; }
       // crop l2 in [o_off2, o_off2+no2) and embed into the padded grid
       BoxMap bm = dense_map(lno0, lno1, L.no[2], L.ngc[1], L.pitch2, L.gcb[0], L.gcb[1], L.gcb[2], L.o_off[2]);
       bm.c_str[0] = lno1 * L.n[2]; bm.c_str[1] = L.n[2];
       box_copy<C>(st, (C *)p->d_grid, W1, bm, BOX_C2A, false, &p->launches);
     } else {
-      if (p->fft_z_fwd) { FftType<R>::exec_c2r(p->fft_z_fwd, W1, (R *)W0); p->launches++; }
+      if (p->fft_z_fwd) { FftType<R>::exec_c2r(p->fft_z_fwd, W1, (R *)W0); p->lib_launches++; }
       BoxMap bm = dense_map(lno0, lno1, L.no[2], L.ngc[1], L.pitch2, L.gcb[0], L.gcb[1], L.gcb[2], L.o_off[2]);
       bm.c_str[0] = lno1 * L.n[2]; bm.c_str[1] = L.n[2];
       box_copy<R>(st, (R *)p->d_grid, (R *)W0, bm, BOX_C2A, false, &p->launches);
@@ -387,22 +387,22 @@ template <class R> struct Core {
       BoxMap bm = dense_map(lno0, lno1, L.no[2], L.ngc[1], L.pitch2, L.gcb[0], L.gcb[1], L.gcb[2], L.o_off[2]);
       bm.c_str[0] = lno1 * L.n[2]; bm.c_str[1] = L.n[2];
       box_copy<C>(st, (C *)p->d_grid, W1, bm, BOX_A2C, false, &p->launches);
-      if (p->fft_z_bwd) { FftType<R>::exec_c2c(p->fft_z_bwd, W1, CUFFT_INVERSE); p->launches++; }
+      if (p->fft_z_bwd) { FftType<R>::exec_c2c(p->fft_z_bwd, W1, CUFFT_INVERSE); p->lib_launches++; }
     } else {
       if (pruned2) PNB_CUDA(cudaMemsetAsync(W0, 0, sizeof(R) * (size_t)(lno0 * lno1 * L.n[2]), st));
       BoxMap bm = dense_map(lno0, lno1, L.no[2], L.ngc[1], L.pitch2, L.gcb[0], L.gcb[1], L.gcb[2], L.o_off[2]);
       bm.c_str[0] = lno1 * L.n[2]; bm.c_str[1] = L.n[2];
       box_copy<R>(st, (R *)p->d_grid, (R *)W0, bm, BOX_A2C, false, &p->launches);
-      if (p->fft_z_bwd) { FftType<R>::exec_r2c(p->fft_z_bwd, (R *)W0, W1); p->launches++; }
+      if (p->fft_z_bwd) { FftType<R>::exec_r2c(p->fft_z_bwd, (R *)W0, W1); p->lib_launches++; }
     }
     // L4 in W1 -> L3 in W0
     if (L.no[1] < L.n[1]) stage_backward_zero(p, G.st[2], W1, W0, W0, G.L3_elems);
     else run_stage_backward<C>(G.st[2], p->mesh, W1, W0, W0, st, &p->launches);
-    if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_INVERSE); p->launches++; }
+    if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_INVERSE); p->lib_launches++; }
     // L3 in W0 -> L1 in W1
     if (L.no[0] < L.n[0]) stage_backward_zero(p, G.st[1], W0, W1, W1, G.L1_elems);
     else run_stage_backward<C>(G.st[1], p->mesh, W0, W1, W1, st, &p->launches);
-    if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_INVERSE); p->launches++; }
+    if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_INVERSE); p->lib_launches++; }
     // L1 in W1 -> g1
     run_stage_backward<C>(G.st[0], p->mesh, W1, W0, p->d_g1, st, &p->launches);
   }
@@ -469,12 +469,12 @@ template <class R> struct Core {
       box_copy<T>(st, grid, sb, slab(0, gcb, n_up), BOX_A2C, false, &p->launches);
     }
     // what arrives: from down: its "to up" message (same size as my n_up); from up: its "to down" message
-    PNB_NCCL(ncclGroupStart());
-    PNB_NCCL(ncclSend(sb, (size_t)n_up * sizeof(T), ncclChar, up, world_nccl(), st));
-    PNB_NCCL(ncclSend(sb + n_up, (size_t)n_dn * sizeof(T), ncclChar, down, world_nccl(), st));
-    PNB_NCCL(ncclRecv(rb, (size_t)n_up * sizeof(T), ncclChar, down, world_nccl(), st));
-    PNB_NCCL(ncclRecv(rb + n_up, (size_t)n_dn * sizeof(T), ncclChar, up, world_nccl(), st));
-    PNB_NCCL(ncclGroupEnd());
+    PNB_NCCL(nccl_api().GroupStart());
+    PNB_NCCL(nccl_api().Send(sb, (size_t)n_up * sizeof(T), ncclChar, up, world_nccl(), st));
+    PNB_NCCL(nccl_api().Send(sb + n_up, (size_t)n_dn * sizeof(T), ncclChar, down, world_nccl(), st));
+    PNB_NCCL(nccl_api().Recv(rb, (size_t)n_up * sizeof(T), ncclChar, down, world_nccl(), st));
+    PNB_NCCL(nccl_api().Recv(rb + n_up, (size_t)n_dn * sizeof(T), ncclChar, up, world_nccl(), st));
+    PNB_NCCL(nccl_api().GroupEnd());
     if (!reduce) {
       box_copy<T>(st, grid, rb, slab(0, gcb, 0), BOX_C2A, false, &p->launches);               // from down: below halo
       box_copy<T>(st, grid, rb, slab(gcb + lno, gca, n_up), BOX_C2A, false, &p->launches);    // from up: above halo
@@ -614,7 +614,8 @@ template <class R> struct Core {
     k_items_per_tile<<<(tg.ntiles + 256) / 256, 256, 0, st>>>(tg, nd->d_tile_count, n_items);
     cub::DeviceScan::ExclusiveSum(p->d_sort_tmp, tmp, n_items, item_start, (int)nt1, st);
     k_fill_items<<<(tg.ntiles + 255) / 256, 256, 0, st>>>(tg, nd->d_tile_count, nd->d_tile_start, item_start, nd->d_item, nd->d_nitems);
-    p->launches += 6;
+    p->launches += 3;       // k_bin_nodes, k_items_per_tile, k_fill_items
+    p->lib_launches += 4;   // cub radix sort + 3 scans
     nd->max_items = (long long)max_items;
   }
 

@@ -24,11 +24,26 @@ namespace pnb {
 
 ncclComm_t world_nccl();  // comm.cu: lazily created NCCL communicator over all ranks
 
+// NCCL is bound at run time (dlopen of libnccl.so.2, comm.cu) the first time a multi-rank plan needs it: the library
+// then shares whatever NCCL the process already loaded (e.g. the one bundled with PyTorch) instead of forcing a
+// second copy into the process, and single-rank users need no NCCL at all.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  const char *(*GetErrorString)(ncclResult_t);
+};
+const NcclApi &nccl_api();
+
 #define PNB_NCCL(call)                                                                             \
   do {                                                                                             \
     ncclResult_t r__ = (call);                                                                     \
     if (r__ != ncclSuccess) {                                                                      \
-      fprintf(stderr, "pnfft-b200: NCCL error %s at %s:%d\n", ncclGetErrorString(r__), __FILE__, __LINE__); \
+      fprintf(stderr, "pnfft-b200: NCCL error %s at %s:%d\n", nccl_api().GetErrorString(r__), __FILE__, __LINE__); \
       abort();                                                                                     \
     }                                                                                              \
   } while (0)
@@ -207,18 +222,18 @@ inline PipeGeom build_pipe(const Layout &L, const Mesh &M) {
 template <class C>
 inline void exchange_chunks(const Stage &S, const Mesh &M, C *from, C *to, bool forward, cudaStream_t st) {
   const bool multi = M.size > 1;
-  if (multi) PNB_NCCL(ncclGroupStart());
+  if (multi) PNB_NCCL(nccl_api().GroupStart());
   for (const auto &T : S.tr) {
     const long long ns = forward ? T.send_elems : T.recv_elems, nr = forward ? T.recv_elems : T.send_elems;
     const long long os = forward ? T.send_off : T.recv_off, orr = forward ? T.recv_off : T.send_off;
     if (T.peer == M.rank) {
       if (ns > 0) PNB_CUDA(cudaMemcpyAsync(to + orr, from + os, sizeof(C) * (size_t)ns, cudaMemcpyDeviceToDevice, st));
     } else {
-      if (ns > 0) PNB_NCCL(ncclSend(from + os, (size_t)ns * sizeof(C), ncclChar, T.peer, world_nccl(), st));
-      if (nr > 0) PNB_NCCL(ncclRecv(to + orr, (size_t)nr * sizeof(C), ncclChar, T.peer, world_nccl(), st));
+      if (ns > 0) PNB_NCCL(nccl_api().Send(from + os, (size_t)ns * sizeof(C), ncclChar, T.peer, world_nccl(), st));
+      if (nr > 0) PNB_NCCL(nccl_api().Recv(to + orr, (size_t)nr * sizeof(C), ncclChar, T.peer, world_nccl(), st));
     }
   }
-  if (multi) PNB_NCCL(ncclGroupEnd());
+  if (multi) PNB_NCCL(nccl_api().GroupEnd());
 }
 
 // forward: src array A -> (pack) bufB -> (exchange) bufA' -> (unpack) dst array.  Caller provides

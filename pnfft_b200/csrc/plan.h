@@ -168,7 +168,8 @@ template <class R> struct Plan {
   // timers (seconds), reference slots api/pnfft.h:407-418
   double timer_trafo[10], timer_adj[10];
   double stage_ms[2][8];
-  long long launches = 0;
+  long long launches = 0;       // kernels of this library launched so far
+  long long lib_launches = 0;   // cuFFT / CUB / NCCL calls issued so far
   int kernel_variant = 0;
 
   cudaEvent_t ev[16];

@@ -1,0 +1,76 @@
+"""CPU tests of the drop-in boundary: libpnfft_b200.so loads without a GPU, exports every entry point that
+include/pnfft.h declares (both precisions), keeps the reference's flag values, and answers the layout queries
+(pure integer / one-division host work, reference api/api-guru.c:84-107) identically to the golden reference output.
+No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pnfft_b200 import api as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "pnfft.h")).read()
+    body = src[src.index("#define PNFFT_B200_API"):src.index("#define PNFFT_B200_MANGLE_D")]
+    names = set(re.findall(r"PNX\((\w+)\)\s*\(", body))
+    names -= {"plan_s", "nodes_s"}
+    plain = set(re.findall(r"^\w[\w\s\*]*?\b(pnfft_b200_\w+)\s*\(", src, flags=re.M))
+    mpi = set(re.findall(r"\b(MPI_\w+)\s*\(", open(os.path.join(ROOT, "include", "mpi.h")).read()))
+    return names, plain, mpi
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = A.lib()
+    names, plain, mpi = declared_symbols()
+    assert len(names) >= 70
+    missing = [p + n for n in sorted(names) for p in ("pnfft_", "pnfftf_") if not hasattr(lib, p + n)]
+    missing += [n for n in sorted(plain | mpi) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_flag_values_match_reference_header():
+    """ABI constants of reference api/pnfft.h:302-418, parsed from include/pnfft.h."""
+    src = open(os.path.join(ROOT, "include", "pnfft.h")).read()
+    want = {"PNFFT_PRE_PHI_HAT": 1 << 0, "PNFFT_FAST_GAUSSIAN": 1 << 1, "PNFFT_FG_PSI": 1 << 1, "PNFFT_MALLOC_F_HAT": 1 << 6,
+            "PNFFT_INTERLACED": 1 << 8, "PNFFT_TRANSPOSED_F_HAT": 1 << 11, "PNFFT_DIFF_AD": 0, "PNFFT_DIFF_IK": 1 << 12,
+            "PNFFT_WINDOW_KAISER_BESSEL": 0, "PNFFT_WINDOW_GAUSSIAN": 1 << 13, "PNFFT_WINDOW_BSPLINE": 1 << 14,
+            "PNFFT_WINDOW_SINC_POWER": 1 << 15, "PNFFT_WINDOW_BESSEL_I0": 1 << 16, "PNFFT_SORT_NODES": 1 << 18,
+            "PNFFT_MALLOC_X": 1, "PNFFT_MALLOC_F": 2, "PNFFT_MALLOC_GRAD_F": 4, "PNFFT_PRE_PSI": 2, "PNFFT_PRE_GRAD_PSI": 4,
+            "PNFFT_COMPUTE_F": 1, "PNFFT_COMPUTE_GRAD_F": 2, "PNFFT_COMPUTE_ACCUMULATED": 16, "PNFFT_OMIT_DECONV": 32,
+            "PNFFT_OMIT_FFT": 64, "PNFFT_OMIT_CONV": 128, "PNFFT_TIMER_LENGTH": 10}
+    for name, val in want.items():
+        mm = re.search(r"#define\s+%s\s+\(?\s*([^\n]+?)\s*\)?\s*(/\*.*)?$" % name, src, flags=re.M)
+        assert mm, name
+        expr = re.sub(r"(\d)[uU]\b", r"\1", mm.group(1)).strip()
+        assert eval(expr, {"__builtins__": {}}, {k: v for k, v in want.items()}) == val, (name, expr)
+
+
+def test_single_rank_layout_matches_golden_reference():
+    L = np.load(os.path.join(GOLD, "layouts.npz"))
+    comm = A.create_procmesh_2d(1, 1)
+    for key in sorted(k[:-4] for k in L.files if k.endswith("_1x1_c2c_cfg") or k.endswith("_1x1_c2r_cfg")):
+        cfg = L[key + "_cfg"]
+        N, n, m, c2r = tuple(cfg[0:3]), tuple(cfg[3:6]), int(cfg[6]), bool(cfg[7])
+        lN, lNs, lo, up = A.local_size_guru(N, n, tuple(L[key + "_xmax"]), m, comm, c2r=c2r)
+        assert np.array_equal(lN, L[key + "_local_N"][0]) and np.array_equal(lNs, L[key + "_local_N_start"][0])
+        assert np.array_equal(lo, L[key + "_lo"][0]) and np.array_equal(up, L[key + "_up"][0])
+
+
+def test_procmesh_mismatch_is_reported():
+    with pytest.raises(ValueError):
+        A.create_procmesh_2d(2, 2)      # one rank only: reference util/util.c returns non-zero
+
+
+def test_missing_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    comm = A.create_procmesh_2d(1, 1)
+    with pytest.raises(RuntimeError):
+        A.Plan.init_guru((16, 16, 16), (32, 32, 32), (0.5,) * 3, 6, 0, comm)   # NULL + message, never a CPU fallback

@@ -1,0 +1,104 @@
+"""CPU tests of the checker itself: the clean-room restatement (oracle/pnfft_oracle.c) and, where it was built, the
+compiled reference (oracle/_ref) against the golden vectors of tests/golden/ (generated from the unmodified reference
+by tools/make_golden.py).  Tolerances: values 1e-13 (double) / 1e-5 (float) rel-l2; integer outputs identical."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import checker, refdrv
+from tests.util import rel_l2
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "t_*.npz")))
+
+
+def _impls(single):
+    out = [("port", checker.port(single))]
+    if refdrv.available(single):
+        out.append(("reference", refdrv.get(single)))
+    return out
+
+
+def test_golden_present():
+    assert len(CASES) >= 40
+    assert os.path.exists(os.path.join(GOLD, "layouts.npz")) and os.path.exists(os.path.join(GOLD, "node_index.npz"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_transform_golden(case):
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    single, c2r = bool(g["single"]), bool(g["c2r"])
+    tol = 1e-5 if single else 1e-13
+    N, m, flags = tuple(int(v) for v in g["N"]), int(g["m"]), int(g["flags"])
+    for name, impl in _impls(single):
+        t = impl.trafo(N, g["x"], g["f_hat"], m=m, pnfft_flags=flags, compute_flags=3, c2r=c2r)
+        a = impl.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], m=m, pnfft_flags=flags, compute_flags=3, c2r=c2r)
+        assert rel_l2(t["f"], g["out_f"]) <= tol, name
+        # float sinc-power gradient: cot(w) - 1/w cancels catastrophically near w = 0 (reference :1897-1917), the
+        # float reference itself is only good to ~1e-4 there
+        gtol = 1e-4 if (single and "sinc_power" in case) else tol
+        assert rel_l2(t["grad_f"], g["out_grad_f"]) <= gtol, name
+        assert rel_l2(a["f_hat"], g["out_f_hat"]) <= gtol, name   # the adjoint spreads grad_f with the same dpsi
+        psi, dpsi = impl.probe_tensor(g["x"][:16], N, m=m, pnfft_flags=flags)
+        assert np.abs(psi - g["psi"]).max() <= tol * max(1.0, np.abs(g["psi"]).max()), name
+        assert np.abs(dpsi - g["dpsi"]).max() <= 10 * gtol * max(1.0, np.abs(g["dpsi"]).max()), name
+
+
+def test_layout_golden():
+    """Block decomposition, pruned FFT output size and node borders over 1x1 .. 2x4 meshes, even / ragged / truncated-torus
+    sizes: integers identical, borders bit-identical (reference kernel/ndft-parallel.c:734-822, api/api-guru.c:195-220)."""
+    L = np.load(os.path.join(GOLD, "layouts.npz"))
+    keys = sorted(k[:-4] for k in L.files if k.endswith("_cfg"))
+    assert len(keys) == 24
+    for key in keys:
+        cfg = L[key + "_cfg"]
+        N, n, m, c2r, mesh = tuple(cfg[0:3]), tuple(cfg[3:6]), int(cfg[6]), bool(cfg[7]), (int(cfg[8]), int(cfg[9]))
+        for name, impl in _impls(False):
+            r = impl.layout(N, n, m=m, np_mesh=mesh, x_max=tuple(L[key + "_xmax"]), c2r=c2r)
+            for k in ("local_N", "local_N_start", "local_no", "local_no_start"):
+                assert np.array_equal(r[k], L[key + "_" + k]), (name, key, k)
+            assert tuple(r["no"]) == tuple(L[key + "_no"]), (name, key)
+            assert np.array_equal(r["lo"], L[key + "_lo"]) and np.array_equal(r["up"], L[key + "_up"]), (name, key)
+
+
+def test_node_index_golden():
+    """node -> rank ownership, local grid index u_j and plain index m0, and the sort key: bit-exact."""
+    g = np.load(os.path.join(GOLD, "node_index.npz"))
+    N, m, x = tuple(int(v) for v in g["N"]), int(g["m"]), g["x"]
+    po = checker.port(False)
+    for mesh in [(1, 1), (2, 2), (2, 4)]:
+        owner, idx = po.node_index(x, N, m=m, np_mesh=mesh)
+        assert np.array_equal(owner, g["owner_%dx%d" % mesh])
+        assert np.array_equal(idx, g["index_%dx%d" % mesh])
+    keys = po.probe_sort_keys(x, N, m=m)
+    assert np.array_equal(np.sort(keys, kind="stable"), g["sort_keys"])
+    assert np.array_equal(np.argsort(keys, kind="stable"), g["sort_perm"])   # stable LSD radix == stable argsort
+
+
+def test_port_matches_reference_on_new_inputs():
+    """Beyond the fixtures: fresh seeded inputs, when the compiled reference is available in this container."""
+    if not refdrv.available(False):
+        pytest.skip("oracle/_ref not built here")
+    from tests.util import make_inputs
+    ref, po = refdrv.get(False), checker.port(False)
+    N = (12, 16, 8)
+    for c2r in (False, True):
+        x, fh, f, g = make_inputs(N, 150, 11, c2r=c2r)
+        for flags in (0, 1 << 14, (1 << 13) | 2):
+            rt = ref.trafo(N, x, fh, pnfft_flags=flags, compute_flags=3, c2r=c2r, m=4)
+            pt = po.trafo(N, x, fh, pnfft_flags=flags, compute_flags=3, c2r=c2r, m=4)
+            assert rel_l2(pt["f"], rt["f"]) <= 1e-13 and rel_l2(pt["grad_f"], rt["grad_f"]) <= 1e-13
+
+
+def test_adjointness():
+    """<A f_hat, f> == <f_hat, A^H f>: a size-independent property of the trafo/adj pair (no oracle needed)."""
+    from tests.util import make_inputs
+    po = checker.port(False)
+    N = (8, 8, 8)
+    x, fh, f, _ = make_inputs(N, 100, 5)
+    t = po.trafo(N, x, fh, compute_flags=1, m=4)["f"]
+    a = po.adj(N, x, f=f, compute_flags=1, m=4)["f_hat"]
+    lhs, rhs = np.vdot(f, t), np.vdot(a, fh)
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
