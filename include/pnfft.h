@@ -160,8 +160,9 @@ typedef float pnfftf_complex[2];
   void PNX(b200_sort_nodes)(PNX(plan) ths, PNX(nodes) nodes, ptrdiff_t *keys /* [M] */, ptrdiff_t *perm /* [M] */); \
   /* 3*(2m+1) window values (and derivatives, may be NULL) per node as the kernels evaluate them */ \
   void PNX(b200_window_tensor)(PNX(plan) ths, PNX(nodes) nodes, R *psi /* [M][3][2m+1] */, R *dpsi); \
-  /* select kernels: bit 0 = generic global-memory gridding kernels instead of the tiled ones;      \
-   * bit 1 = exact window evaluation instead of the per-tap polynomials fitted at plan time */ \
+  /* select kernels (default 0 = z-marching register kernels): bit 0 = generic global-memory gridding  \
+   * kernels; bit 1 = exact window evaluation instead of the per-tap polynomials fitted at plan time; \
+   * bit 2 = shared-memory tile kernels (first implementation, kept for comparison) */                \
   void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant);                                    \
   int PNX(b200_get_poly_degree)(PNX(plan) ths);                                                     \
   /* device time (ms) of the last trafo/adj stages: [0]=B gather/scatter kernel only,              \

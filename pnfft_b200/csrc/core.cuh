@@ -6,7 +6,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "gridding.cuh"
+#include "zmarch.cuh"
 #include "gridops.cuh"
 
 namespace pnb {
@@ -551,16 +551,25 @@ template <class R> struct Core {
     return *mirror;
   }
 
+  // kernel families: 0 = z-marching register kernels (default), 1 = generic global-memory kernels,
+  // 4 = shared-memory tile kernels (the first implementation, kept for comparison)
+  static int kernel_family(const P *p) {
+    const int m = p->L.m;
+    const bool fits = (m == 4 || m == 6 || m == 8);
+    if (p->kernel_variant == 1 || !fits) return 1;
+    return p->kernel_variant == 4 ? 4 : 0;
+  }
   static TileGeom tile_geom(const P *p, bool *tiled_ok) {
     TileGeom tg;
     const int m = p->L.m;
-    bool ok = (p->kernel_variant == 0) && (m == 4 || m == 6 || m == 8);
-    tg.T[0] = (m <= 6) ? 8 : 6; tg.T[1] = tg.T[0]; tg.T[2] = (m <= 6) ? 16 : 8;
+    const int fam = kernel_family(p);
+    if (fam == 0) { tg.T[0] = (m <= 6) ? 16 : 8; tg.T[1] = 4; tg.T[2] = (m <= 6) ? 8 : 4; }   // == ZmCfg<m>::T0, T1, ZS
+    else { tg.T[0] = (m <= 6) ? 8 : 6; tg.T[1] = tg.T[0]; tg.T[2] = (m <= 6) ? 16 : 8; }
     for (int t = 0; t < 3; t++) tg.nt[t] = (int)((p->L.local_no[t] + tg.T[t] - 1) / tg.T[t]);
     for (int t = 0; t < 3; t++) if (tg.nt[t] < 1) tg.nt[t] = 1;
     tg.ntiles = tg.nt[0] * tg.nt[1] * tg.nt[2];
     tg.chunk = 512;
-    if (tiled_ok) *tiled_ok = ok;
+    if (tiled_ok) *tiled_ok = fam != 1;
     return tg;
   }
 
@@ -611,16 +620,45 @@ template <class R> struct Core {
     cub::DeviceRadixSort::SortPairs(p->d_sort_tmp, tmp, nd->d_tile, nd->d_tile_sorted, nd->d_idx, nd->d_perm, M, 0, bits, st);
     int *n_items = nd->d_tile_count + nt1, *item_start = nd->d_tile_start + nt1;
     cub::DeviceScan::ExclusiveSum(p->d_sort_tmp, tmp, nd->d_tile_count, nd->d_tile_start, (int)nt1, st);
-    k_items_per_tile<<<(tg.ntiles + 256) / 256, 256, 0, st>>>(tg, nd->d_tile_count, n_items);
-    cub::DeviceScan::ExclusiveSum(p->d_sort_tmp, tmp, n_items, item_start, (int)nt1, st);
-    k_fill_items<<<(tg.ntiles + 255) / 256, 256, 0, st>>>(tg, nd->d_tile_count, nd->d_tile_start, item_start, nd->d_item, nd->d_nitems);
-    p->launches += 3;       // k_bin_nodes, k_items_per_tile, k_fill_items
-    p->lib_launches += 4;   // cub radix sort + 3 scans
+    p->launches += 1;       // k_bin_nodes
+    p->lib_launches += 2;   // cub radix sort + scan
+    if (kernel_family(p) == 4) {   // (tile, node-chunk) work items of the shared-memory tile kernels
+      k_items_per_tile<<<(tg.ntiles + 256) / 256, 256, 0, st>>>(tg, nd->d_tile_count, n_items);
+      cub::DeviceScan::ExclusiveSum(p->d_sort_tmp, tmp, n_items, item_start, (int)nt1, st);
+      k_fill_items<<<(tg.ntiles + 255) / 256, 256, 0, st>>>(tg, nd->d_tile_count, nd->d_tile_start, item_start, nd->d_item, nd->d_nitems);
+      p->launches += 2;
+      p->lib_launches += 1;
+    }
     nd->max_items = (long long)max_items;
   }
 
   template <bool CPLX, int M_, bool GRAD>
+  static void launch_zm(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
+    typedef ZmCfg<M_> Cfg;
+    typedef ZmSmem<R, CPLX, M_, GRAD> Sm;
+    const TileGeom tg = tile_geom(p, nullptr);
+    const GridGeom<R> g = geom(p);
+    const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::R0, Cfg::R1, Cfg::ZB);
+    ZmGeom zg;
+    zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2];
+    zg.nseg = (tg.nt[2] + Cfg::ZSEG - 1) / Cfg::ZSEG;
+    const unsigned nblk = (unsigned)(tg.nt[0] * tg.nt[1] * zg.nseg);
+    if (!scatter) {
+      auto kern = k_gather_zm<R, CPLX, M_, GRAD>;
+      PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
+      kern<<<nblk, Cfg::NT, Sm::gather, p->stream>>>(tm, g, zg, na, nd->d_tile_start);
+    } else {
+      auto kern = k_scatter_zm<R, CPLX, M_, GRAD>;
+      PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
+      kern<<<nblk, Cfg::NT, Sm::scatter, p->stream>>>(tm, g, zg, na, nd->d_tile_start);
+    }
+    PNB_CUDA(cudaGetLastError());
+    p->launches++;
+  }
+
+  template <bool CPLX, int M_, bool GRAD>
   static void launch_tiled(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
+    if (kernel_family(p) == 0) { launch_zm<CPLX, M_, GRAD>(p, nd, na, scatter); return; }
     typedef typename CellT<R, CPLX>::type Cell;
     typedef TileCfg<M_, (int)sizeof(Cell)> Cfg;
     typedef TiledSmem<R, CPLX, M_, GRAD> Sm;
