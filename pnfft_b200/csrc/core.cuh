@@ -531,7 +531,7 @@ template <class R> struct Core {
     cudaFree(nd->d_x); cudaFree(nd->d_f); cudaFree(nd->d_grad_f);
     cudaFree(nd->d_tile); cudaFree(nd->d_tile_sorted); cudaFree(nd->d_perm); cudaFree(nd->d_idx);
     cudaFree(nd->d_tile_count); cudaFree(nd->d_tile_start); cudaFree(nd->d_item); cudaFree(nd->d_nitems);
-    cudaFree(nd->d_pre_psi); cudaFree(nd->d_pre_dpsi);
+    cudaFree(nd->d_pre_psi); cudaFree(nd->d_pre_dpsi); cudaFree(nd->d_wtab);
     delete nd;
   }
 
@@ -635,6 +635,7 @@ template <class R> struct Core {
   template <bool CPLX, int M_, bool GRAD>
   static void launch_zm(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
     typedef ZmCfg<M_> Cfg;
+    typedef ZmTab<R, M_, GRAD> Tab;
     typedef ZmSmem<R, CPLX, M_, GRAD> Sm;
     const TileGeom tg = tile_geom(p, nullptr);
     const GridGeom<R> g = geom(p);
@@ -643,14 +644,27 @@ template <class R> struct Core {
     zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2];
     zg.nseg = (tg.nt[2] + Cfg::ZSEG - 1) / Cfg::ZSEG;
     const unsigned nblk = (unsigned)(tg.nt[0] * tg.nt[1] * zg.nseg);
+    // 1. node table: window factors evaluated once per node and axis (+ f / grad_f for the adjoint), sorted order
+    const size_t need = (size_t)na.M * Tab::ROWLEN + 64;
+    ensure(&nd->d_wtab, &nd->cap_wtab, need);
+    {
+      auto kt = k_node_table<R, M_, GRAD>;
+      const long long nthr = 3LL * na.M;
+      const size_t psm = g.poly ? sizeof(R) * (size_t)(g.poly_deg + 1) * 3 * Cfg::C : 0;
+      kt<<<(unsigned)((nthr + 191) / 192), 192, psm, p->stream>>>(g, na, CPLX ? 2 : 1, scatter ? 1 : 0, nd->d_wtab);
+      p->launches++;
+    }
+    // 2. gridding
     if (!scatter) {
+      GatherOut<R> out;
+      out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
       auto kern = k_gather_zm<R, CPLX, M_, GRAD>;
       PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
-      kern<<<nblk, Cfg::NT, Sm::gather, p->stream>>>(tm, g, zg, na, nd->d_tile_start);
+      kern<<<nblk, Cfg::NT, Sm::gather, p->stream>>>(tm, zg, nd->d_wtab, nd->d_tile_start, out);
     } else {
       auto kern = k_scatter_zm<R, CPLX, M_, GRAD>;
       PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
-      kern<<<nblk, Cfg::NT, Sm::scatter, p->stream>>>(tm, g, zg, na, nd->d_tile_start);
+      kern<<<nblk, Cfg::NT, Sm::scatter, p->stream>>>(tm, zg, nd->d_wtab, nd->d_tile_start);
     }
     PNB_CUDA(cudaGetLastError());
     p->launches++;

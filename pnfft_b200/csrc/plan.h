@@ -209,6 +209,10 @@ template <class R> struct Nodes {
 
   // PNFFT_PRE_PSI tables in sorted order (reference kernel/ndft-parallel.c:1184-1240)
   R *d_pre_psi = nullptr, *d_pre_dpsi = nullptr;
+
+  // per-call node table of the z-marching kernels (zmarch.cuh: ZmTab), grown on demand
+  R *d_wtab = nullptr;
+  size_t cap_wtab = 0;
 };
 
 }  // namespace pnb
