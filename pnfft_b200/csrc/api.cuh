@@ -367,8 +367,9 @@ void PNX(b200_window_tensor)(PNX(plan) ths, PNX(nodes) nodes, RT *psi, RT *dpsi)
   cudaFree(d_psi); cudaFree(d_dpsi);
 }
 
-// variant bit 0: generic global-memory kernels; bit 1: exact window evaluation instead of the fitted polynomials
-void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant) { AS_PLAN(ths)->kernel_variant = variant & 5; AS_PLAN(ths)->use_poly = (variant & 2) ? 0 : 1; }
+// variant bit 0: generic global-memory kernels; bit 1: exact window evaluation instead of the fitted polynomials;
+// 4: shared-memory tile kernels; 8: z-march v1 (CTA-synchronous) instead of the warp-autonomous v2
+void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant) { AS_PLAN(ths)->kernel_variant = variant & 13; AS_PLAN(ths)->use_poly = (variant & 2) ? 0 : 1; }
 int PNX(b200_get_poly_degree)(PNX(plan) ths) { return AS_PLAN(ths)->poly_deg; }
 void PNX(b200_get_stage_ms)(PNX(plan) ths, int adjoint, double *ms8) { for (int i = 0; i < 8; i++) ms8[i] = AS_PLAN(ths)->stage_ms[adjoint ? 1 : 0][i]; }
 long long PNX(b200_kernel_launches)(PNX(plan) ths) { return AS_PLAN(ths)->launches; }

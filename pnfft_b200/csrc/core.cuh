@@ -6,7 +6,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "zmarch.cuh"
+#include "zmarch2.cuh"
 #include "gridops.cuh"
 
 namespace pnb {
@@ -551,25 +551,32 @@ template <class R> struct Core {
     return *mirror;
   }
 
-  // kernel families: 0 = z-marching register kernels (default), 1 = generic global-memory kernels,
+  // kernel families: 2 = warp-autonomous z-marching register kernels (default for m = 4, 6), 0 = z-marching v1
+  // (CTA-synchronous; default for m = 8, variant 8 forces it), 1 = generic global-memory kernels,
   // 4 = shared-memory tile kernels (the first implementation, kept for comparison)
   static int kernel_family(const P *p) {
     const int m = p->L.m;
     const bool fits = (m == 4 || m == 6 || m == 8);
-    if (p->kernel_variant == 1 || !fits) return 1;
-    return p->kernel_variant == 4 ? 4 : 0;
+    const int kv = p->kernel_variant & 13;
+    if (kv == 1 || !fits) return 1;
+    if (kv == 4) return 4;
+    if (kv == 8 || m == 8) return 0;
+    return 2;
   }
   static TileGeom tile_geom(const P *p, bool *tiled_ok) {
     TileGeom tg;
     const int m = p->L.m;
     const int fam = kernel_family(p);
-    if (fam == 0) { tg.T[0] = (m <= 6) ? 16 : 8; tg.T[1] = 4; tg.T[2] = (m <= 6) ? 8 : 4; }   // == ZmCfg<m>::T0, T1, ZS
+    tg.sub = 1;
+    if (fam == 2) { tg.T[0] = Zm2Cfg<6>::T0; tg.T[1] = 16 - 2 * m; tg.T[2] = Zm2Cfg<6>::ZS; tg.sub = Zm2Cfg<6>::SUB; }   // == Zm2Cfg<m>::T0, T1, ZS
+    else if (fam == 0) { tg.T[0] = (m <= 6) ? 16 : 8; tg.T[1] = 4; tg.T[2] = (m <= 6) ? 8 : 4; }   // == ZmCfg<m>::T0, T1, ZS
     else { tg.T[0] = (m <= 6) ? 8 : 6; tg.T[1] = tg.T[0]; tg.T[2] = (m <= 6) ? 16 : 8; }
     for (int t = 0; t < 3; t++) tg.nt[t] = (int)((p->L.local_no[t] + tg.T[t] - 1) / tg.T[t]);
     for (int t = 0; t < 3; t++) if (tg.nt[t] < 1) tg.nt[t] = 1;
     tg.ntiles = tg.nt[0] * tg.nt[1] * tg.nt[2];
     tg.chunk = 512;
     if (tiled_ok) *tiled_ok = fam != 1;
+    tg.family = fam;
     return tg;
   }
 
@@ -586,7 +593,7 @@ template <class R> struct Core {
       PNB_CUDA(cudaMalloc((void **)&nd->d_idx, sizeof(int) * c));
       nd->cap_nodes = c;
     }
-    const size_t nt1 = (size_t)tg.ntiles + 2;
+    const size_t nt1 = (size_t)tg.ntiles * tg.sub + 2;
     if (nd->cap_tiles < nt1) {
       cudaFree(nd->d_tile_count); cudaFree(nd->d_tile_start);
       PNB_CUDA(cudaMalloc((void **)&nd->d_tile_count, sizeof(int) * 2 * nt1));   // counts | items per tile
@@ -606,7 +613,7 @@ template <class R> struct Core {
     const GridGeom<R> g = geom(p);
     k_bin_nodes<R><<<(M + 255) / 256, 256, 0, st>>>(g, tg, d_x, M, nd->d_tile, nd->d_idx, nd->d_tile_count);
     int bits = 1;
-    while ((1LL << bits) <= tg.ntiles) bits++;
+    while ((1LL << bits) <= (long long)tg.ntiles * tg.sub) bits++;
     size_t tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, nd->d_tile, nd->d_tile_sorted, nd->d_idx, nd->d_perm, M, 0, bits, st);
     size_t tmp2 = 0;
@@ -670,8 +677,57 @@ template <class R> struct Core {
     p->launches++;
   }
 
+  // z-march v2 (zmarch2.cuh): coalesced node table, then the warp-autonomous gather / scatter
+  template <bool CPLX, int M_, bool GRAD>
+  static void launch_zm2(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
+    if constexpr (M_ == 4 || M_ == 6) {
+      typedef Zm2Cfg<M_> Cfg;
+      typedef Zm2Smem<R, CPLX, M_, GRAD> Sm;
+      const TileGeom tg = tile_geom(p, nullptr);
+      const GridGeom<R> g = geom(p);
+      const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, 2, 16, Cfg::ZB);
+      Zm2Geom zg;
+      zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2];
+      // whole columns per work item when there are enough columns to fill the GPU, else split along z
+      const int ncol = tg.nt[0] * tg.nt[1];
+      int nseg = 1;
+      while (ncol * nseg < 8 * 148 && nseg * 2 <= tg.nt[2]) nseg *= 2;
+      zg.zseg = (tg.nt[2] + nseg - 1) / nseg;
+      zg.nseg = (tg.nt[2] + zg.zseg - 1) / zg.zseg;
+      const unsigned nblk = (unsigned)(ncol * zg.nseg);
+      const size_t psm = g.poly ? sizeof(R) * (size_t)(g.poly_deg + 1) * 3 * Cfg::C : 0;
+      const unsigned ntb = (unsigned)((na.M + kZm2TabNodes - 1) / kZm2TabNodes);
+      if (!scatter) {
+        typedef typename Sm::RowG Row;
+        ensure(&nd->d_wtab, &nd->cap_wtab, (size_t)na.M * Row::ROWLEN + 64);
+        auto kt = k_node_table2<R, M_, GRAD, false, CPLX>;
+        const size_t tsm = (size_t)kZm2TabNodes * Row::ROWBYTES + psm;
+        PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, na, nd->d_wtab);
+        GatherOut<R> out;
+        out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
+        auto kern = k_gather_zm2<R, CPLX, M_, GRAD>;
+        PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
+        kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, nd->d_wtab, nd->d_tile_start, out);
+      } else {
+        typedef typename Sm::RowS Row;
+        ensure(&nd->d_wtab, &nd->cap_wtab, (size_t)na.M * Row::ROWLEN + 64);
+        auto kt = k_node_table2<R, M_, GRAD, true, CPLX>;
+        const size_t tsm = (size_t)kZm2TabNodes * Row::ROWBYTES + psm;
+        PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, na, nd->d_wtab);
+        auto kern = k_scatter_zm2<R, CPLX, M_, GRAD>;
+        PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
+        kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::scatter, p->stream>>>(tm, zg, nd->d_wtab, nd->d_tile_start);
+      }
+      PNB_CUDA(cudaGetLastError());
+      p->launches += 2;
+    }
+  }
+
   template <bool CPLX, int M_, bool GRAD>
   static void launch_tiled(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
+    if (kernel_family(p) == 2) { launch_zm2<CPLX, M_, GRAD>(p, nd, na, scatter); return; }
     if (kernel_family(p) == 0) { launch_zm<CPLX, M_, GRAD>(p, nd, na, scatter); return; }
     typedef typename CellT<R, CPLX>::type Cell;
     typedef TileCfg<M_, (int)sizeof(Cell)> Cfg;

@@ -109,6 +109,8 @@ struct TileGeom {
   int nt[3];       // tiles per axis
   int ntiles;
   int chunk;       // max nodes per work item
+  int family;      // kernel family the geometry was made for (Core::kernel_family)
+  int sub;         // bins per tile: 1, or T[0] when nodes are also ordered by their x offset inside the tile (z-march v2)
 };
 
 template <class R>
@@ -119,9 +121,12 @@ __global__ void k_bin_nodes(GridGeom<R> g, TileGeom tg, const R *__restrict__ x,
   R xs[3] = {x[3 * (size_t)j], x[3 * (size_t)j + 1], x[3 * (size_t)j + 2]}, nx[3], fl[3];
   int cell[3];
   project_node(g, xs, nx, fl, cell);
-  int tile = tg.ntiles;  // nodes outside the rank's block (undefined behaviour in the reference) are skipped
-  if (cell[0] >= 0 && cell[0] < g.lno[0] && cell[1] >= 0 && cell[1] < g.lno[1] && cell[2] >= 0 && cell[2] < g.lno[2])
-    tile = ((cell[0] / tg.T[0]) * tg.nt[1] + cell[1] / tg.T[1]) * tg.nt[2] + cell[2] / tg.T[2];
+  int tile = tg.ntiles * tg.sub;  // nodes outside the rank's block (undefined behaviour in the reference) are skipped
+  if (cell[0] >= 0 && cell[0] < g.lno[0] && cell[1] >= 0 && cell[1] < g.lno[1] && cell[2] >= 0 && cell[2] < g.lno[2]) {
+    const int c0 = cell[0] / tg.T[0];
+    tile = (c0 * tg.nt[1] + cell[1] / tg.T[1]) * tg.nt[2] + cell[2] / tg.T[2];
+    if (tg.sub > 1) tile = tile * tg.sub + (cell[0] - c0 * tg.T[0]);
+  }
   tile_of[j] = tile;
   idx[j] = j;
   atomicAdd(&tile_count[tile], 1);

@@ -1,0 +1,716 @@
+// Warp-autonomous z-marching gridding kernels (v2, the default B / B^T path for m = 4 and 6).
+// Reference loops replaced: kernel/assign.c:478-1130 (the (2m+1)^3 inner loops), kernel/ndft-parallel.c:2703-3009.
+//
+// What v1 (zmarch.cuh) taught (profiles/r1_zmarch_v1_ncu_full.md): with the grid cells in registers the FP64 pipe is
+// the right bound, but v1 spent 45 % of its stall samples in CTA-wide barriers (row warps see very different node
+// counts) and only 19-24 % of its issued instructions were DFMA (every warp walked every node and tested whether the
+// footprint met its rows).  v2 removes both:
+//   * no CTA-wide barrier after start-up: every consumer warp owns the grid rows (x = 2w, 2w+1; all 16 y rows) of the
+//     column tile's footprint, keeps their sliding z window in registers, and loads / flushes ITS rows with its own TMA
+//     boxes [2][16][ZB] and its own mbarrier.  Warps drift apart by up to the depth of the node ring.
+//   * nodes are sorted by (column tile, z sub-chunk, dx): the rows of warp w meet exactly the nodes with
+//     dx in [2w-2m, 2w+1], a contiguous range of every chunk, found from a 17-entry prefix table in the chunk header.
+//     No per-node skip test, no predicated weight loads (the x / y weight rows are stored zero-padded).
+//   * the gather leaves its per-row partial sums in mbarrier-guarded shared-memory stages; whichever warps are idle
+//     (the edge rows see few nodes) grab nodes of the previous chunk from an atomic ticket and do their x-y reduction.
+//   * the node loops are software pipelined by hand (header / x / y weights of the next node are fetched while the
+//     z taps of the current one run), because one warp per CTA meets every node and issues in order.
+// A producer warp streams the node table (k_node_table2: window factors once per node and axis, written coalesced)
+// into a shared-memory ring with 1-d bulk copies and builds the chunk headers.
+#pragma once
+#include <climits>
+
+#include "zmarch.cuh"
+
+namespace pnb {
+
+template <int M_> struct Zm2Cfg {
+  static constexpr int C = 2 * M_ + 1;
+  static constexpr int R1 = 16;                  // footprint rows along y: half a warp
+  static constexpr int T1 = R1 - 2 * M_;         // column tile, cells (m=6: 4, m=4: 8)
+  static constexpr int T0 = 10;                  // 11 consumer warps (m=6) + producer = 384 threads: 168 registers each
+  static constexpr int SUB = 16;                 // x-offset bins per tile in the sort key (>= T0)
+  static constexpr int ZS = 4;                   // z sub-chunk == window advance
+  static constexpr int ZB = 4;                   // z extent of one TMA box
+  static constexpr int R0 = T0 + 2 * M_;
+  static constexpr int NCW = R0 / 2;             // consumer warps, two x rows each
+  static constexpr int W = ZS + 2 * M_;          // register window (cells)
+  static constexpr int NFL = (W + ZS - 1) / ZS;  // flushes until a touched window is all zero again
+  static_assert(T1 >= 1 && R0 % 2 == 0 && W % ZS == 0 && ZS % ZB == 0 && T0 <= SUB, "unsupported cutoff");
+};
+
+struct Zm2Geom {
+  int nc[2];       // column tiles per axis
+  int nt2;         // z sub-chunks per column
+  int zseg;        // sub-chunks per work item
+  int nseg;        // work items per column
+};
+
+// Node-table row (units of R).  hdr = 8 ints {-dx*sizeof(R), -dy*sizeof(R), dz, dx, node index j, 0, 0, 0};
+// X = [0, psi_x[0..C), 0...], Y = [0 x (T1-1), psi_y[0..C), 0 x (T1-1)...], Z = psi_z[0..C) (zero padded);
+// the same three rows of dpsi when GRAD; vals = f (and grad_f) of the node for the adjoint.
+template <class R, int M_, bool GRAD, bool VALS, bool CPLX> struct Zm2Row {
+  typedef Zm2Cfg<M_> Cfg;
+  static constexpr int AL = 16 / (int)sizeof(R);
+  static constexpr int up(int v) { return (v + AL - 1) / AL * AL; }
+  static constexpr int C = Cfg::C;
+  static constexpr int HDR = 32 / (int)sizeof(R);
+  static constexpr int XP = up(C + 2), YP = up(C + 2 * (Cfg::T1 - 1)), ZP = up(C);
+  static constexpr int oX = HDR, oY = oX + XP, oZ = oY + YP;
+  static constexpr int oDX = oZ + ZP, oDY = oDX + XP, oDZ = oDY + YP;
+  static constexpr int oV = GRAD ? oDZ + ZP : oZ + ZP;
+  static constexpr int NV = VALS ? up((CPLX ? 2 : 1) * (GRAD ? 4 : 1)) : 0;
+  static constexpr int ROWLEN = oV + NV;
+  static constexpr int ROWBYTES = ROWLEN * (int)sizeof(R);
+  static_assert(ROWBYTES % 16 == 0, "bulk copies need 16-byte granules");
+};
+
+constexpr int kZm2HdrBytes = 128;    // chunk header: {tz, count, first sorted index, 0, start[0..T0]}
+constexpr int kZm2TabNodes = 64;     // nodes per block of the table kernel
+
+// ------------------------------------------------------------------------------------------------
+// node table: one thread per (node, axis); rows assembled in shared memory, written out coalesced
+// ------------------------------------------------------------------------------------------------
+template <class R, int M_, bool GRAD, bool VALS, bool CPLX>
+__global__ void __launch_bounds__(3 * kZm2TabNodes)
+k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
+  typedef Zm2Cfg<M_> Cfg;
+  typedef Zm2Row<R, M_, GRAD, VALS, CPLX> Row;
+  constexpr int C = Cfg::C, NCOMP = CPLX ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R *rows = reinterpret_cast<R *>(smem_raw);
+  R *poly_s = rows + (size_t)kZm2TabNodes * Row::ROWLEN;
+  if (g.poly) for (int i = threadIdx.x; i < (g.poly_deg + 1) * 3 * C; i += blockDim.x) poly_s[i] = g.poly[i];
+  __syncthreads();
+  const int p0 = blockIdx.x * kZm2TabNodes;
+  const int nn = min(kZm2TabNodes, na.M - p0);
+  const int ln = threadIdx.x / 3, t = threadIdx.x - 3 * ln;
+  if (ln < nn) {
+    const int p = p0 + ln;
+    const int j = na.perm[p];
+    const R nxv = mul_rn(g.n[t], na.x[3 * (size_t)j + t]);
+    const R flv = m_floor(nxv), fr = nxv - flv;
+    R psi[C], dpsi[GRAD ? C : 1];
+    if (na.pre_psi) {
+#pragma unroll
+      for (int s = 0; s < C; s++) {
+        psi[s] = na.pre_psi[(size_t)p * 3 * C + t * C + s];
+        if (GRAD) dpsi[s] = na.pre_dpsi[(size_t)p * 3 * C + t * C + s];
+      }
+    } else if (g.poly && fr != (R)0) {
+      // per-tap polynomials in u = 2 frac - 1 (Core::fit_window_polys); all taps advance together (Horner)
+      const R u = (R)2 * fr - (R)1;
+      const R *a = poly_s + t * C;
+      const int nv = 3 * C;
+#pragma unroll
+      for (int s = 0; s < C; s++) { psi[s] = a[g.poly_deg * nv + s]; if (GRAD) dpsi[s] = (R)0; }
+      for (int k = g.poly_deg - 1; k >= 0; k--) {
+#pragma unroll
+        for (int s = 0; s < C; s++) {
+          if (GRAD) dpsi[s] = dpsi[s] * u + psi[s];
+          psi[s] = psi[s] * u + a[k * nv + s];
+        }
+      }
+      if (GRAD) {
+        const R sc = (R)2 * g.n[t];
+#pragma unroll
+        for (int s = 0; s < C; s++) dpsi[s] *= sc;
+      }
+    } else {
+      // exact formulas (nodes on a grid line, windows without a polynomial fit): through a local scratch row
+      R tp[C], td[C];
+      if (g.kind == WIN_BSPLINE) {
+        bspline_taps<R>(M_, fr, g.n[t], tp, GRAD ? td : nullptr);
+      } else if (g.kind == WIN_GAUSSIAN && g.fast_gauss) {
+        const R d = nxv - (flv - (R)M_);
+        const R e_sqr = m_exp(-(d * d) / g.b[t]), e_lin = m_exp((R)2 * d / g.b[t]);
+        R tmp = e_sqr;
+        for (int s = 0; s < C; s++) {
+          const R v = tmp * g.exp_const[t * C + s];
+          tp[s] = v;
+          td[s] = (R)(-2.0) * g.n[t] / g.b[t] * (d - (R)s) * v;
+          tmp *= e_lin;
+        }
+      } else {
+#pragma unroll 1
+        for (int s = 0; s < C; s++) {
+          R a = (R)0, b = (R)0;
+          window_tap<R>(g.kind, flv - nxv - (R)M_ + (R)s, g.n[t], g.b[t], M_, GRAD, &a, &b);
+          tp[s] = a; td[s] = b;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < C; s++) { psi[s] = tp[s]; if (GRAD) dpsi[s] = td[s]; }
+    }
+    R *row = rows + (size_t)ln * Row::ROWLEN;
+    const int off = t == 0 ? Row::oX : (t == 1 ? Row::oY : Row::oZ);
+    const int len = t == 0 ? Row::XP : (t == 1 ? Row::YP : Row::ZP);
+    const int lead = t == 0 ? 1 : (t == 1 ? Cfg::T1 - 1 : 0);
+    for (int i = 0; i < len; i++) { row[off + i] = (R)0; if (GRAD) row[off + (Row::oDX - Row::oX) + i] = (R)0; }
+#pragma unroll
+    for (int s = 0; s < C; s++) { row[off + lead + s] = psi[s]; if (GRAD) row[off + (Row::oDX - Row::oX) + lead + s] = dpsi[s]; }
+    // cell offset inside the (T0, T1, ZS) tile
+    const int cell = (int)flv - g.los[t];
+    const int T = t == 0 ? Cfg::T0 : (t == 1 ? Cfg::T1 : Cfg::ZS);
+    const int d = cell - (cell / T) * T;
+    int *h = reinterpret_cast<int *>(row);
+    if (t == 0) { h[0] = -d * (int)sizeof(R); h[3] = d; h[4] = j; }
+    else if (t == 1) { h[1] = -d * (int)sizeof(R); h[5] = 0; }
+    else { h[2] = d; h[6] = 0; h[7] = 0; }
+    if (VALS && t == 0) {
+      R *v = row + Row::oV;
+      for (int c = 0; c < Row::NV; c++) v[c] = (R)0;
+      if (na.f) for (int c = 0; c < NCOMP; c++) v[c] = na.f[((size_t)j * na.f_stride + na.f_off) * NCOMP + c];
+      if (GRAD) for (int c = 0; c < 3 * NCOMP; c++) v[NCOMP + c] = na.grad[(size_t)j * 3 * NCOMP + c];
+    }
+  }
+  __syncthreads();
+  const uint4 *src = reinterpret_cast<const uint4 *>(rows);
+  uint4 *dst = reinterpret_cast<uint4 *>(tab + (size_t)p0 * Row::ROWLEN);
+  const int n16 = nn * (Row::ROWBYTES / 16);
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory carve-up
+// ------------------------------------------------------------------------------------------------
+template <class R, bool CPLX, int M_, bool GRAD> struct Zm2Smem {
+  typedef typename CellT<R, CPLX>::type Cell;
+  typedef Zm2Cfg<M_> Cfg;
+  typedef Zm2Row<R, M_, GRAD, true, CPLX> RowS;
+  typedef Zm2Row<R, M_, GRAD, false, CPLX> RowG;
+  static constexpr int WARP_BOX = 32 * Cfg::ZS * (int)sizeof(Cell);       // bytes one warp stages per window advance
+  // scatter: two staging buffers per warp, ring of S chunks of GB nodes
+  static constexpr int SS = 4, SGB = 32;
+  static constexpr int s_stage = kZm2HdrBytes + SGB * RowS::ROWBYTES;
+  static constexpr int s_off_ring = Cfg::NCW * 2 * WARP_BOX;
+  static constexpr int s_off_bar = s_off_ring + SS * s_stage;
+  static constexpr int scatter = s_off_bar + 2 * SS * 8;
+  // gather: one staging buffer per warp, ring, P stages of per-row partial sums
+  static constexpr int GS = 4, GP = 2;
+  static constexpr int GGB = GRAD ? 8 : 16;
+  static constexpr int PN = Cfg::C * 16 * (GRAD ? 2 : 1);                 // partial cells per node
+  static constexpr int g_stage = kZm2HdrBytes + GGB * RowG::ROWBYTES;
+  static constexpr int g_off_ring = Cfg::NCW * WARP_BOX;
+  static constexpr int g_off_part = g_off_ring + GS * g_stage;
+  static constexpr int g_off_bar = g_off_part + GP * GGB * PN * (int)sizeof(Cell);
+  static constexpr int gather = g_off_bar + (2 * GS + 2 * GP + Cfg::NCW) * 8;
+  static_assert(s_stage % 16 == 0 && g_stage % 16 == 0 && s_off_ring % 128 == 0 && g_off_ring % 128 == 0, "alignment");
+  static_assert(scatter <= 232448 && gather <= 232448, "shared-memory budget of one CTA exceeded");
+};
+
+// mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of spinning on the issue port
+__device__ __forceinline__ void mbar_wait_park(unsigned long long *bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITP_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONEP_%=;\n"
+      "bra WAITP_%=;\n"
+      "DONEP_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase), "r"(20000u) : "memory");
+}
+
+// z taps of one node from / into the register window; the z offset picks one of ZS statically indexed variants
+// through a two- (three-) level branch tree (cheaper than the jump table a switch compiles to)
+template <int D, int C, bool GRAD, class R, class Cell, int W, int ZP>
+__device__ __forceinline__ void zm2_acc(Cell (&win)[W], const R (&wz)[ZP], const R (&dwz)[ZP], const Cell &A, const Cell &B) {
+#pragma unroll
+  for (int k = 0; k < C; k++) {
+    fma_cell(win[D + k], wz[k], A);
+    if (GRAD) fma_cell(win[D + k], dwz[k], B);
+  }
+}
+template <int D, int C, bool GRAD, class R, class Cell, int W, int ZP>
+__device__ __forceinline__ void zm2_dot(const Cell (&win)[W], const R (&wz)[ZP], const R (&dwz)[ZP], Cell &t, Cell &td) {
+  Cell t1, td1;
+  zero_cell(t); zero_cell(td); zero_cell(t1); zero_cell(td1);
+#pragma unroll
+  for (int k = 0; k + 1 < C; k += 2) {
+    fma_cell(t, wz[k], win[D + k]);
+    fma_cell(t1, wz[k + 1], win[D + k + 1]);
+    if (GRAD) { fma_cell(td, dwz[k], win[D + k]); fma_cell(td1, dwz[k + 1], win[D + k + 1]); }
+  }
+  fma_cell(t, wz[C - 1], win[D + C - 1]);
+  if (GRAD) fma_cell(td, dwz[C - 1], win[D + C - 1]);
+  add_cell(t, t1);
+  if (GRAD) add_cell(td, td1);
+}
+#define ZM2_TREE(d, CALL)                                         \
+  do {                                                            \
+    if constexpr (ZS == 4) {                                      \
+      if ((d) & 2) { if ((d) & 1) { CALL(3); } else { CALL(2); } } \
+      else { if ((d) & 1) { CALL(1); } else { CALL(0); } }        \
+    } else {                                                      \
+      static_assert(ZS == 8, "z sub-chunk must be 4 or 8");       \
+      if ((d) & 4) {                                              \
+        if ((d) & 2) { if ((d) & 1) { CALL(7); } else { CALL(6); } } \
+        else { if ((d) & 1) { CALL(5); } else { CALL(4); } }      \
+      } else {                                                    \
+        if ((d) & 2) { if ((d) & 1) { CALL(3); } else { CALL(2); } } \
+        else { if ((d) & 1) { CALL(1); } else { CALL(0); } }      \
+      }                                                           \
+    }                                                             \
+  } while (0)
+
+__device__ __forceinline__ int warp_any_volatile(int pred) {
+  int res;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.s32 p, %1, 0;\n"
+      "vote.sync.any.pred q, p, 0xffffffff;\n"
+      "selp.s32 %0, 1, 0, q;\n"
+      "}\n" : "=r"(res) : "r"(pred) : "memory");
+  return res;
+}
+
+// producer warp: chunk headers + node-table rows of one work item into the ring; NEND end markers at the end
+template <int T0, int SUB, int S, int GB, int ROWBYTES, int STAGE, int NEND>
+__device__ __forceinline__ void zm2_produce(unsigned char *ring, unsigned long long *full, unsigned long long *empty,
+                                            const unsigned char *tab, const int *__restrict__ bs, int tz0, int tz1, int lane) {
+  int kb = 0;
+  int gs_next = (lane <= T0) ? bs[(size_t)tz0 * SUB + lane] : 0;
+  for (int tz = tz0; tz < tz1; tz++) {
+    const int gs = gs_next;
+    if (tz + 1 < tz1) gs_next = (lane <= T0) ? bs[(size_t)(tz + 1) * SUB + lane] : 0;
+    const int s = __shfl_sync(0xffffffffu, gs, 0), e = __shfl_sync(0xffffffffu, gs, T0);
+    for (int c0 = s; c0 < e; c0 += GB, kb++) {
+      const int st = kb % S;
+      mbar_wait_park(&empty[st], (((unsigned)(kb / S)) & 1u) ^ 1u);
+      const int cnt = min(GB, e - c0);
+      unsigned char *sp = ring + (size_t)st * STAGE;
+      int *h = reinterpret_cast<int *>(sp);
+      if (lane <= T0) h[4 + lane] = min(max(gs - c0, 0), cnt);
+      if (lane == 0) { h[0] = tz; h[1] = cnt; h[2] = c0; h[3] = 0; }
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned bytes = (unsigned)(cnt * ROWBYTES);
+        mbar_expect_tx(&full[st], bytes);
+        bulk_load_1d(sp + kZm2HdrBytes, tab + (size_t)c0 * ROWBYTES, bytes, &full[st]);
+      }
+    }
+  }
+  for (int k = 0; k < NEND; k++, kb++) {
+    const int st = kb % S;
+    mbar_wait_park(&empty[st], (((unsigned)(kb / S)) & 1u) ^ 1u);
+    if (lane == 0) {
+      int *h = reinterpret_cast<int *>(ring + (size_t)st * STAGE);
+      h[0] = INT_MAX; h[1] = 0;
+      mbar_arrive(&full[st]);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter (adjoint B^T)
+// ------------------------------------------------------------------------------------------------
+template <class R, bool CPLX, int M_, bool GRAD>
+__global__ void __launch_bounds__((Zm2Cfg<M_>::NCW + 1) * 32, 1)
+k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__restrict__ tab, const int *__restrict__ bin_start) {
+  typedef typename CellT<R, CPLX>::type Cell;
+  typedef Zm2Cfg<M_> Cfg;
+  typedef Zm2Smem<R, CPLX, M_, GRAD> Sm;
+  typedef typename Sm::RowS Row;
+  constexpr int C = Cfg::C, T0 = Cfg::T0, T1 = Cfg::T1, ZS = Cfg::ZS, ZB = Cfg::ZB, W = Cfg::W, NCW = Cfg::NCW;
+  constexpr int NCOMP = CPLX ? 2 : 1, S = Sm::SS, GB = Sm::SGB, ROWBYTES = Row::ROWBYTES, STAGE = Sm::s_stage, ZP = Row::ZP;
+  constexpr int SZ = (int)sizeof(R);
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *ring = smem_raw + Sm::s_off_ring;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + Sm::s_off_bar);
+  unsigned long long *empty = full + S;
+
+  const int col = blockIdx.x / zg.nseg, seg = blockIdx.x - col * zg.nseg;
+  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
+  const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
+  if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;            // no nodes in this work item
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < S; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCW) {
+    zm2_produce<T0, Cfg::SUB, S, GB, ROWBYTES, STAGE, 1>(ring, full, empty, reinterpret_cast<const unsigned char *>(tab), bs, tz0, tz1, lane);
+    return;
+  }
+
+  const int cx = col / zg.nc[1], cy = col - cx * zg.nc[1];
+  const int o0 = cx * T0 + 2 * warp, o1 = cy * T1;
+  const int r0 = 2 * warp + (lane >> 4), r1 = lane & 15;
+  const int aX = (Row::oX + 1 + r0) * SZ, aY = (Row::oY + T1 - 1 + r1) * SZ;
+  constexpr int dOff = (Row::oDX - Row::oX) * SZ;
+  const int dxlo = max(0, 2 * warp - (C - 1)), dxhi1 = min(T0 - 1, 2 * warp + 1) + 1;
+  Cell *mystg = reinterpret_cast<Cell *>(smem_raw) + (size_t)warp * 2 * 32 * ZS;
+
+  Cell win[W];
+#pragma unroll
+  for (int i = 0; i < W; i++) zero_cell(win[i]);
+  int cur = tz0, dirty = 0, nfl = 0;
+
+  // the first ZS cells of the window are final: reduce-add them into the grid, advance the window
+  auto flush_advance = [&]() {
+    Cell *sb = mystg + (nfl & 1) * (32 * ZS);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box issued two flushes ago was read
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < ZS; q++) sb[(q / ZB) * (32 * ZB) + lane * ZB + (q % ZB)] = win[q];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int b = 0; b < ZS / ZB; b++) tma_reduce_add_3d(sb + b * (32 * ZB), &tmap, (cur * ZS + b * ZB) * NCOMP, o1, o0);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    nfl++;
+#pragma unroll
+    for (int i = 0; i < W - ZS; i++) win[i] = win[i + ZS];
+#pragma unroll
+    for (int i = W - ZS; i < W; i++) zero_cell(win[i]);
+    cur++;
+  };
+
+  // operands of one node that depend on this thread's rows: x and y weights (and derivatives), node values
+  struct Ops { R w0, w1, dw0, dw1; Cell f, g0, g1, g2; };
+  auto fetch = [&](const unsigned char *row, const int4 &hd, Ops &o) {
+    o.w0 = *reinterpret_cast<const R *>(row + aX + hd.x);
+    o.w1 = *reinterpret_cast<const R *>(row + aY + hd.y);
+    const R *v = reinterpret_cast<const R *>(row) + Row::oV;
+    Cell z; zero_cell(z);
+    o.f = load_in(v, z);
+    if (GRAD) {
+      o.dw0 = *reinterpret_cast<const R *>(row + aX + dOff + hd.x);
+      o.dw1 = *reinterpret_cast<const R *>(row + aY + dOff + hd.y);
+      o.g0 = load_in(v + NCOMP, z); o.g1 = load_in(v + 2 * NCOMP, z); o.g2 = load_in(v + 3 * NCOMP, z);
+    }
+  };
+
+  for (int kb = 0;; kb++) {
+    const int st = kb % S;
+    mbar_wait_park(&full[st], ((unsigned)(kb / S)) & 1u);
+    const unsigned char *sp = ring + (size_t)st * STAGE;
+    const int *h = reinterpret_cast<const int *>(sp);
+    const int tz = h[0];
+    if (tz == INT_MAX) break;
+    const int lo = h[4 + dxlo], hi = h[4 + dxhi1];
+    if (hi > lo) {
+      while (cur < tz) {
+        if (dirty > 0) { flush_advance(); dirty--; }
+        else cur = tz;
+      }
+      const unsigned char *row = sp + kZm2HdrBytes + (size_t)lo * ROWBYTES;
+      const unsigned char *last = sp + kZm2HdrBytes + (size_t)(hi - 1) * ROWBYTES;
+      // software pipeline: header two nodes ahead, thread-dependent operands one node ahead
+      int4 hd = *reinterpret_cast<const int4 *>(row);
+      const unsigned char *row1 = row + ROWBYTES < last ? row + ROWBYTES : last;
+      int4 hn = *reinterpret_cast<const int4 *>(row1);
+      Ops op;
+      fetch(row, hd, op);
+      for (int i = lo; i < hi; i++) {
+        const R *rr = reinterpret_cast<const R *>(row);
+        R wz[ZP], dwz[ZP];
+#pragma unroll
+        for (int k = 0; k < ZP; k += 16 / SZ) {
+          typedef typename WPair<R>::type P2;
+          if constexpr (SZ == 8) {
+            const P2 w = *reinterpret_cast<const P2 *>(rr + Row::oZ + k);
+            wz[k] = w.x; wz[k + 1] = w.y;
+            if (GRAD) { const P2 d = *reinterpret_cast<const P2 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; }
+          } else {
+            const float4 w = *reinterpret_cast<const float4 *>(rr + Row::oZ + k);
+            wz[k] = w.x; wz[k + 1] = w.y; wz[k + 2] = w.z; wz[k + 3] = w.w;
+            if (GRAD) { const float4 d = *reinterpret_cast<const float4 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; dwz[k + 2] = d.z; dwz[k + 3] = d.w; }
+          }
+        }
+        Cell A = scale_cell(op.w0 * op.w1, op.f), B;
+        zero_cell(B);
+        if (GRAD) {
+          fma_cell(A, op.dw0 * op.w1, op.g0);
+          fma_cell(A, op.w0 * op.dw1, op.g1);
+          B = scale_cell(op.w0 * op.w1, op.g2);
+        }
+        const int dz = hd.z;
+        // prefetch
+        const unsigned char *row2 = row1 + ROWBYTES < last ? row1 + ROWBYTES : last;
+        const int4 hn2 = *reinterpret_cast<const int4 *>(row2);
+        fetch(row1, hn, op);
+#define ZM2_CALL(D) zm2_acc<D, C, GRAD>(win, wz, dwz, A, B)
+        ZM2_TREE(dz, ZM2_CALL);
+#undef ZM2_CALL
+        hd = hn; hn = hn2; row = row1; row1 = row2;
+      }
+      dirty = Cfg::NFL;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+  while (dirty > 0) { flush_advance(); dirty--; }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive the bulk reads
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather (trafo B)
+// ------------------------------------------------------------------------------------------------
+// sum NV values over the 32 lanes with NV-1 + log2(32/NV) exchanges; the lane whose upper bits spell k ends up with
+// the total of value k (returned in v[0], k in *which); all lanes sharing those upper bits hold the same total
+template <int NV, class R> __device__ __forceinline__ void lanes_reduce(R (&v)[NV], int lane, int *which) {
+  int w = 0;
+  int bit = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1, bit >>= 1) {
+    const bool hi = (lane & bit) != 0;
+#pragma unroll
+    for (int k = 0; k < n / 2; k++) {
+      const R send = hi ? v[k] : v[k + n / 2];
+      const R keep = hi ? v[k + n / 2] : v[k];
+      v[k] = keep + shfl_xor(send, bit);
+    }
+    w += hi ? n / 2 : 0;
+  }
+  for (; bit > 0; bit >>= 1) v[0] += shfl_xor(v[0], bit);
+  *which = w;
+}
+
+// x-y contraction of one node's per-row partial sums by one warp: lane = (x row parity, y row); the y weight of a lane
+// is the same for all its x rows, so it multiplies the per-lane sums once at the end
+template <class R, bool CPLX, int M_, bool GRAD, class Row, class Cell>
+__device__ __forceinline__ void zm2_reduce_node(const unsigned char *row, const Cell *pp, int lane, const GatherOut<R> &out) {
+  typedef Zm2Cfg<M_> Cfg;
+  constexpr int C = Cfg::C, T1 = Cfg::T1, NCOMP = CPLX ? 2 : 1, SZ = (int)sizeof(R);
+  const int *hd = reinterpret_cast<const int *>(row);
+  const int ny = hd[1], j = hd[4];
+  const R *rr = reinterpret_cast<const R *>(row);
+  const R w1 = *reinterpret_cast<const R *>(row + (Row::oY + T1 - 1 + (lane & 15)) * SZ + ny);
+  R dw1 = (R)0;
+  if (GRAD) dw1 = *reinterpret_cast<const R *>(row + (Row::oDY + T1 - 1 + (lane & 15)) * SZ + ny);
+  Cell s, sd, u;
+  zero_cell(s); zero_cell(sd); zero_cell(u);
+#pragma unroll
+  for (int it = 0; it < (C + 1) / 2; it++) {
+    const int i0 = 2 * it + (lane >> 4);
+    const bool ok = (2 * it + 1 < C) || i0 < C;
+    const R w0 = rr[Row::oX + 1 + i0];                       // zero beyond the last tap
+    Cell t, td;
+    zero_cell(t); zero_cell(td);
+    if (ok) { t = pp[32 * it + lane]; if (GRAD) td = pp[C * 16 + 32 * it + lane]; }
+    fma_cell(s, w0, t);
+    if (GRAD) {
+      const R dw0 = rr[Row::oDX + 1 + i0];
+      fma_cell(sd, dw0, t);
+      fma_cell(u, w0, td);
+    }
+  }
+  constexpr int NVAL = NCOMP * (GRAD ? 4 : 1);
+  R v[NVAL];
+  const Cell af = scale_cell(w1, s);
+  if constexpr (CPLX) {
+    v[0] = af.x; v[1] = af.y;
+    if constexpr (GRAD) {
+      const Cell a0 = scale_cell(w1, sd), a1 = scale_cell(dw1, s), a2 = scale_cell(w1, u);
+      v[2] = a0.x; v[3] = a0.y; v[4] = a1.x; v[5] = a1.y; v[6] = a2.x; v[7] = a2.y;
+    }
+  } else {
+    v[0] = af;
+    if constexpr (GRAD) { v[1] = scale_cell(w1, sd); v[2] = scale_cell(dw1, s); v[3] = scale_cell(w1, u); }
+  }
+  int which;
+  lanes_reduce<NVAL>(v, lane, &which);
+  if ((lane & (32 / NVAL - 1)) == 0) {
+    R *o = nullptr;
+    if (which < NCOMP) { if (out.f) o = out.f + ((size_t)j * out.f_stride + out.f_off) * NCOMP + which; }
+    else if (GRAD) o = out.grad + (size_t)j * 3 * NCOMP + (which - NCOMP);
+    if (o) *o = out.accumulate ? *o + v[0] : v[0];
+  }
+}
+
+template <class R, bool CPLX, int M_, bool GRAD>
+__global__ void __launch_bounds__((Zm2Cfg<M_>::NCW + 1) * 32, 1)
+k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__restrict__ tab, const int *__restrict__ bin_start,
+             GatherOut<R> out) {
+  typedef typename CellT<R, CPLX>::type Cell;
+  typedef Zm2Cfg<M_> Cfg;
+  typedef Zm2Smem<R, CPLX, M_, GRAD> Sm;
+  typedef typename Sm::RowG Row;
+  constexpr int C = Cfg::C, T0 = Cfg::T0, T1 = Cfg::T1, ZS = Cfg::ZS, ZB = Cfg::ZB, W = Cfg::W, NCW = Cfg::NCW;
+  constexpr int NCOMP = CPLX ? 2 : 1, S = Sm::GS, P = Sm::GP, GB = Sm::GGB, ROWBYTES = Row::ROWBYTES, STAGE = Sm::g_stage, PN = Sm::PN;
+  constexpr int ZP = Row::ZP, SZ = (int)sizeof(R);
+  constexpr unsigned BOXB = 32 * ZB * (unsigned)sizeof(Cell);
+  static_assert(S >= 3 && P >= 2, "ring / partial stages too shallow for the deferred reduction");
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *ring = smem_raw + Sm::g_off_ring;
+  Cell *part = reinterpret_cast<Cell *>(smem_raw + Sm::g_off_part);
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + Sm::g_off_bar);
+  unsigned long long *empty = full + S;
+  unsigned long long *pfull = empty + S;
+  unsigned long long *pempty = pfull + P;
+  unsigned long long *wbar = pempty + P;
+
+  const int col = blockIdx.x / zg.nseg, seg = blockIdx.x - col * zg.nseg;
+  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
+  const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
+  if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < S; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
+    for (int i = 0; i < P; i++) { mbar_init(&pfull[i], NCW); mbar_init(&pempty[i], NCW); }
+    for (int i = 0; i < NCW; i++) mbar_init(&wbar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCW) {
+    zm2_produce<T0, Cfg::SUB, S, GB, ROWBYTES, STAGE, 1>(ring, full, empty, reinterpret_cast<const unsigned char *>(tab), bs, tz0, tz1, lane);
+    return;
+  }
+
+  // ---- consumer warps ----
+  const int cx = col / zg.nc[1], cy = col - cx * zg.nc[1];
+  const int o0 = cx * T0 + 2 * warp, o1 = cy * T1;
+  const int r0 = 2 * warp + (lane >> 4), r1 = lane & 15;
+  const int dxlo = max(0, 2 * warp - (C - 1)), dxhi1 = min(T0 - 1, 2 * warp + 1) + 1;
+  Cell *mystg = reinterpret_cast<Cell *>(smem_raw) + (size_t)warp * 32 * ZS;
+  unsigned long long *mybar = &wbar[warp];
+  unsigned wph = 0;
+
+  Cell win[W];
+  int cur = INT_MIN / 2;       // sub-chunk whose cells [cur*ZS, cur*ZS + W) are in the window
+  bool pending = false;        // a load of the cells [cur*ZS + W, +ZS) is in flight
+
+  auto issue = [&](int zc, int nbox) {       // lane 0: nbox TMA boxes [2][16][ZB] starting at cell zc
+    if (lane == 0) {
+      mbar_expect_tx(mybar, BOXB * (unsigned)nbox);
+      for (int b = 0; b < nbox; b++) tma_load_3d(mystg + b * (32 * ZB), &tmap, (zc + b * ZB) * NCOMP, o1, o0, mybar);
+    }
+  };
+  // wait for the staged boxes and copy my row's cells into the window.  The vote consumes the loaded values, so every
+  // lane's shared-memory reads have RETURNED before lane 0 may re-arm the staging buffer with the next TMA load.
+  auto take = [&](auto first_tag, auto nbox_tag) {
+    constexpr int FIRST = decltype(first_tag)::value, NBOX = decltype(nbox_tag)::value;
+    mbar_wait(mybar, wph);
+    wph ^= 1u;
+    int nan = 0;
+#pragma unroll
+    for (int b = 0; b < NBOX; b++)
+#pragma unroll
+      for (int q = 0; q < ZB; q++) {
+        win[FIRST + b * ZB + q] = mystg[b * (32 * ZB) + lane * ZB + q];
+        nan |= cell_is_nan(win[FIRST + b * ZB + q]);
+      }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    (void)warp_any_volatile(nan);
+  };
+  auto drop_pending = [&]() {
+    if (pending) { mbar_wait(mybar, wph); wph ^= 1u; pending = false; }
+  };
+  auto reload = [&](int tz) {      // whole window at sub-chunk tz, then prefetch the next advance
+    drop_pending();
+    const int z0 = tz * ZS;
+    constexpr int PER = ZS / ZB;   // boxes per staging buffer
+    static_assert(W % ZS == 0 && W / ZS <= 6, "window reload written for at most six whole rounds");
+    issue(z0, PER);
+    take(std::integral_constant<int, 0>(), std::integral_constant<int, PER>());
+    if constexpr (W / ZS > 1) { issue(z0 + ZS, PER); take(std::integral_constant<int, (W / ZS > 1) ? ZS : 0>(), std::integral_constant<int, PER>()); }
+    if constexpr (W / ZS > 2) { issue(z0 + 2 * ZS, PER); take(std::integral_constant<int, (W / ZS > 2) ? 2 * ZS : 0>(), std::integral_constant<int, PER>()); }
+    if constexpr (W / ZS > 3) { issue(z0 + 3 * ZS, PER); take(std::integral_constant<int, (W / ZS > 3) ? 3 * ZS : 0>(), std::integral_constant<int, PER>()); }
+    if constexpr (W / ZS > 4) { issue(z0 + 4 * ZS, PER); take(std::integral_constant<int, (W / ZS > 4) ? 4 * ZS : 0>(), std::integral_constant<int, PER>()); }
+    if constexpr (W / ZS > 5) { issue(z0 + 5 * ZS, PER); take(std::integral_constant<int, (W / ZS > 5) ? 5 * ZS : 0>(), std::integral_constant<int, PER>()); }
+    cur = tz;
+    issue(z0 + W, PER);
+    pending = true;
+  };
+  auto advance1 = [&]() {
+#pragma unroll
+    for (int i = 0; i < W - ZS; i++) win[i] = win[i + ZS];
+    take(std::integral_constant<int, W - ZS>(), std::integral_constant<int, ZS / ZB>());
+    cur++;
+    issue(cur * ZS + W, ZS / ZB);
+  };
+
+  // deferred x-y reduction of chunk kr: wait until every warp has left its partial sums, then take nodes from the
+  // chunk's ticket counter (in its ring header) until none are left; releases the partial stage and the ring stage
+  auto help = [&](int kr) {
+    const int st = kr % S, ps = kr % P;
+    unsigned char *sp = ring + (size_t)st * STAGE;
+    int *h = reinterpret_cast<int *>(sp);
+    mbar_wait_park(&pfull[ps], ((unsigned)(kr / P)) & 1u);
+    const int cnt = h[1];
+    for (;;) {
+      int i = 0;
+      if (lane == 0) i = atomicAdd(&h[3], 1);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      if (i >= cnt) break;
+      zm2_reduce_node<R, CPLX, M_, GRAD, Row>(sp + kZm2HdrBytes + (size_t)i * ROWBYTES, part + (size_t)(ps * GB + i) * PN, lane, out);
+    }
+    __syncwarp();
+    if (lane == 0) { mbar_arrive(&pempty[ps]); mbar_arrive(&empty[st]); }
+  };
+
+  const int aP = (r0 * 16 + r1);
+  int kb = 0;
+  for (;; kb++) {
+    const int st = kb % S, ps = kb % P;
+    mbar_wait_park(&full[st], ((unsigned)(kb / S)) & 1u);
+    const unsigned char *sp = ring + (size_t)st * STAGE;
+    const int *h = reinterpret_cast<const int *>(sp);
+    const int tz = h[0];
+    if (tz == INT_MAX) break;
+    const int lo = h[4 + dxlo], hi = h[4 + dxhi1];
+    mbar_wait_park(&pempty[ps], (((unsigned)(kb / P)) & 1u) ^ 1u);
+    if (hi > lo) {
+      if (tz != cur) {
+        if (pending && tz == cur + 1) advance1();
+        else if (pending && tz == cur + 2) { advance1(); advance1(); }
+        else reload(tz);
+      }
+      const unsigned char *row = sp + kZm2HdrBytes + (size_t)lo * ROWBYTES;
+      const unsigned char *last = sp + kZm2HdrBytes + (size_t)(hi - 1) * ROWBYTES;
+      Cell *pb = part + (size_t)(ps * GB + lo) * PN + aP;
+      int4 hd = *reinterpret_cast<const int4 *>(row);
+      for (int i = lo; i < hi; i++, pb += PN) {
+        const R *rr = reinterpret_cast<const R *>(row);
+        R wz[ZP], dwz[ZP];
+#pragma unroll
+        for (int k = 0; k < ZP; k += 16 / SZ) {
+          typedef typename WPair<R>::type P2;
+          if constexpr (SZ == 8) {
+            const P2 w = *reinterpret_cast<const P2 *>(rr + Row::oZ + k);
+            wz[k] = w.x; wz[k + 1] = w.y;
+            if (GRAD) { const P2 d = *reinterpret_cast<const P2 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; }
+          } else {
+            const float4 w = *reinterpret_cast<const float4 *>(rr + Row::oZ + k);
+            wz[k] = w.x; wz[k + 1] = w.y; wz[k + 2] = w.z; wz[k + 3] = w.w;
+            if (GRAD) { const float4 d = *reinterpret_cast<const float4 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; dwz[k + 2] = d.z; dwz[k + 3] = d.w; }
+          }
+        }
+        const unsigned char *row1 = row + ROWBYTES < last ? row + ROWBYTES : last;
+        const int4 hn = *reinterpret_cast<const int4 *>(row1);       // prefetch the next header
+        Cell t, td;
+        const int dz = hd.z;
+#define ZM2_CALL(D) zm2_dot<D, C, GRAD>(win, wz, dwz, t, td)
+        ZM2_TREE(dz, ZM2_CALL);
+#undef ZM2_CALL
+        const int i0 = r0 - hd.w;
+        if ((unsigned)i0 < (unsigned)C) {
+          Cell *p = pb - hd.w * 16;
+          p[0] = t;
+          if (GRAD) p[C * 16] = td;
+        }
+        hd = hn; row = row1;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&pfull[ps]);
+    if (kb >= 1) help(kb - 1);
+  }
+  if (kb >= 1) help(kb - 1);
+  drop_pending();    // no TMA write may still be in flight when the CTA retires
+}
+
+}  // namespace pnb
