@@ -120,14 +120,15 @@ inline TmapEncodeFn tmap_encoder() {
 }
 
 template <class R>
-inline CUtensorMap make_grid_tmap(void *grid, const Layout &L, int ncomp, int bx, int by, int bz) {
+inline CUtensorMap make_grid_tmap(void *grid, const Layout &L, int ncomp, int bx, int by, int bz, int swizzle = 0) {
   CUtensorMap tm;
   const cuuint64_t gdim[3] = {(cuuint64_t)L.pitch2 * ncomp, (cuuint64_t)L.ngc[1], (cuuint64_t)L.ngc[0]};
   const cuuint64_t gstr[2] = {(cuuint64_t)L.pitch2 * ncomp * sizeof(R), (cuuint64_t)L.ngc[1] * L.pitch2 * ncomp * sizeof(R)};
   const cuuint32_t box[3] = {(cuuint32_t)(bz * ncomp), (cuuint32_t)by, (cuuint32_t)bx};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapDataType dt = sizeof(R) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUresult r = tmap_encoder()(&tm, dt, 3, grid, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+  const CUtensorMapSwizzle sw = swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUresult r = tmap_encoder()(&tm, dt, 3, grid, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { fprintf(stderr, "pnfft-b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r); abort(); }
   return tm;
@@ -685,7 +686,8 @@ template <class R> struct Core {
       typedef Zm2Smem<R, CPLX, M_, GRAD> Sm;
       const TileGeom tg = tile_geom(p, nullptr);
       const GridGeom<R> g = geom(p);
-      const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, 2, 16, Cfg::ZB);
+      typedef typename CellT<R, CPLX>::type Cell;
+      const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::XW, 16, Cfg::ZB, zm2_swizzle_mode<Cell, Cfg::ZB>());
       Zm2Geom zg;
       zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2];
       // whole columns per work item when there are enough columns to fill the GPU, else split along z

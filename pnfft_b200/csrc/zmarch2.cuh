@@ -28,15 +28,17 @@ template <int M_> struct Zm2Cfg {
   static constexpr int C = 2 * M_ + 1;
   static constexpr int R1 = 16;                  // footprint rows along y: half a warp
   static constexpr int T1 = R1 - 2 * M_;         // column tile, cells (m=6: 4, m=4: 8)
-  static constexpr int T0 = 10;                  // 11 consumer warps (m=6) + producer = 384 threads: 168 registers each
+  static constexpr int T0 = 12;                  // R0 = 24 (m=6): 6 consumer warps of 4 x rows
   static constexpr int SUB = 16;                 // x-offset bins per tile in the sort key (>= T0)
   static constexpr int ZS = 4;                   // z sub-chunk == window advance
   static constexpr int ZB = 4;                   // z extent of one TMA box
+  static constexpr int XW = 4;                   // x rows per warp: two per thread (register blocking), two lane halves
   static constexpr int R0 = T0 + 2 * M_;
-  static constexpr int NCW = R0 / 2;             // consumer warps, two x rows each
-  static constexpr int W = ZS + 2 * M_;          // register window (cells)
+  static constexpr int NCW = R0 / XW;            // consumer warps
+  static constexpr int W = ZS + 2 * M_;          // register window (cells) per row
   static constexpr int NFL = (W + ZS - 1) / ZS;  // flushes until a touched window is all zero again
-  static_assert(T1 >= 1 && R0 % 2 == 0 && W % ZS == 0 && ZS % ZB == 0 && T0 <= SUB, "unsupported cutoff");
+  static constexpr int XLEAD = XW - 1;           // zero padding in front of the x weights
+  static_assert(T1 >= 1 && R0 % XW == 0 && W % ZB == 0 && ZS % ZB == 0 && T0 <= SUB, "unsupported cutoff");
 };
 
 struct Zm2Geom {
@@ -47,7 +49,8 @@ struct Zm2Geom {
 };
 
 // Node-table row (units of R).  hdr = 8 ints {-dx*sizeof(R), -dy*sizeof(R), dz, dx, node index j, 0, 0, 0};
-// X = [0, psi_x[0..C), 0...], Y = [0 x (T1-1), psi_y[0..C), 0 x (T1-1)...], Z = psi_z[0..C) (zero padded);
+// X = [0 x XLEAD, psi_x[0..C), 0 x XLEAD...], Y = [0 x (T1-1), psi_y[0..C), 0 x (T1-1)...], Z = [0 x dz, psi_z[0..C), 0...] of length W: the z weights
+// already aligned with the register window of the node's sub-chunk, so the kernels need no per-node dispatch on dz;
 // the same three rows of dpsi when GRAD; vals = f (and grad_f) of the node for the adjoint.
 template <class R, int M_, bool GRAD, bool VALS, bool CPLX> struct Zm2Row {
   typedef Zm2Cfg<M_> Cfg;
@@ -55,7 +58,7 @@ template <class R, int M_, bool GRAD, bool VALS, bool CPLX> struct Zm2Row {
   static constexpr int up(int v) { return (v + AL - 1) / AL * AL; }
   static constexpr int C = Cfg::C;
   static constexpr int HDR = 32 / (int)sizeof(R);
-  static constexpr int XP = up(C + 2), YP = up(C + 2 * (Cfg::T1 - 1)), ZP = up(C);
+  static constexpr int XP = up(C + 2 * Cfg::XLEAD), YP = up(C + 2 * (Cfg::T1 - 1)), ZP = up(Cfg::W);
   static constexpr int oX = HDR, oY = oX + XP, oZ = oY + YP;
   static constexpr int oDX = oZ + ZP, oDY = oDX + XP, oDZ = oDY + YP;
   static constexpr int oV = GRAD ? oDZ + ZP : oZ + ZP;
@@ -145,14 +148,14 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
     R *row = rows + (size_t)ln * Row::ROWLEN;
     const int off = t == 0 ? Row::oX : (t == 1 ? Row::oY : Row::oZ);
     const int len = t == 0 ? Row::XP : (t == 1 ? Row::YP : Row::ZP);
-    const int lead = t == 0 ? 1 : (t == 1 ? Cfg::T1 - 1 : 0);
+    const int cell = (int)flv - g.los[t];
+    const int T = t == 0 ? Cfg::T0 : (t == 1 ? Cfg::T1 : Cfg::ZS);
+    const int d = cell - (cell / T) * T;
+    const int lead = t == 0 ? Cfg::XLEAD : (t == 1 ? Cfg::T1 - 1 : min(max(d, 0), Cfg::ZS - 1));
     for (int i = 0; i < len; i++) { row[off + i] = (R)0; if (GRAD) row[off + (Row::oDX - Row::oX) + i] = (R)0; }
 #pragma unroll
     for (int s = 0; s < C; s++) { row[off + lead + s] = psi[s]; if (GRAD) row[off + (Row::oDX - Row::oX) + lead + s] = dpsi[s]; }
     // cell offset inside the (T0, T1, ZS) tile
-    const int cell = (int)flv - g.los[t];
-    const int T = t == 0 ? Cfg::T0 : (t == 1 ? Cfg::T1 : Cfg::ZS);
-    const int d = cell - (cell / T) * T;
     int *h = reinterpret_cast<int *>(row);
     if (t == 0) { h[0] = -d * (int)sizeof(R); h[3] = d; h[4] = j; }
     else if (t == 1) { h[1] = -d * (int)sizeof(R); h[5] = 0; }
@@ -179,7 +182,8 @@ template <class R, bool CPLX, int M_, bool GRAD> struct Zm2Smem {
   typedef Zm2Cfg<M_> Cfg;
   typedef Zm2Row<R, M_, GRAD, true, CPLX> RowS;
   typedef Zm2Row<R, M_, GRAD, false, CPLX> RowG;
-  static constexpr int WARP_BOX = 32 * Cfg::ZS * (int)sizeof(Cell);       // bytes one warp stages per window advance
+  static constexpr int WARP_ROWS = Cfg::XW * 16;                           // grid rows one warp owns
+  static constexpr int WARP_BOX = WARP_ROWS * Cfg::ZS * (int)sizeof(Cell); // bytes one warp stages per window advance
   // scatter: two staging buffers per warp, ring of S chunks of GB nodes
   static constexpr int SS = 4, SGB = 32;
   static constexpr int s_stage = kZm2HdrBytes + SGB * RowS::ROWBYTES;
@@ -195,7 +199,7 @@ template <class R, bool CPLX, int M_, bool GRAD> struct Zm2Smem {
   static constexpr int g_off_part = g_off_ring + GS * g_stage;
   static constexpr int g_off_bar = g_off_part + GP * GGB * PN * (int)sizeof(Cell);
   static constexpr int gather = g_off_bar + (2 * GS + 2 * GP + Cfg::NCW) * 8;
-  static_assert(s_stage % 16 == 0 && g_stage % 16 == 0 && s_off_ring % 128 == 0 && g_off_ring % 128 == 0, "alignment");
+  static_assert(s_stage % 16 == 0 && g_stage % 16 == 0 && s_off_ring % 128 == 0 && g_off_ring % 128 == 0 && WARP_BOX % 1024 == 0, "alignment");
   static_assert(scatter <= 232448 && gather <= 232448, "shared-memory budget of one CTA exceeded");
 };
 
@@ -224,16 +228,13 @@ __device__ __forceinline__ void zm2_acc(Cell (&win)[W], const R (&wz)[ZP], const
 }
 template <int D, int C, bool GRAD, class R, class Cell, int W, int ZP>
 __device__ __forceinline__ void zm2_dot(const Cell (&win)[W], const R (&wz)[ZP], const R (&dwz)[ZP], Cell &t, Cell &td) {
-  Cell t1, td1;
+  Cell t1, td1;    // two accumulation chains per sum
   zero_cell(t); zero_cell(td); zero_cell(t1); zero_cell(td1);
 #pragma unroll
-  for (int k = 0; k + 1 < C; k += 2) {
-    fma_cell(t, wz[k], win[D + k]);
-    fma_cell(t1, wz[k + 1], win[D + k + 1]);
-    if (GRAD) { fma_cell(td, dwz[k], win[D + k]); fma_cell(td1, dwz[k + 1], win[D + k + 1]); }
+  for (int k = 0; k < C; k++) {
+    if (k & 1) { fma_cell(t1, wz[k], win[D + k]); if (GRAD) fma_cell(td1, dwz[k], win[D + k]); }
+    else { fma_cell(t, wz[k], win[D + k]); if (GRAD) fma_cell(td, dwz[k], win[D + k]); }
   }
-  fma_cell(t, wz[C - 1], win[D + C - 1]);
-  if (GRAD) fma_cell(td, dwz[C - 1], win[D + C - 1]);
   add_cell(t, t1);
   if (GRAD) add_cell(td, td1);
 }
@@ -305,6 +306,39 @@ __device__ __forceinline__ void zm2_produce(unsigned char *ring, unsigned long l
 }
 
 // ------------------------------------------------------------------------------------------------
+// staging layout: one TMA box is [XW][16][ZB] cells, z innermost; with 64- or 32-byte box rows the tensor map uses the
+// matching shared-memory swizzle so that the 16-byte chunks a quarter warp touches fall into different banks
+// ------------------------------------------------------------------------------------------------
+template <int IB> __device__ __forceinline__ int zm2_swz(int byte_off) {
+  constexpr int mask = IB == 64 ? 3 : (IB == 32 ? 1 : 0);
+  return byte_off ^ (((byte_off >> 7) & mask) << 4);
+}
+template <class Cell, int ZB> __device__ __forceinline__ Cell *zm2_stg(void *buf, int rho, int k) {
+  constexpr int IB = ZB * (int)sizeof(Cell);
+  return reinterpret_cast<Cell *>(reinterpret_cast<unsigned char *>(buf) + zm2_swz<IB>(rho * IB + k * (int)sizeof(Cell)));
+}
+template <class Cell, int ZB> constexpr int zm2_swizzle_mode() {   // 0 none, 1 = 32 B, 2 = 64 B
+  return ZB * (int)sizeof(Cell) == 64 ? 2 : (ZB * (int)sizeof(Cell) == 32 ? 1 : 0);
+}
+
+template <class R, int ZP, bool GRAD, class Row>
+__device__ __forceinline__ void zm2_load_wz(const R *rr, R (&wz)[ZP], R (&dwz)[ZP]) {
+  constexpr int SZ = (int)sizeof(R);
+#pragma unroll
+  for (int k = 0; k < ZP; k += 16 / SZ) {
+    if constexpr (SZ == 8) {
+      const double2 w = *reinterpret_cast<const double2 *>(rr + Row::oZ + k);
+      wz[k] = w.x; wz[k + 1] = w.y;
+      if (GRAD) { const double2 d = *reinterpret_cast<const double2 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; }
+    } else {
+      const float4 w = *reinterpret_cast<const float4 *>(rr + Row::oZ + k);
+      wz[k] = w.x; wz[k + 1] = w.y; wz[k + 2] = w.z; wz[k + 3] = w.w;
+      if (GRAD) { const float4 d = *reinterpret_cast<const float4 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; dwz[k + 2] = d.z; dwz[k + 3] = d.w; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // scatter (adjoint B^T)
 // ------------------------------------------------------------------------------------------------
 template <class R, bool CPLX, int M_, bool GRAD>
@@ -314,9 +348,9 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
   typedef Zm2Cfg<M_> Cfg;
   typedef Zm2Smem<R, CPLX, M_, GRAD> Sm;
   typedef typename Sm::RowS Row;
-  constexpr int C = Cfg::C, T0 = Cfg::T0, T1 = Cfg::T1, ZS = Cfg::ZS, ZB = Cfg::ZB, W = Cfg::W, NCW = Cfg::NCW;
+  constexpr int C = Cfg::C, T0 = Cfg::T0, T1 = Cfg::T1, ZS = Cfg::ZS, ZB = Cfg::ZB, W = Cfg::W, NCW = Cfg::NCW, XW = Cfg::XW;
   constexpr int NCOMP = CPLX ? 2 : 1, S = Sm::SS, GB = Sm::SGB, ROWBYTES = Row::ROWBYTES, STAGE = Sm::s_stage, ZP = Row::ZP;
-  constexpr int SZ = (int)sizeof(R);
+  constexpr int SZ = (int)sizeof(R), WROWS = Sm::WARP_ROWS, BOXB = WROWS * ZB * (int)sizeof(Cell);
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *ring = smem_raw + Sm::s_off_ring;
@@ -341,50 +375,57 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
   }
 
   const int cx = col / zg.nc[1], cy = col - cx * zg.nc[1];
-  const int o0 = cx * T0 + 2 * warp, o1 = cy * T1;
-  const int r0 = 2 * warp + (lane >> 4), r1 = lane & 15;
-  const int aX = (Row::oX + 1 + r0) * SZ, aY = (Row::oY + T1 - 1 + r1) * SZ;
+  const int o0 = cx * T0 + XW * warp, o1 = cy * T1;
+  const int hlf = lane >> 4, r1 = lane & 15;
+  const int rbase = XW * warp + 2 * hlf;                 // the first of my two x rows
+  const int rho0 = (2 * hlf) * 16 + r1, rho1 = rho0 + 16;   // their rows inside the warp's TMA box
+  const int aX = (Row::oX + Cfg::XLEAD + rbase) * SZ, aY = (Row::oY + T1 - 1 + r1) * SZ;
   constexpr int dOff = (Row::oDX - Row::oX) * SZ;
-  const int dxlo = max(0, 2 * warp - (C - 1)), dxhi1 = min(T0 - 1, 2 * warp + 1) + 1;
-  Cell *mystg = reinterpret_cast<Cell *>(smem_raw) + (size_t)warp * 2 * 32 * ZS;
+  const int dxlo = max(0, XW * warp - (C - 1)), dxhi1 = min(T0 - 1, XW * warp + XW - 1) + 1;
+  unsigned char *mystg = smem_raw + (size_t)warp * 2 * Sm::WARP_BOX;
 
-  Cell win[W];
+  Cell wa[W], wb[W];
 #pragma unroll
-  for (int i = 0; i < W; i++) zero_cell(win[i]);
+  for (int i = 0; i < W; i++) { zero_cell(wa[i]); zero_cell(wb[i]); }
   int cur = tz0, dirty = 0, nfl = 0;
 
-  // the first ZS cells of the window are final: reduce-add them into the grid, advance the window
+  // the first ZS cells of the windows are final: reduce-add them into the grid, advance the windows
   auto flush_advance = [&]() {
-    Cell *sb = mystg + (nfl & 1) * (32 * ZS);
+    unsigned char *sb = mystg + (nfl & 1) * Sm::WARP_BOX;
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box issued two flushes ago was read
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < ZS; q++) sb[(q / ZB) * (32 * ZB) + lane * ZB + (q % ZB)] = win[q];
+    for (int q = 0; q < ZS; q++) {
+      *zm2_stg<Cell, ZB>(sb + (q / ZB) * BOXB, rho0, q % ZB) = wa[q];
+      *zm2_stg<Cell, ZB>(sb + (q / ZB) * BOXB, rho1, q % ZB) = wb[q];
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
 #pragma unroll
-      for (int b = 0; b < ZS / ZB; b++) tma_reduce_add_3d(sb + b * (32 * ZB), &tmap, (cur * ZS + b * ZB) * NCOMP, o1, o0);
+      for (int b = 0; b < ZS / ZB; b++) tma_reduce_add_3d(sb + b * BOXB, &tmap, (cur * ZS + b * ZB) * NCOMP, o1, o0);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     nfl++;
 #pragma unroll
-    for (int i = 0; i < W - ZS; i++) win[i] = win[i + ZS];
+    for (int i = 0; i < W - ZS; i++) { wa[i] = wa[i + ZS]; wb[i] = wb[i + ZS]; }
 #pragma unroll
-    for (int i = W - ZS; i < W; i++) zero_cell(win[i]);
+    for (int i = W - ZS; i < W; i++) { zero_cell(wa[i]); zero_cell(wb[i]); }
     cur++;
   };
 
   // operands of one node that depend on this thread's rows: x and y weights (and derivatives), node values
-  struct Ops { R w0, w1, dw0, dw1; Cell f, g0, g1, g2; };
+  struct Ops { R w0a, w0b, w1, dw0a, dw0b, dw1; Cell f, g0, g1, g2; };
   auto fetch = [&](const unsigned char *row, const int4 &hd, Ops &o) {
-    o.w0 = *reinterpret_cast<const R *>(row + aX + hd.x);
+    o.w0a = *reinterpret_cast<const R *>(row + aX + hd.x);
+    o.w0b = *reinterpret_cast<const R *>(row + aX + SZ + hd.x);
     o.w1 = *reinterpret_cast<const R *>(row + aY + hd.y);
     const R *v = reinterpret_cast<const R *>(row) + Row::oV;
     Cell z; zero_cell(z);
     o.f = load_in(v, z);
     if (GRAD) {
-      o.dw0 = *reinterpret_cast<const R *>(row + aX + dOff + hd.x);
+      o.dw0a = *reinterpret_cast<const R *>(row + aX + dOff + hd.x);
+      o.dw0b = *reinterpret_cast<const R *>(row + aX + SZ + dOff + hd.x);
       o.dw1 = *reinterpret_cast<const R *>(row + aY + dOff + hd.y);
       o.g0 = load_in(v + NCOMP, z); o.g1 = load_in(v + 2 * NCOMP, z); o.g2 = load_in(v + 3 * NCOMP, z);
     }
@@ -412,36 +453,26 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
       Ops op;
       fetch(row, hd, op);
       for (int i = lo; i < hi; i++) {
-        const R *rr = reinterpret_cast<const R *>(row);
         R wz[ZP], dwz[ZP];
-#pragma unroll
-        for (int k = 0; k < ZP; k += 16 / SZ) {
-          typedef typename WPair<R>::type P2;
-          if constexpr (SZ == 8) {
-            const P2 w = *reinterpret_cast<const P2 *>(rr + Row::oZ + k);
-            wz[k] = w.x; wz[k + 1] = w.y;
-            if (GRAD) { const P2 d = *reinterpret_cast<const P2 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; }
-          } else {
-            const float4 w = *reinterpret_cast<const float4 *>(rr + Row::oZ + k);
-            wz[k] = w.x; wz[k + 1] = w.y; wz[k + 2] = w.z; wz[k + 3] = w.w;
-            if (GRAD) { const float4 d = *reinterpret_cast<const float4 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; dwz[k + 2] = d.z; dwz[k + 3] = d.w; }
-          }
-        }
-        Cell A = scale_cell(op.w0 * op.w1, op.f), B;
-        zero_cell(B);
+        zm2_load_wz<R, ZP, GRAD, Row>(reinterpret_cast<const R *>(row), wz, dwz);
+        // per-row amplitudes: A_e = w0_e (w1 f + dw1 g1) + dw0_e (w1 g0), B_e = w0_e (w1 g2)
+        Cell u = scale_cell(op.w1, op.f), A0, A1, B0, B1;
+        zero_cell(B0); zero_cell(B1);
         if (GRAD) {
-          fma_cell(A, op.dw0 * op.w1, op.g0);
-          fma_cell(A, op.w0 * op.dw1, op.g1);
-          B = scale_cell(op.w0 * op.w1, op.g2);
+          fma_cell(u, op.dw1, op.g1);
+          const Cell v = scale_cell(op.w1, op.g0), sg = scale_cell(op.w1, op.g2);
+          A0 = scale_cell(op.w0a, u); fma_cell(A0, op.dw0a, v);
+          A1 = scale_cell(op.w0b, u); fma_cell(A1, op.dw0b, v);
+          B0 = scale_cell(op.w0a, sg); B1 = scale_cell(op.w0b, sg);
+        } else {
+          A0 = scale_cell(op.w0a, u); A1 = scale_cell(op.w0b, u);
         }
-        const int dz = hd.z;
         // prefetch
         const unsigned char *row2 = row1 + ROWBYTES < last ? row1 + ROWBYTES : last;
         const int4 hn2 = *reinterpret_cast<const int4 *>(row2);
         fetch(row1, hn, op);
-#define ZM2_CALL(D) zm2_acc<D, C, GRAD>(win, wz, dwz, A, B)
-        ZM2_TREE(dz, ZM2_CALL);
-#undef ZM2_CALL
+        zm2_acc<0, W, GRAD>(wa, wz, dwz, A0, B0);
+        zm2_acc<0, W, GRAD>(wb, wz, dwz, A1, B1);
         hd = hn; hn = hn2; row = row1; row1 = row2;
       }
       dirty = Cfg::NFL;
@@ -494,13 +525,13 @@ __device__ __forceinline__ void zm2_reduce_node(const unsigned char *row, const 
   for (int it = 0; it < (C + 1) / 2; it++) {
     const int i0 = 2 * it + (lane >> 4);
     const bool ok = (2 * it + 1 < C) || i0 < C;
-    const R w0 = rr[Row::oX + 1 + i0];                       // zero beyond the last tap
+    const R w0 = rr[Row::oX + Cfg::XLEAD + i0];                       // zero beyond the last tap
     Cell t, td;
     zero_cell(t); zero_cell(td);
     if (ok) { t = pp[32 * it + lane]; if (GRAD) td = pp[C * 16 + 32 * it + lane]; }
     fma_cell(s, w0, t);
     if (GRAD) {
-      const R dw0 = rr[Row::oDX + 1 + i0];
+      const R dw0 = rr[Row::oDX + Cfg::XLEAD + i0];
       fma_cell(sd, dw0, t);
       fma_cell(u, w0, td);
     }
@@ -536,10 +567,10 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
   typedef Zm2Cfg<M_> Cfg;
   typedef Zm2Smem<R, CPLX, M_, GRAD> Sm;
   typedef typename Sm::RowG Row;
-  constexpr int C = Cfg::C, T0 = Cfg::T0, T1 = Cfg::T1, ZS = Cfg::ZS, ZB = Cfg::ZB, W = Cfg::W, NCW = Cfg::NCW;
+  constexpr int C = Cfg::C, T0 = Cfg::T0, T1 = Cfg::T1, ZS = Cfg::ZS, ZB = Cfg::ZB, W = Cfg::W, NCW = Cfg::NCW, XW = Cfg::XW;
   constexpr int NCOMP = CPLX ? 2 : 1, S = Sm::GS, P = Sm::GP, GB = Sm::GGB, ROWBYTES = Row::ROWBYTES, STAGE = Sm::g_stage, PN = Sm::PN;
-  constexpr int ZP = Row::ZP, SZ = (int)sizeof(R);
-  constexpr unsigned BOXB = 32 * ZB * (unsigned)sizeof(Cell);
+  constexpr int ZP = Row::ZP, WROWS = Sm::WARP_ROWS;
+  constexpr unsigned BOXB = WROWS * ZB * (unsigned)sizeof(Cell);
   static_assert(S >= 3 && P >= 2, "ring / partial stages too shallow for the deferred reduction");
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -572,24 +603,26 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
 
   // ---- consumer warps ----
   const int cx = col / zg.nc[1], cy = col - cx * zg.nc[1];
-  const int o0 = cx * T0 + 2 * warp, o1 = cy * T1;
-  const int r0 = 2 * warp + (lane >> 4), r1 = lane & 15;
-  const int dxlo = max(0, 2 * warp - (C - 1)), dxhi1 = min(T0 - 1, 2 * warp + 1) + 1;
-  Cell *mystg = reinterpret_cast<Cell *>(smem_raw) + (size_t)warp * 32 * ZS;
+  const int o0 = cx * T0 + XW * warp, o1 = cy * T1;
+  const int hlf = lane >> 4, r1 = lane & 15;
+  const int rbase = XW * warp + 2 * hlf;
+  const int rho0 = (2 * hlf) * 16 + r1, rho1 = rho0 + 16;
+  const int dxlo = max(0, XW * warp - (C - 1)), dxhi1 = min(T0 - 1, XW * warp + XW - 1) + 1;
+  unsigned char *mystg = smem_raw + (size_t)warp * Sm::WARP_BOX;
   unsigned long long *mybar = &wbar[warp];
   unsigned wph = 0;
 
-  Cell win[W];
-  int cur = INT_MIN / 2;       // sub-chunk whose cells [cur*ZS, cur*ZS + W) are in the window
+  Cell wa[W], wb[W];
+  int cur = INT_MIN / 2;       // sub-chunk whose cells [cur*ZS, cur*ZS + W) are in the windows
   bool pending = false;        // a load of the cells [cur*ZS + W, +ZS) is in flight
 
-  auto issue = [&](int zc, int nbox) {       // lane 0: nbox TMA boxes [2][16][ZB] starting at cell zc
+  auto issue = [&](int zc, int nbox) {       // lane 0: nbox TMA boxes [XW][16][ZB] starting at cell zc
     if (lane == 0) {
       mbar_expect_tx(mybar, BOXB * (unsigned)nbox);
-      for (int b = 0; b < nbox; b++) tma_load_3d(mystg + b * (32 * ZB), &tmap, (zc + b * ZB) * NCOMP, o1, o0, mybar);
+      for (int b = 0; b < nbox; b++) tma_load_3d(mystg + b * BOXB, &tmap, (zc + b * ZB) * NCOMP, o1, o0, mybar);
     }
   };
-  // wait for the staged boxes and copy my row's cells into the window.  The vote consumes the loaded values, so every
+  // wait for the staged boxes and copy my rows' cells into the windows.  The vote consumes the loaded values, so every
   // lane's shared-memory reads have RETURNED before lane 0 may re-arm the staging buffer with the next TMA load.
   auto take = [&](auto first_tag, auto nbox_tag) {
     constexpr int FIRST = decltype(first_tag)::value, NBOX = decltype(nbox_tag)::value;
@@ -600,8 +633,9 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
     for (int b = 0; b < NBOX; b++)
 #pragma unroll
       for (int q = 0; q < ZB; q++) {
-        win[FIRST + b * ZB + q] = mystg[b * (32 * ZB) + lane * ZB + q];
-        nan |= cell_is_nan(win[FIRST + b * ZB + q]);
+        wa[FIRST + b * ZB + q] = *zm2_stg<Cell, ZB>(mystg + b * BOXB, rho0, q);
+        wb[FIRST + b * ZB + q] = *zm2_stg<Cell, ZB>(mystg + b * BOXB, rho1, q);
+        nan |= cell_is_nan(wa[FIRST + b * ZB + q]) | cell_is_nan(wb[FIRST + b * ZB + q]);
       }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     (void)warp_any_volatile(nan);
@@ -609,25 +643,27 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
   auto drop_pending = [&]() {
     if (pending) { mbar_wait(mybar, wph); wph ^= 1u; pending = false; }
   };
-  auto reload = [&](int tz) {      // whole window at sub-chunk tz, then prefetch the next advance
+  auto reload = [&](int tz) {      // whole windows at sub-chunk tz, then prefetch the next advance
     drop_pending();
     const int z0 = tz * ZS;
     constexpr int PER = ZS / ZB;   // boxes per staging buffer
-    static_assert(W % ZS == 0 && W / ZS <= 6, "window reload written for at most six whole rounds");
-    issue(z0, PER);
-    take(std::integral_constant<int, 0>(), std::integral_constant<int, PER>());
-    if constexpr (W / ZS > 1) { issue(z0 + ZS, PER); take(std::integral_constant<int, (W / ZS > 1) ? ZS : 0>(), std::integral_constant<int, PER>()); }
-    if constexpr (W / ZS > 2) { issue(z0 + 2 * ZS, PER); take(std::integral_constant<int, (W / ZS > 2) ? 2 * ZS : 0>(), std::integral_constant<int, PER>()); }
-    if constexpr (W / ZS > 3) { issue(z0 + 3 * ZS, PER); take(std::integral_constant<int, (W / ZS > 3) ? 3 * ZS : 0>(), std::integral_constant<int, PER>()); }
-    if constexpr (W / ZS > 4) { issue(z0 + 4 * ZS, PER); take(std::integral_constant<int, (W / ZS > 4) ? 4 * ZS : 0>(), std::integral_constant<int, PER>()); }
-    if constexpr (W / ZS > 5) { issue(z0 + 5 * ZS, PER); take(std::integral_constant<int, (W / ZS > 5) ? 5 * ZS : 0>(), std::integral_constant<int, PER>()); }
+    constexpr int NB = W / ZB;     // boxes of the whole window
+    static_assert(NB <= 6 * PER, "window reload written for at most six rounds");
+#define ZM2_ROUND(r)                                                                                                   \
+    if constexpr ((r) * PER < NB) {                                                                                    \
+      constexpr int nb_ = (NB - (r) * PER) < PER ? (NB - (r) * PER) : PER;                                             \
+      issue(z0 + (r) * ZS, nb_);                                                                                       \
+      take(std::integral_constant<int, ((r) * PER < NB) ? (r) * ZS : 0>(), std::integral_constant<int, nb_>());        \
+    }
+    ZM2_ROUND(0) ZM2_ROUND(1) ZM2_ROUND(2) ZM2_ROUND(3) ZM2_ROUND(4) ZM2_ROUND(5)
+#undef ZM2_ROUND
     cur = tz;
     issue(z0 + W, PER);
     pending = true;
   };
   auto advance1 = [&]() {
 #pragma unroll
-    for (int i = 0; i < W - ZS; i++) win[i] = win[i + ZS];
+    for (int i = 0; i < W - ZS; i++) { wa[i] = wa[i + ZS]; wb[i] = wb[i + ZS]; }
     take(std::integral_constant<int, W - ZS>(), std::integral_constant<int, ZS / ZB>());
     cur++;
     issue(cur * ZS + W, ZS / ZB);
@@ -652,7 +688,7 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
     if (lane == 0) { mbar_arrive(&pempty[ps]); mbar_arrive(&empty[st]); }
   };
 
-  const int aP = (r0 * 16 + r1);
+  const int aP = (rbase * 16 + r1);
   int kb = 0;
   for (;; kb++) {
     const int st = kb % S, ps = kb % P;
@@ -674,34 +710,17 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
       Cell *pb = part + (size_t)(ps * GB + lo) * PN + aP;
       int4 hd = *reinterpret_cast<const int4 *>(row);
       for (int i = lo; i < hi; i++, pb += PN) {
-        const R *rr = reinterpret_cast<const R *>(row);
         R wz[ZP], dwz[ZP];
-#pragma unroll
-        for (int k = 0; k < ZP; k += 16 / SZ) {
-          typedef typename WPair<R>::type P2;
-          if constexpr (SZ == 8) {
-            const P2 w = *reinterpret_cast<const P2 *>(rr + Row::oZ + k);
-            wz[k] = w.x; wz[k + 1] = w.y;
-            if (GRAD) { const P2 d = *reinterpret_cast<const P2 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; }
-          } else {
-            const float4 w = *reinterpret_cast<const float4 *>(rr + Row::oZ + k);
-            wz[k] = w.x; wz[k + 1] = w.y; wz[k + 2] = w.z; wz[k + 3] = w.w;
-            if (GRAD) { const float4 d = *reinterpret_cast<const float4 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; dwz[k + 2] = d.z; dwz[k + 3] = d.w; }
-          }
-        }
+        zm2_load_wz<R, ZP, GRAD, Row>(reinterpret_cast<const R *>(row), wz, dwz);
         const unsigned char *row1 = row + ROWBYTES < last ? row + ROWBYTES : last;
         const int4 hn = *reinterpret_cast<const int4 *>(row1);       // prefetch the next header
-        Cell t, td;
-        const int dz = hd.z;
-#define ZM2_CALL(D) zm2_dot<D, C, GRAD>(win, wz, dwz, t, td)
-        ZM2_TREE(dz, ZM2_CALL);
-#undef ZM2_CALL
-        const int i0 = r0 - hd.w;
-        if ((unsigned)i0 < (unsigned)C) {
-          Cell *p = pb - hd.w * 16;
-          p[0] = t;
-          if (GRAD) p[C * 16] = td;
-        }
+        Cell ta, tda, tb, tdb;
+        zm2_dot<0, W, GRAD>(wa, wz, dwz, ta, tda);
+        zm2_dot<0, W, GRAD>(wb, wz, dwz, tb, tdb);
+        const int i0 = rbase - hd.w;
+        Cell *p = pb - hd.w * 16;
+        if ((unsigned)i0 < (unsigned)C) { p[0] = ta; if (GRAD) p[C * 16] = tda; }
+        if ((unsigned)(i0 + 1) < (unsigned)C) { p[16] = tb; if (GRAD) p[C * 16 + 16] = tdb; }
         hd = hn; row = row1;
       }
     }
