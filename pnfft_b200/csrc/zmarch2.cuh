@@ -321,21 +321,17 @@ template <class Cell, int ZB> constexpr int zm2_swizzle_mode() {   // 0 none, 1 
   return ZB * (int)sizeof(Cell) == 64 ? 2 : (ZB * (int)sizeof(Cell) == 32 ? 1 : 0);
 }
 
-template <class R, int ZP, bool GRAD, class Row>
-__device__ __forceinline__ void zm2_load_wz(const R *rr, R (&wz)[ZP], R (&dwz)[ZP]) {
-  constexpr int SZ = (int)sizeof(R);
-#pragma unroll
-  for (int k = 0; k < ZP; k += 16 / SZ) {
-    if constexpr (SZ == 8) {
-      const double2 w = *reinterpret_cast<const double2 *>(rr + Row::oZ + k);
-      wz[k] = w.x; wz[k + 1] = w.y;
-      if (GRAD) { const double2 d = *reinterpret_cast<const double2 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; }
-    } else {
-      const float4 w = *reinterpret_cast<const float4 *>(rr + Row::oZ + k);
-      wz[k] = w.x; wz[k + 1] = w.y; wz[k + 2] = w.z; wz[k + 3] = w.w;
-      if (GRAD) { const float4 d = *reinterpret_cast<const float4 *>(rr + Row::oDZ + k); dwz[k] = d.x; dwz[k + 1] = d.y; dwz[k + 2] = d.z; dwz[k + 3] = d.w; }
-    }
-  }
+// The z weights of a node stream through a small rotating set of 16-byte register "quads" (2 doubles / 4 floats):
+// slot j % D holds quad j; as soon as a quad is consumed its slot is refilled with quad j + D of the same node or, past
+// the end of the row, with the first quads of the NEXT node, so the shared-memory latency never drains the pipeline.
+template <class R> struct ZQuad;
+template <> struct ZQuad<double> { typedef double2 type; static constexpr int PER = 2; };
+template <> struct ZQuad<float> { typedef float4 type; static constexpr int PER = 4; };
+__device__ __forceinline__ double zq_get(const double2 &q, int e) { return e == 0 ? q.x : q.y; }
+__device__ __forceinline__ float zq_get(const float4 &q, int e) { return e == 0 ? q.x : (e == 1 ? q.y : (e == 2 ? q.z : q.w)); }
+template <int NQT, bool GRAD> constexpr int zm2_depth() {
+  constexpr int dmax = GRAD ? 2 : 4;
+  return (dmax >= 4 && NQT % 4 == 0) ? 4 : ((dmax >= 3 && NQT % 3 == 0) ? 3 : ((NQT % 2 == 0) ? 2 : 1));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -446,15 +442,21 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
       }
       const unsigned char *row = sp + kZm2HdrBytes + (size_t)lo * ROWBYTES;
       const unsigned char *last = sp + kZm2HdrBytes + (size_t)(hi - 1) * ROWBYTES;
-      // software pipeline: header two nodes ahead, thread-dependent operands one node ahead
+      // software pipeline: header two nodes ahead, thread-dependent operands one node ahead, z weights streamed
+      typedef typename ZQuad<R>::type Quad;
+      constexpr int PER = ZQuad<R>::PER, NQT = ZP / PER, D = zm2_depth<NQT, true>();   // two quads in flight: the windows leave no room for more
       int4 hd = *reinterpret_cast<const int4 *>(row);
       const unsigned char *row1 = row + ROWBYTES < last ? row + ROWBYTES : last;
       int4 hn = *reinterpret_cast<const int4 *>(row1);
       Ops op;
       fetch(row, hd, op);
+      Quad Q[D], DQ[D];
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        Q[j] = *reinterpret_cast<const Quad *>(row + (Row::oZ + j * PER) * SZ);
+        if (GRAD) DQ[j] = *reinterpret_cast<const Quad *>(row + (Row::oDZ + j * PER) * SZ);
+      }
       for (int i = lo; i < hi; i++) {
-        R wz[ZP], dwz[ZP];
-        zm2_load_wz<R, ZP, GRAD, Row>(reinterpret_cast<const R *>(row), wz, dwz);
         // per-row amplitudes: A_e = w0_e (w1 f + dw1 g1) + dw0_e (w1 g0), B_e = w0_e (w1 g2)
         Cell u = scale_cell(op.w1, op.f), A0, A1, B0, B1;
         zero_cell(B0); zero_cell(B1);
@@ -471,8 +473,25 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
         const unsigned char *row2 = row1 + ROWBYTES < last ? row1 + ROWBYTES : last;
         const int4 hn2 = *reinterpret_cast<const int4 *>(row2);
         fetch(row1, hn, op);
-        zm2_acc<0, W, GRAD>(wa, wz, dwz, A0, B0);
-        zm2_acc<0, W, GRAD>(wb, wz, dwz, A1, B1);
+#pragma unroll
+        for (int j = 0; j < NQT; j++) {
+          const Quad w = Q[j % D];
+          Quad dw = w;
+          if (GRAD) dw = DQ[j % D];
+          const unsigned char *src = (j + D < NQT) ? row : row1;
+          const int jq = (j + D < NQT) ? j + D : j + D - NQT;
+          Q[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oZ + jq * PER) * SZ);
+          if (GRAD) DQ[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oDZ + jq * PER) * SZ);
+#pragma unroll
+          for (int e = 0; e < PER; e++) {
+            const int k = j * PER + e;
+            if (k < W) {
+              fma_cell(wa[k], zq_get(w, e), A0);
+              fma_cell(wb[k], zq_get(w, e), A1);
+              if (GRAD) { fma_cell(wa[k], zq_get(dw, e), B0); fma_cell(wb[k], zq_get(dw, e), B1); }
+            }
+          }
+        }
         hd = hn; hn = hn2; row = row1; row1 = row2;
       }
       dirty = Cfg::NFL;
@@ -708,15 +727,45 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
       const unsigned char *row = sp + kZm2HdrBytes + (size_t)lo * ROWBYTES;
       const unsigned char *last = sp + kZm2HdrBytes + (size_t)(hi - 1) * ROWBYTES;
       Cell *pb = part + (size_t)(ps * GB + lo) * PN + aP;
+      typedef typename ZQuad<R>::type Quad;
+      constexpr int SZ = (int)sizeof(R), PER = ZQuad<R>::PER, NQT = ZP / PER, D = zm2_depth<NQT, GRAD>();
       int4 hd = *reinterpret_cast<const int4 *>(row);
+      Quad Q[D], DQ[D];
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        Q[j] = *reinterpret_cast<const Quad *>(row + (Row::oZ + j * PER) * SZ);
+        if (GRAD) DQ[j] = *reinterpret_cast<const Quad *>(row + (Row::oDZ + j * PER) * SZ);
+      }
       for (int i = lo; i < hi; i++, pb += PN) {
-        R wz[ZP], dwz[ZP];
-        zm2_load_wz<R, ZP, GRAD, Row>(reinterpret_cast<const R *>(row), wz, dwz);
         const unsigned char *row1 = row + ROWBYTES < last ? row + ROWBYTES : last;
         const int4 hn = *reinterpret_cast<const int4 *>(row1);       // prefetch the next header
-        Cell ta, tda, tb, tdb;
-        zm2_dot<0, W, GRAD>(wa, wz, dwz, ta, tda);
-        zm2_dot<0, W, GRAD>(wb, wz, dwz, tb, tdb);
+        Cell ta, tda, tb, tdb, ta1, tb1;     // F only: two chains per sum; with the gradient the four sums are chains enough
+        zero_cell(ta); zero_cell(tda); zero_cell(tb); zero_cell(tdb); zero_cell(ta1); zero_cell(tb1);
+#pragma unroll
+        for (int j = 0; j < NQT; j++) {
+          const Quad w = Q[j % D];
+          Quad dw = w;
+          if (GRAD) dw = DQ[j % D];
+          const unsigned char *src = (j + D < NQT) ? row : row1;
+          const int jq = (j + D < NQT) ? j + D : j + D - NQT;
+          Q[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oZ + jq * PER) * SZ);
+          if (GRAD) DQ[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oDZ + jq * PER) * SZ);
+#pragma unroll
+          for (int e = 0; e < PER; e++) {
+            const int k = j * PER + e;
+            if (k < W) {
+              if (GRAD) {
+                fma_cell(ta, zq_get(w, e), wa[k]); fma_cell(tb, zq_get(w, e), wb[k]);
+                fma_cell(tda, zq_get(dw, e), wa[k]); fma_cell(tdb, zq_get(dw, e), wb[k]);
+              } else if (k & 1) {
+                fma_cell(ta1, zq_get(w, e), wa[k]); fma_cell(tb1, zq_get(w, e), wb[k]);
+              } else {
+                fma_cell(ta, zq_get(w, e), wa[k]); fma_cell(tb, zq_get(w, e), wb[k]);
+              }
+            }
+          }
+        }
+        if (!GRAD) { add_cell(ta, ta1); add_cell(tb, tb1); }
         const int i0 = rbase - hd.w;
         Cell *p = pb - hd.w * 16;
         if ((unsigned)i0 < (unsigned)C) { p[0] = ta; if (GRAD) p[C * 16] = tda; }
