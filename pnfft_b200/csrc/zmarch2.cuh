@@ -24,15 +24,22 @@
 
 namespace pnb {
 
+#ifndef ZM2_PARK_NS
+#define ZM2_PARK_NS 500u
+#endif
+#ifndef ZM2_RPT
+#define ZM2_RPT 1
+#endif
 template <int M_> struct Zm2Cfg {
   static constexpr int C = 2 * M_ + 1;
   static constexpr int R1 = 16;                  // footprint rows along y: half a warp
   static constexpr int T1 = R1 - 2 * M_;         // column tile, cells (m=6: 4, m=4: 8)
-  static constexpr int T0 = 12;                  // R0 = 24 (m=6): 6 consumer warps of 4 x rows
+  static constexpr int RPT = ZM2_RPT;            // x rows per thread (register blocking)
+  static constexpr int T0 = RPT == 2 ? 12 : 10;  // R0 = 24 (m=6): 6 consumer warps of 4 x rows / R0 = 22: 11 warps of 2 rows
   static constexpr int SUB = 16;                 // x-offset bins per tile in the sort key (>= T0)
   static constexpr int ZS = 4;                   // z sub-chunk == window advance
   static constexpr int ZB = 4;                   // z extent of one TMA box
-  static constexpr int XW = 4;                   // x rows per warp: two per thread (register blocking), two lane halves
+  static constexpr int XW = 2 * RPT;             // x rows per warp: RPT per thread, two lane halves
   static constexpr int R0 = T0 + 2 * M_;
   static constexpr int NCW = R0 / XW;            // consumer warps
   static constexpr int W = ZS + 2 * M_;          // register window (cells) per row
@@ -199,7 +206,7 @@ template <class R, bool CPLX, int M_, bool GRAD> struct Zm2Smem {
   static constexpr int g_off_part = g_off_ring + GS * g_stage;
   static constexpr int g_off_bar = g_off_part + GP * GGB * PN * (int)sizeof(Cell);
   static constexpr int gather = g_off_bar + (2 * GS + 2 * GP + Cfg::NCW) * 8;
-  static_assert(s_stage % 16 == 0 && g_stage % 16 == 0 && s_off_ring % 128 == 0 && g_off_ring % 128 == 0 && WARP_BOX % 1024 == 0, "alignment");
+  static_assert(s_stage % 16 == 0 && g_stage % 16 == 0 && s_off_ring % 128 == 0 && g_off_ring % 128 == 0 && WARP_BOX % 512 == 0, "alignment");
   static_assert(scatter <= 232448 && gather <= 232448, "shared-memory budget of one CTA exceeded");
 };
 
@@ -213,7 +220,7 @@ __device__ __forceinline__ void mbar_wait_park(unsigned long long *bar, unsigned
       "@p bra DONEP_%=;\n"
       "bra WAITP_%=;\n"
       "DONEP_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(phase), "r"(20000u) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase), "r"(ZM2_PARK_NS) : "memory");
 }
 
 // z taps of one node from / into the register window; the z offset picks one of ZS statically indexed variants
@@ -373,16 +380,19 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
   const int cx = col / zg.nc[1], cy = col - cx * zg.nc[1];
   const int o0 = cx * T0 + XW * warp, o1 = cy * T1;
   const int hlf = lane >> 4, r1 = lane & 15;
-  const int rbase = XW * warp + 2 * hlf;                 // the first of my two x rows
-  const int rho0 = (2 * hlf) * 16 + r1, rho1 = rho0 + 16;   // their rows inside the warp's TMA box
+  constexpr int RPT = Cfg::RPT;
+  const int rbase = XW * warp + RPT * hlf;               // the first of my RPT x rows
+  const int rho0 = (RPT * hlf) * 16 + r1;                // its row inside the warp's TMA box (the next one is 16 further)
   const int aX = (Row::oX + Cfg::XLEAD + rbase) * SZ, aY = (Row::oY + T1 - 1 + r1) * SZ;
   constexpr int dOff = (Row::oDX - Row::oX) * SZ;
   const int dxlo = max(0, XW * warp - (C - 1)), dxhi1 = min(T0 - 1, XW * warp + XW - 1) + 1;
   unsigned char *mystg = smem_raw + (size_t)warp * 2 * Sm::WARP_BOX;
 
-  Cell wa[W], wb[W];
+  Cell win[RPT][W];
 #pragma unroll
-  for (int i = 0; i < W; i++) { zero_cell(wa[i]); zero_cell(wb[i]); }
+  for (int e = 0; e < RPT; e++)
+#pragma unroll
+    for (int i = 0; i < W; i++) zero_cell(win[e][i]);
   int cur = tz0, dirty = 0, nfl = 0;
 
   // the first ZS cells of the windows are final: reduce-add them into the grid, advance the windows
@@ -391,10 +401,9 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box issued two flushes ago was read
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < ZS; q++) {
-      *zm2_stg<Cell, ZB>(sb + (q / ZB) * BOXB, rho0, q % ZB) = wa[q];
-      *zm2_stg<Cell, ZB>(sb + (q / ZB) * BOXB, rho1, q % ZB) = wb[q];
-    }
+    for (int q = 0; q < ZS; q++)
+#pragma unroll
+      for (int e = 0; e < RPT; e++) *zm2_stg<Cell, ZB>(sb + (q / ZB) * BOXB, rho0 + 16 * e, q % ZB) = win[e][q];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
@@ -404,24 +413,27 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
     }
     nfl++;
 #pragma unroll
-    for (int i = 0; i < W - ZS; i++) { wa[i] = wa[i + ZS]; wb[i] = wb[i + ZS]; }
+    for (int e = 0; e < RPT; e++) {
 #pragma unroll
-    for (int i = W - ZS; i < W; i++) { zero_cell(wa[i]); zero_cell(wb[i]); }
+      for (int i = 0; i < W - ZS; i++) win[e][i] = win[e][i + ZS];
+#pragma unroll
+      for (int i = W - ZS; i < W; i++) zero_cell(win[e][i]);
+    }
     cur++;
   };
 
   // operands of one node that depend on this thread's rows: x and y weights (and derivatives), node values
-  struct Ops { R w0a, w0b, w1, dw0a, dw0b, dw1; Cell f, g0, g1, g2; };
+  struct Ops { R w0[RPT], w1, dw0[RPT], dw1; Cell f, g0, g1, g2; };
   auto fetch = [&](const unsigned char *row, const int4 &hd, Ops &o) {
-    o.w0a = *reinterpret_cast<const R *>(row + aX + hd.x);
-    o.w0b = *reinterpret_cast<const R *>(row + aX + SZ + hd.x);
+#pragma unroll
+    for (int e = 0; e < RPT; e++) o.w0[e] = *reinterpret_cast<const R *>(row + aX + e * SZ + hd.x);
     o.w1 = *reinterpret_cast<const R *>(row + aY + hd.y);
     const R *v = reinterpret_cast<const R *>(row) + Row::oV;
     Cell z; zero_cell(z);
     o.f = load_in(v, z);
     if (GRAD) {
-      o.dw0a = *reinterpret_cast<const R *>(row + aX + dOff + hd.x);
-      o.dw0b = *reinterpret_cast<const R *>(row + aX + SZ + dOff + hd.x);
+#pragma unroll
+      for (int e = 0; e < RPT; e++) o.dw0[e] = *reinterpret_cast<const R *>(row + aX + e * SZ + dOff + hd.x);
       o.dw1 = *reinterpret_cast<const R *>(row + aY + dOff + hd.y);
       o.g0 = load_in(v + NCOMP, z); o.g1 = load_in(v + 2 * NCOMP, z); o.g2 = load_in(v + 3 * NCOMP, z);
     }
@@ -458,16 +470,15 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
       }
       for (int i = lo; i < hi; i++) {
         // per-row amplitudes: A_e = w0_e (w1 f + dw1 g1) + dw0_e (w1 g0), B_e = w0_e (w1 g2)
-        Cell u = scale_cell(op.w1, op.f), A0, A1, B0, B1;
-        zero_cell(B0); zero_cell(B1);
+        Cell u = scale_cell(op.w1, op.f), A[RPT], B[RPT];
         if (GRAD) {
           fma_cell(u, op.dw1, op.g1);
           const Cell v = scale_cell(op.w1, op.g0), sg = scale_cell(op.w1, op.g2);
-          A0 = scale_cell(op.w0a, u); fma_cell(A0, op.dw0a, v);
-          A1 = scale_cell(op.w0b, u); fma_cell(A1, op.dw0b, v);
-          B0 = scale_cell(op.w0a, sg); B1 = scale_cell(op.w0b, sg);
+#pragma unroll
+          for (int e = 0; e < RPT; e++) { A[e] = scale_cell(op.w0[e], u); fma_cell(A[e], op.dw0[e], v); B[e] = scale_cell(op.w0[e], sg); }
         } else {
-          A0 = scale_cell(op.w0a, u); A1 = scale_cell(op.w0b, u);
+#pragma unroll
+          for (int e = 0; e < RPT; e++) { A[e] = scale_cell(op.w0[e], u); zero_cell(B[e]); }
         }
         // prefetch
         const unsigned char *row2 = row1 + ROWBYTES < last ? row1 + ROWBYTES : last;
@@ -486,9 +497,11 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
           for (int e = 0; e < PER; e++) {
             const int k = j * PER + e;
             if (k < W) {
-              fma_cell(wa[k], zq_get(w, e), A0);
-              fma_cell(wb[k], zq_get(w, e), A1);
-              if (GRAD) { fma_cell(wa[k], zq_get(dw, e), B0); fma_cell(wb[k], zq_get(dw, e), B1); }
+#pragma unroll
+              for (int r = 0; r < RPT; r++) {
+                fma_cell(win[r][k], zq_get(w, e), A[r]);
+                if (GRAD) fma_cell(win[r][k], zq_get(dw, e), B[r]);
+              }
             }
           }
         }
@@ -508,9 +521,9 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
 // ------------------------------------------------------------------------------------------------
 // sum NV values over the 32 lanes with NV-1 + log2(32/NV) exchanges; the lane whose upper bits spell k ends up with
 // the total of value k (returned in v[0], k in *which); all lanes sharing those upper bits hold the same total
-template <int NV, class R> __device__ __forceinline__ void lanes_reduce(R (&v)[NV], int lane, int *which) {
+template <int NV, int WIDTH, class R> __device__ __forceinline__ void lanes_reduce(R (&v)[NV], int lane, int *which) {
   int w = 0;
-  int bit = 16;
+  int bit = WIDTH / 2;
 #pragma unroll
   for (int n = NV; n > 1; n >>= 1, bit >>= 1) {
     const bool hi = (lane & bit) != 0;
@@ -526,51 +539,62 @@ template <int NV, class R> __device__ __forceinline__ void lanes_reduce(R (&v)[N
   *which = w;
 }
 
-// x-y contraction of one node's per-row partial sums by one warp: lane = (x row parity, y row); the y weight of a lane
-// is the same for all its x rows, so it multiplies the per-lane sums once at the end
+// x-y contraction of the per-row partial sums of FOUR nodes by one warp, one node per quarter warp (8 lanes).  Lane l8
+// of a quarter walks the node's (2m+1) x 16 partials eight at a time: entry e = 8 it + l8 is x row it / 2 (the same for
+// the whole quarter) and y row 8 (it & 1) + l8, so a lane meets two y weights only and applies them once at the end.
+// The 8-lane reduction then leaves one output value per lane (with the gradient: exactly the 8 reals of f and grad f).
 template <class R, bool CPLX, int M_, bool GRAD, class Row, class Cell>
-__device__ __forceinline__ void zm2_reduce_node(const unsigned char *row, const Cell *pp, int lane, const GatherOut<R> &out) {
+__device__ __forceinline__ void zm2_reduce_quad(const unsigned char *row, const Cell *pp, bool live, int lane, const GatherOut<R> &out) {
   typedef Zm2Cfg<M_> Cfg;
   constexpr int C = Cfg::C, T1 = Cfg::T1, NCOMP = CPLX ? 2 : 1, SZ = (int)sizeof(R);
+  const int l8 = lane & 7;
   const int *hd = reinterpret_cast<const int *>(row);
   const int ny = hd[1], j = hd[4];
   const R *rr = reinterpret_cast<const R *>(row);
-  const R w1 = *reinterpret_cast<const R *>(row + (Row::oY + T1 - 1 + (lane & 15)) * SZ + ny);
-  R dw1 = (R)0;
-  if (GRAD) dw1 = *reinterpret_cast<const R *>(row + (Row::oDY + T1 - 1 + (lane & 15)) * SZ + ny);
-  Cell s, sd, u;
-  zero_cell(s); zero_cell(sd); zero_cell(u);
+  R w1[2], dw1[2];
 #pragma unroll
-  for (int it = 0; it < (C + 1) / 2; it++) {
-    const int i0 = 2 * it + (lane >> 4);
-    const bool ok = (2 * it + 1 < C) || i0 < C;
-    const R w0 = rr[Row::oX + Cfg::XLEAD + i0];                       // zero beyond the last tap
-    Cell t, td;
-    zero_cell(t); zero_cell(td);
-    if (ok) { t = pp[32 * it + lane]; if (GRAD) td = pp[C * 16 + 32 * it + lane]; }
-    fma_cell(s, w0, t);
+  for (int b = 0; b < 2; b++) {
+    w1[b] = *reinterpret_cast<const R *>(row + (Row::oY + T1 - 1 + 8 * b + l8) * SZ + ny);
+    dw1[b] = GRAD ? *reinterpret_cast<const R *>(row + (Row::oDY + T1 - 1 + 8 * b + l8) * SZ + ny) : (R)0;
+  }
+  Cell s[2], sd[2], u[2];
+#pragma unroll
+  for (int b = 0; b < 2; b++) { zero_cell(s[b]); zero_cell(sd[b]); zero_cell(u[b]); }
+#pragma unroll
+  for (int it = 0; it < 2 * C; it++) {
+    const int i0 = it >> 1, b = it & 1;
+    const R w0 = rr[Row::oX + Cfg::XLEAD + i0];
+    const Cell t = pp[8 * it + l8];
+    fma_cell(s[b], w0, t);
     if (GRAD) {
       const R dw0 = rr[Row::oDX + Cfg::XLEAD + i0];
-      fma_cell(sd, dw0, t);
-      fma_cell(u, w0, td);
+      const Cell td = pp[C * 16 + 8 * it + l8];
+      fma_cell(sd[b], dw0, t);
+      fma_cell(u[b], w0, td);
     }
   }
   constexpr int NVAL = NCOMP * (GRAD ? 4 : 1);
   R v[NVAL];
-  const Cell af = scale_cell(w1, s);
+  Cell af = scale_cell(w1[0], s[0]);
+  fma_cell(af, w1[1], s[1]);
   if constexpr (CPLX) {
     v[0] = af.x; v[1] = af.y;
     if constexpr (GRAD) {
-      const Cell a0 = scale_cell(w1, sd), a1 = scale_cell(dw1, s), a2 = scale_cell(w1, u);
+      Cell a0 = scale_cell(w1[0], sd[0]), a1 = scale_cell(dw1[0], s[0]), a2 = scale_cell(w1[0], u[0]);
+      fma_cell(a0, w1[1], sd[1]); fma_cell(a1, dw1[1], s[1]); fma_cell(a2, w1[1], u[1]);
       v[2] = a0.x; v[3] = a0.y; v[4] = a1.x; v[5] = a1.y; v[6] = a2.x; v[7] = a2.y;
     }
   } else {
     v[0] = af;
-    if constexpr (GRAD) { v[1] = scale_cell(w1, sd); v[2] = scale_cell(dw1, s); v[3] = scale_cell(w1, u); }
+    if constexpr (GRAD) {
+      Cell a0 = scale_cell(w1[0], sd[0]), a1 = scale_cell(dw1[0], s[0]), a2 = scale_cell(w1[0], u[0]);
+      fma_cell(a0, w1[1], sd[1]); fma_cell(a1, dw1[1], s[1]); fma_cell(a2, w1[1], u[1]);
+      v[1] = a0; v[2] = a1; v[3] = a2;
+    }
   }
   int which;
-  lanes_reduce<NVAL>(v, lane, &which);
-  if ((lane & (32 / NVAL - 1)) == 0) {
+  lanes_reduce<NVAL, 8>(v, lane, &which);
+  if (live && (l8 & (8 / NVAL - 1)) == 0) {
     R *o = nullptr;
     if (which < NCOMP) { if (out.f) o = out.f + ((size_t)j * out.f_stride + out.f_off) * NCOMP + which; }
     else if (GRAD) o = out.grad + (size_t)j * 3 * NCOMP + (which - NCOMP);
@@ -624,14 +648,15 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
   const int cx = col / zg.nc[1], cy = col - cx * zg.nc[1];
   const int o0 = cx * T0 + XW * warp, o1 = cy * T1;
   const int hlf = lane >> 4, r1 = lane & 15;
-  const int rbase = XW * warp + 2 * hlf;
-  const int rho0 = (2 * hlf) * 16 + r1, rho1 = rho0 + 16;
+  constexpr int RPT = Cfg::RPT;
+  const int rbase = XW * warp + RPT * hlf;
+  const int rho0 = (RPT * hlf) * 16 + r1;
   const int dxlo = max(0, XW * warp - (C - 1)), dxhi1 = min(T0 - 1, XW * warp + XW - 1) + 1;
   unsigned char *mystg = smem_raw + (size_t)warp * Sm::WARP_BOX;
   unsigned long long *mybar = &wbar[warp];
   unsigned wph = 0;
 
-  Cell wa[W], wb[W];
+  Cell win[RPT][W];
   int cur = INT_MIN / 2;       // sub-chunk whose cells [cur*ZS, cur*ZS + W) are in the windows
   bool pending = false;        // a load of the cells [cur*ZS + W, +ZS) is in flight
 
@@ -651,11 +676,12 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
 #pragma unroll
     for (int b = 0; b < NBOX; b++)
 #pragma unroll
-      for (int q = 0; q < ZB; q++) {
-        wa[FIRST + b * ZB + q] = *zm2_stg<Cell, ZB>(mystg + b * BOXB, rho0, q);
-        wb[FIRST + b * ZB + q] = *zm2_stg<Cell, ZB>(mystg + b * BOXB, rho1, q);
-        nan |= cell_is_nan(wa[FIRST + b * ZB + q]) | cell_is_nan(wb[FIRST + b * ZB + q]);
-      }
+      for (int q = 0; q < ZB; q++)
+#pragma unroll
+        for (int e = 0; e < RPT; e++) {
+          win[e][FIRST + b * ZB + q] = *zm2_stg<Cell, ZB>(mystg + b * BOXB, rho0 + 16 * e, q);
+          nan |= cell_is_nan(win[e][FIRST + b * ZB + q]);
+        }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     (void)warp_any_volatile(nan);
   };
@@ -682,12 +708,16 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
   };
   auto advance1 = [&]() {
 #pragma unroll
-    for (int i = 0; i < W - ZS; i++) { wa[i] = wa[i + ZS]; wb[i] = wb[i + ZS]; }
+    for (int i = 0; i < W - ZS; i++)
+#pragma unroll
+      for (int e = 0; e < RPT; e++) win[e][i] = win[e][i + ZS];
     take(std::integral_constant<int, W - ZS>(), std::integral_constant<int, ZS / ZB>());
     cur++;
     issue(cur * ZS + W, ZS / ZB);
   };
 
+  // the warps whose rows meet every node of the tile are the critical path: they leave the reduction to the others
+  const bool helper = (dxhi1 - dxlo) < T0;
   // deferred x-y reduction of chunk kr: wait until every warp has left its partial sums, then take nodes from the
   // chunk's ticket counter (in its ring header) until none are left; releases the partial stage and the ring stage
   auto help = [&](int kr) {
@@ -696,12 +726,16 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
     int *h = reinterpret_cast<int *>(sp);
     mbar_wait_park(&pfull[ps], ((unsigned)(kr / P)) & 1u);
     const int cnt = h[1];
-    for (;;) {
-      int i = 0;
-      if (lane == 0) i = atomicAdd(&h[3], 1);
-      i = __shfl_sync(0xffffffffu, i, 0);
-      if (i >= cnt) break;
-      zm2_reduce_node<R, CPLX, M_, GRAD, Row>(sp + kZm2HdrBytes + (size_t)i * ROWBYTES, part + (size_t)(ps * GB + i) * PN, lane, out);
+    if (helper) {
+      for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&h[3], 4);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= cnt) break;
+        const int mine = i + (lane >> 3);
+        const int ic = mine < cnt ? mine : cnt - 1;
+        zm2_reduce_quad<R, CPLX, M_, GRAD, Row>(sp + kZm2HdrBytes + (size_t)ic * ROWBYTES, part + (size_t)(ps * GB + ic) * PN, mine < cnt, lane, out);
+      }
     }
     __syncwarp();
     if (lane == 0) { mbar_arrive(&pempty[ps]); mbar_arrive(&empty[st]); }
@@ -739,8 +773,9 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
       for (int i = lo; i < hi; i++, pb += PN) {
         const unsigned char *row1 = row + ROWBYTES < last ? row + ROWBYTES : last;
         const int4 hn = *reinterpret_cast<const int4 *>(row1);       // prefetch the next header
-        Cell ta, tda, tb, tdb, ta1, tb1;     // F only: two chains per sum; with the gradient the four sums are chains enough
-        zero_cell(ta); zero_cell(tda); zero_cell(tb); zero_cell(tdb); zero_cell(ta1); zero_cell(tb1);
+        Cell t[RPT], td[RPT], t1[RPT];       // F only: two chains per sum; with the gradient the sums are chains enough
+#pragma unroll
+        for (int r = 0; r < RPT; r++) { zero_cell(t[r]); zero_cell(td[r]); zero_cell(t1[r]); }
 #pragma unroll
         for (int j = 0; j < NQT; j++) {
           const Quad w = Q[j % D];
@@ -754,22 +789,22 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
           for (int e = 0; e < PER; e++) {
             const int k = j * PER + e;
             if (k < W) {
-              if (GRAD) {
-                fma_cell(ta, zq_get(w, e), wa[k]); fma_cell(tb, zq_get(w, e), wb[k]);
-                fma_cell(tda, zq_get(dw, e), wa[k]); fma_cell(tdb, zq_get(dw, e), wb[k]);
-              } else if (k & 1) {
-                fma_cell(ta1, zq_get(w, e), wa[k]); fma_cell(tb1, zq_get(w, e), wb[k]);
-              } else {
-                fma_cell(ta, zq_get(w, e), wa[k]); fma_cell(tb, zq_get(w, e), wb[k]);
+#pragma unroll
+              for (int r = 0; r < RPT; r++) {
+                if (GRAD) { fma_cell(t[r], zq_get(w, e), win[r][k]); fma_cell(td[r], zq_get(dw, e), win[r][k]); }
+                else if (k & 1) fma_cell(t1[r], zq_get(w, e), win[r][k]);
+                else fma_cell(t[r], zq_get(w, e), win[r][k]);
               }
             }
           }
         }
-        if (!GRAD) { add_cell(ta, ta1); add_cell(tb, tb1); }
         const int i0 = rbase - hd.w;
         Cell *p = pb - hd.w * 16;
-        if ((unsigned)i0 < (unsigned)C) { p[0] = ta; if (GRAD) p[C * 16] = tda; }
-        if ((unsigned)(i0 + 1) < (unsigned)C) { p[16] = tb; if (GRAD) p[C * 16 + 16] = tdb; }
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+          if (!GRAD) add_cell(t[r], t1[r]);
+          if ((unsigned)(i0 + r) < (unsigned)C) { p[16 * r] = t[r]; if (GRAD) p[C * 16 + 16 * r] = td[r]; }
+        }
         hd = hn; row = row1;
       }
     }
