@@ -266,6 +266,7 @@ template <class R> struct Core {
       return nullptr;
     }
     select_device_for_rank();
+    if (mesh.size > 1) (void)world_nccl();   // collective: create the NCCL communicator outside of any ncclGroup
 
     P *p = new P();
     p->mesh = mesh;
