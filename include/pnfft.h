@@ -16,6 +16,7 @@
 
 #include <stddef.h>
 #include <mpi.h>
+#include <pfft.h>   /* the reference's header pulls it in as well (api/pnfft.h:28-29); see include/pfft.h */
 
 #ifdef __cplusplus
 extern "C" {
@@ -131,6 +132,18 @@ typedef float pnfftf_complex[2];
                                                                                                     \
   void PNX(vpr_complex)(C *data, ptrdiff_t N, const char *name, MPI_Comm comm);                     \
   void PNX(vpr_real)(R *data, ptrdiff_t N, const char *name, MPI_Comm comm);                        \
+  /* per-rank print of a 3-d block: reference api/pnfft.h:233-238 */                                \
+  void PNX(apr_complex_3d)(C *data, ptrdiff_t *local_N, ptrdiff_t *local_N_start, unsigned pnfft_flags, \
+                           const char *name, MPI_Comm comm);                                        \
+  void PNX(apr_real_3d)(R *data, ptrdiff_t *local_N, ptrdiff_t *local_N_start, unsigned pnfft_flags, \
+                        const char *name, MPI_Comm comm);                                           \
+  /* second window derivative (Hessian path, out of scope): prints a notice and returns 0 */         \
+  R PNX(ddpsi)(const PNX(plan) ths, int dim, R x);                                                  \
+  /* command line helpers of the test drivers: reference util/getargs.c:24-31, api/api-basic.c:820-938 */ \
+  void PNX(get_args)(int argc, char **argv, const char *name, int neededArgs, unsigned type, void *parameter); \
+  void PNX(check_init_parameters)(int argc, char **argv, ptrdiff_t *N, ptrdiff_t *n, ptrdiff_t *M, int *m, \
+                                  unsigned *pnfft_flags, unsigned *compute_flags, double *x_max, int *np, \
+                                  int *compare_direct, int *debug);                                 \
                                                                                                     \
   /* timers: reference kernel/timer.c:43-370; the ten slots are filled from CUDA events */          \
   double *PNX(get_timer_trafo)(PNX(plan) ths);                                                      \
@@ -143,6 +156,8 @@ typedef float pnfftf_complex[2];
   void PNX(reset_timer)(PNX(plan) ths);                                                             \
   void PNX(print_average_timer)(const PNX(plan) ths, MPI_Comm comm);                                \
   void PNX(print_average_timer_adv)(const PNX(plan) ths, MPI_Comm comm);                            \
+  void PNX(write_average_timer)(const PNX(plan) ths, const char *name, MPI_Comm comm);              \
+  void PNX(write_average_timer_adv)(const PNX(plan) ths, const char *name, MPI_Comm comm);          \
                                                                                                     \
   /* ---- extensions (no reference counterpart) -------------------------------------------- */   \
   /* padded-grid access for isolating B (PNFFT_OMIT_DECONV|PNFFT_OMIT_FFT, reference               \

@@ -272,6 +272,89 @@ void PNX(print_average_timer)(const PNX(plan) ths, MPI_Comm comm) {
   }
 }
 void PNX(print_average_timer_adv)(const PNX(plan) ths, MPI_Comm comm) { PNX(print_average_timer)(ths, comm); }
+// same averages appended to a file by rank 0 (reference kernel/timer.c write_average_timer*)
+void PNX(write_average_timer)(const PNX(plan) ths, const char *name, MPI_Comm comm) {
+  static const char *names[] = {"iter", "whole", "loop_b", "sort_nodes", "gcells", "matrix_b", "matrix_f", "matrix_d", "shift_input", "shift_output"};
+  int rank = 0; MPI_Comm_rank(comm, &rank);
+  FILE *fp = rank == 0 ? fopen(name, "a") : nullptr;
+  for (int dir = 0; dir < 2; dir++) {
+    double t[PNFFT_TIMER_LENGTH], mx[PNFFT_TIMER_LENGTH];
+    for (int i = 0; i < PNFFT_TIMER_LENGTH; i++) t[i] = dir ? AS_PLAN(ths)->timer_adj[i] : AS_PLAN(ths)->timer_trafo[i];
+    PNX(timer_average)(t);
+    MPI_Reduce(t, mx, PNFFT_TIMER_LENGTH, MPI_DOUBLE, MPI_MAX, 0, comm);
+    if (fp) for (int i = 1; i < 8; i++) fprintf(fp, "pnfft_%s_%s = %.3e;\n", dir ? "adj" : "trafo", names[i], mx[i]);
+  }
+  if (fp) fclose(fp);
+}
+void PNX(write_average_timer_adv)(const PNX(plan) ths, const char *name, MPI_Comm comm) { PNX(write_average_timer)(ths, name, comm); }
+
+// every rank in turn prints its block; k_t = local_N_start[t] + i_t (reference api/pnfft.h:233-238)
+static void apr_block(const RT *data, int ncomp, const INT *local_N, const INT *local_N_start, const char *name, MPI_Comm comm) {
+  int rank = 0, size = 1;
+  MPI_Comm_rank(comm, &rank); MPI_Comm_size(comm, &size);
+  for (int r = 0; r < size; r++) {
+    if (r == rank) {
+      printf("rank %d: %s", rank, name);
+      INT l = 0;
+      for (INT k0 = 0; k0 < local_N[0]; k0++)
+        for (INT k1 = 0; k1 < local_N[1]; k1++) {
+          for (INT k2 = 0; k2 < local_N[2]; k2++, l++) {
+            if (ncomp == 2) printf("  [%td,%td,%td] %.4e%+.4ei", k0 + local_N_start[0], k1 + local_N_start[1], k2 + local_N_start[2], (double)data[2 * l], (double)data[2 * l + 1]);
+            else printf("  [%td,%td,%td] %.4e", k0 + local_N_start[0], k1 + local_N_start[1], k2 + local_N_start[2], (double)data[l]);
+          }
+          printf("\n");
+        }
+      fflush(stdout);
+    }
+    MPI_Barrier(comm);
+  }
+}
+void PNX(apr_complex_3d)(CT *data, INT *local_N, INT *local_N_start, unsigned, const char *name, MPI_Comm comm) {
+  apr_block((const RT *)data, 2, local_N, local_N_start, name, comm);
+}
+void PNX(apr_real_3d)(RT *data, INT *local_N, INT *local_N_start, unsigned, const char *name, MPI_Comm comm) {
+  apr_block(data, 1, local_N, local_N_start, name, comm);
+}
+RT PNX(ddpsi)(const PNX(plan), int, RT) {
+  fprintf(stderr, "pnfft-b200: second window derivatives (Hessian path) are not part of the accelerated path\n");
+  return (RT)0;
+}
+void PNX(get_args)(int argc, char **argv, const char *name, int neededArgs, unsigned type, void *parameter) {
+  pfft_get_args(argc, argv, name, neededArgs, type, parameter);
+}
+// defaults and option names of the reference's test drivers (api/api-basic.c:820-938)
+void PNX(check_init_parameters)(int argc, char **argv, INT *N, INT *n, INT *local_M, int *m, unsigned *pnfft_flags,
+                                unsigned *compute_flags, double *x_max, int *np, int *compare_direct, int *debug) {
+  int window = 4, fast_gaussian = 0, intpol = -1, interlaced = 0, diff_ik = 0, tr_f_hat = 0;
+  int cf = 1, cg = 1, ch = 1;
+  N[0] = N[1] = N[2] = 16; n[0] = n[1] = n[2] = 0; *local_M = 0; *m = 6;
+  x_max[0] = x_max[1] = x_max[2] = 0.5;
+  np[0] = np[1] = np[2] = 2;
+  struct { const char *name; int cnt; unsigned type; void *dst; } opt[] = {
+    {"-pnfft_local_M", 1, PFFT_PTRDIFF_T, local_M}, {"-pnfft_N", 3, PFFT_PTRDIFF_T, N}, {"-pnfft_n", 3, PFFT_PTRDIFF_T, n},
+    {"-pnfft_np", 3, PFFT_INT, np}, {"-pnfft_m", 1, PFFT_INT, m}, {"-pnfft_window", 1, PFFT_INT, &window},
+    {"-pnfft_fast_gaussian", 1, PFFT_INT, &fast_gaussian}, {"-pnfft_intpol", 1, PFFT_INT, &intpol},
+    {"-pnfft_interlaced", 1, PFFT_INT, &interlaced}, {"-pnfft_diff_ik", 1, PFFT_INT, &diff_ik},
+    {"-pnfft_tr_f_hat", 1, PFFT_INT, &tr_f_hat}, {"-pnfft_x_max", 3, PFFT_DOUBLE, x_max}, {"-pnfft_debug", 1, PFFT_INT, debug},
+    {"-pnfft_compare_direct", 1, PFFT_INT, compare_direct}, {"-pnfft_compute_f", 1, PFFT_INT, &cf},
+    {"-pnfft_compute_grad_f", 1, PFFT_INT, &cg}, {"-pnfft_compute_hessian_f", 1, PFFT_INT, &ch}};
+  for (auto &o : opt) pfft_get_args(argc, argv, o.name, o.cnt, o.type, o.dst);
+  if (*local_M == 0) *local_M = N[0] * N[1] * N[2] / ((INT)np[0] * np[1] * np[2]);
+  for (int t = 0; t < 3; t++) if (n[t] == 0) n[t] = 2 * N[t];
+  static const unsigned win_flag[] = {PNFFT_WINDOW_GAUSSIAN, PNFFT_WINDOW_BSPLINE, PNFFT_WINDOW_SINC_POWER, PNFFT_WINDOW_BESSEL_I0,
+                                      PNFFT_WINDOW_KAISER_BESSEL, PNFFT_WINDOW_GAUSSIAN_T};
+  static const unsigned ip_flag[] = {PNFFT_PRE_CONST_PSI, PNFFT_PRE_LIN_PSI, PNFFT_PRE_QUAD_PSI, PNFFT_PRE_CUB_PSI};
+  const unsigned wf = (window >= 0 && window <= 5) ? win_flag[window] : PNFFT_WINDOW_KAISER_BESSEL;
+  const unsigned ipf = (intpol >= 0 && intpol <= 3) ? ip_flag[intpol] : 0u;
+  *compute_flags = (cf ? PNFFT_COMPUTE_F : 0u) | (cg ? PNFFT_COMPUTE_GRAD_F : 0u) | (ch ? PNFFT_COMPUTE_HESSIAN_F : 0u);
+  *pnfft_flags = wf | (fast_gaussian ? PNFFT_FAST_GAUSSIAN : 0u) | ipf | (diff_ik ? PNFFT_DIFF_IK : PNFFT_DIFF_AD) |
+                 (tr_f_hat ? PNFFT_TRANSPOSED_F_HAT : 0u) | (interlaced ? PNFFT_INTERLACED : 0u);
+  pfft_printf(MPI_COMM_WORLD, "pnfft-b200 test set-up: N = %td x %td x %td (-pnfft_N), n = %td x %td x %td (-pnfft_n), local_M = %td "
+              "(-pnfft_local_M), m = %d (-pnfft_m), window = %d (-pnfft_window), fast_gaussian = %d, intpol = %d, interlaced = %d, "
+              "diff_ik = %d, tr_f_hat = %d, compute f/grad/hessian = %d/%d/%d, compare_direct = %d, np = %d x %d x %d (-pnfft_np)\n",
+              N[0], N[1], N[2], n[0], n[1], n[2], *local_M, *m, window, fast_gaussian, intpol, interlaced, diff_ik, tr_f_hat,
+              cf, cg, ch, *compare_direct, np[0], np[1], np[2]);
+}
 
 // ---------------------------------------------------------------------------------------------
 // extensions

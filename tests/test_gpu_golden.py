@@ -182,3 +182,34 @@ def test_multi_gpu_parity(world):
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert r.returncode == 0 and lines, r.stdout[-3000:]
     assert json.loads(lines[-1])["ok"]
+
+
+def _run_driver(name, args, rc_ok=(0,)):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "drivers", name)
+    if not os.path.exists(exe):
+        pytest.skip("reference driver %s not built (make -C oracle drivers needs /root/reference)" % name)
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
+    assert r.returncode in rc_ok, r.stdout[-2000:]
+    return r.stdout
+
+
+def test_reference_drivers():
+    """The reference's OWN test programs (tests/check_trafo.c, check_adj.c, check_vs_pfft.c, pnfft_test.c), compiled
+    unmodified against include/pnfft.h and linked with libpnfft_b200.so, run on the GPU and report the errors they compute
+    themselves: NFFT (m) against a higher-accuracy NFFT (reference tests/check_trafo.c:41-57), and the equispaced
+    forward/backward round trip, which must be the identity (reference tests/check_vs_pfft.c:138-156)."""
+    import re
+    one = ["-pnfft_np", "1", "1", "1", "-pnfft_compute_hessian_f", "0", "-pnfft_N", "16", "16", "16"]
+    for drv in ("check_trafo", "check_adj"):
+        out = _run_driver(drv, one)
+        errs = [float(v) for v in re.findall(r"relative error =\s*([0-9.eE+-]+)", out)]
+        assert errs, out[-2000:]
+        assert max(errs) < 1e-7, out[-2000:]   # truncation error of the method at m=6 (f ~4e-11, AD gradient ~2e-8)
+    out = _run_driver("check_vs_pfft", ["-pnfft_np", "1", "1", "1", "-pnfft_N", "16", "16", "16"])
+    errs = [float(v) for v in re.findall(r"relative maximum error =\s*([0-9.eE+-]+)", out)]
+    assert errs and max(errs) < 1e-10, out[-2000:]
+    out = _run_driver("pnfft_test", [], rc_ok=(0, 1))   # takes no options: its 2x2x2 mesh is refused with one rank,
+    assert "Procmesh" in out or "PNFFT Results" in out   # through pnfft_create_procmesh's non-zero return (util/util.c:23-40)
