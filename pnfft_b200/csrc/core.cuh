@@ -187,65 +187,72 @@ template <class R> struct Core {
   // Per-tap polynomial form of the window (the kernels' on-the-fly evaluation): tap s of axis t as a function
   // of frac = n x - floor(n x) in [0,1) is analytic for every supported window, so a Chebyshev interpolant of
   // modest degree reproduces it to rounding.  Fitted here in double from the exact formulas of window.h, the
-  // degree is raised until the neglected Chebyshev tail is below 2e-17 (double) / 1e-9 (float) of the window
+  // degree is raised until the next Chebyshev coefficients are below 5e-16 (double) / 1e-9 (float) of the window
   // maximum; if degree 24 is not enough the kernels keep the exact evaluation.
   static void fit_window_polys(P *p) {
     const Layout &L = p->L;
     const int c = L.cutoff, nv = 3 * c, m = L.m;
     const int NP = 48;
     const double pi = 3.14159265358979323846;
-    std::vector<double> ck((size_t)nv * NP);
-    double vmax = 0;
+    // Chebyshev coefficients of psi (set 0) and of the AD-gradient weight dpsi (set 1), each tap and axis
+    std::vector<double> ck((size_t)2 * nv * NP);
+    double vmax[2] = {0, 0};
     for (int v = 0; v < nv; v++) {
       const int t = v / c, s = v - t * c;
-      double f[NP];
+      double f[2][NP];
       for (int j = 0; j < NP; j++) {
         const double u = cos(pi * (j + 0.5) / NP), frac = 0.5 * (u + 1.0);
-        double psi, d;
-        window_tap<double>(p->kind, (double)s - (double)m - frac, (double)L.n[t], (double)p->b[t], m, false, &psi, &d);
-        f[j] = psi;
-        vmax = std::max(vmax, fabs(psi));
+        double psi = 0, d = 0;
+        window_tap<double>(p->kind, (double)s - (double)m - frac, (double)L.n[t], (double)p->b[t], m, true, &psi, &d);
+        f[0][j] = psi; f[1][j] = d;
+        vmax[0] = std::max(vmax[0], fabs(psi));
+        vmax[1] = std::max(vmax[1], fabs(d));
       }
-      for (int k = 0; k < NP; k++) {
-        long double acc = 0;
-        for (int j = 0; j < NP; j++) acc += (long double)f[j] * cosl((long double)pi * k * (j + 0.5L) / NP);
-        ck[(size_t)v * NP + k] = (double)(acc * 2.0L / NP * (k == 0 ? 0.5L : 1.0L));
-      }
+      for (int q = 0; q < 2; q++)
+        for (int k = 0; k < NP; k++) {
+          long double acc = 0;
+          for (int j = 0; j < NP; j++) acc += (long double)f[q][j] * cosl((long double)pi * k * (j + 0.5L) / NP);
+          ck[((size_t)q * nv + v) * NP + k] = (double)(acc * 2.0L / NP * (k == 0 ? 0.5L : 1.0L));
+        }
     }
-    const double tol = (sizeof(R) == 8 ? 2e-17 : 1e-9) * vmax;
+    // The coefficients come from double evaluations of the window, so they bottom out at a noise floor of ~1e-16 of
+    // the maximum; a tail-sum criterion below that floor can never be met (it silently disabled the polynomials in
+    // double).  Take the first degree after which three consecutive coefficients of both sets are below tol.
+    const double rtol = sizeof(R) == 8 ? 5e-16 : 1e-9;
     int deg = -1;
-    for (int D = 2; D <= kMaxPolyCoef - 1; D++) {
-      double worst = 0;
-      for (int v = 0; v < nv; v++) {
-        double tail = 0;
-        for (int k = D + 1; k < NP - 8; k++) tail += fabs(ck[(size_t)v * NP + k]);
-        worst = std::max(worst, tail);
-      }
-      if (worst <= tol) { deg = D; break; }
+    for (int D = 2; D <= kMaxPolyCoef - 1 && deg < 0; D++) {
+      bool ok = true;
+      for (int q = 0; q < 2 && ok; q++)
+        for (int v = 0; v < nv && ok; v++)
+          for (int k = D + 1; k <= D + 3; k++)
+            if (fabs(ck[((size_t)q * nv + v) * NP + k]) > rtol * vmax[q]) { ok = false; break; }
+      if (ok) deg = D;
     }
     p->poly_deg = deg;
     if (deg < 0) return;
-    // Chebyshev -> monomial coefficients in u
-    std::vector<R> h((size_t)(deg + 1) * nv);
+    // Chebyshev -> monomial coefficients in u; device layout [set][k][v]
+    std::vector<R> h((size_t)2 * (deg + 1) * nv);
     std::vector<long double> Tkm1((size_t)deg + 1), Tk((size_t)deg + 1), Tn((size_t)deg + 1), a((size_t)deg + 1);
-    for (int v = 0; v < nv; v++) {
-      std::fill(a.begin(), a.end(), 0.0L);
-      std::fill(Tkm1.begin(), Tkm1.end(), 0.0L);
-      std::fill(Tk.begin(), Tk.end(), 0.0L);
-      Tkm1[0] = 1.0L;                       // T_0
-      if (deg >= 1) Tk[1] = 1.0L;           // T_1
-      a[0] += ck[(size_t)v * NP] * Tkm1[0];
-      if (deg >= 1) a[1] += ck[(size_t)v * NP + 1];
-      for (int k = 2; k <= deg; k++) {
-        std::fill(Tn.begin(), Tn.end(), 0.0L);
-        for (int i = 0; i < deg; i++) Tn[(size_t)i + 1] += 2.0L * Tk[(size_t)i];
-        for (int i = 0; i <= deg; i++) Tn[(size_t)i] -= Tkm1[(size_t)i];
-        for (int i = 0; i <= deg; i++) a[(size_t)i] += (long double)ck[(size_t)v * NP + k] * Tn[(size_t)i];
-        Tkm1 = Tk; Tk = Tn;
+    for (int q = 0; q < 2; q++)
+      for (int v = 0; v < nv; v++) {
+        const double *cv = &ck[((size_t)q * nv + v) * NP];
+        std::fill(a.begin(), a.end(), 0.0L);
+        std::fill(Tkm1.begin(), Tkm1.end(), 0.0L);
+        std::fill(Tk.begin(), Tk.end(), 0.0L);
+        Tkm1[0] = 1.0L;                       // T_0
+        if (deg >= 1) Tk[1] = 1.0L;           // T_1
+        a[0] += cv[0] * Tkm1[0];
+        if (deg >= 1) a[1] += cv[1];
+        for (int k = 2; k <= deg; k++) {
+          std::fill(Tn.begin(), Tn.end(), 0.0L);
+          for (int i = 0; i < deg; i++) Tn[(size_t)i + 1] += 2.0L * Tk[(size_t)i];
+          for (int i = 0; i <= deg; i++) Tn[(size_t)i] -= Tkm1[(size_t)i];
+          for (int i = 0; i <= deg; i++) a[(size_t)i] += (long double)cv[k] * Tn[(size_t)i];
+          Tkm1 = Tk; Tk = Tn;
+        }
+        for (int k = 0; k <= deg; k++) h[((size_t)q * (deg + 1) + k) * nv + v] = (R)a[(size_t)k];
       }
-      for (int k = 0; k <= deg; k++) h[(size_t)k * nv + v] = (R)a[(size_t)k];
-    }
-    if (!p->d_poly) PNB_CUDA(cudaMalloc((void **)&p->d_poly, sizeof(R) * (size_t)kMaxPolyCoef * nv));
+    if (!p->d_poly) PNB_CUDA(cudaMalloc((void **)&p->d_poly, sizeof(R) * (size_t)2 * kMaxPolyCoef * nv));
     PNB_CUDA(cudaMemcpy(p->d_poly, h.data(), sizeof(R) * h.size(), cudaMemcpyHostToDevice));
   }
 
@@ -659,7 +666,7 @@ template <class R> struct Core {
     {
       auto kt = k_node_table<R, M_, GRAD>;
       const long long nthr = 3LL * na.M;
-      const size_t psm = g.poly ? sizeof(R) * (size_t)(g.poly_deg + 1) * 3 * Cfg::C : 0;
+      const size_t psm = g.poly ? sizeof(R) * (size_t)2 * (g.poly_deg + 1) * 3 * Cfg::C : 0;
       kt<<<(unsigned)((nthr + 191) / 192), 192, psm, p->stream>>>(g, na, CPLX ? 2 : 1, scatter ? 1 : 0, nd->d_wtab);
       p->launches++;
     }
@@ -698,7 +705,7 @@ template <class R> struct Core {
       zg.zseg = (tg.nt[2] + nseg - 1) / nseg;
       zg.nseg = (tg.nt[2] + zg.zseg - 1) / zg.zseg;
       const unsigned nblk = (unsigned)(ncol * zg.nseg);
-      const size_t psm = g.poly ? sizeof(R) * (size_t)(g.poly_deg + 1) * 3 * Cfg::C : 0;
+      const size_t psm = g.poly ? sizeof(R) * (size_t)2 * (g.poly_deg + 1) * 3 * Cfg::C : 0;
       const unsigned ntb = (unsigned)((na.M + kZm2TabNodes - 1) / kZm2TabNodes);
       if (!scatter) {
         typedef typename Sm::RowG Row;

@@ -77,7 +77,8 @@ __device__ __forceinline__ void warp_window_eval(const GridGeom<R> &g, const R *
 
 // Same 3*(2m+1) values from the per-tap polynomials fitted at plan time (Core::fit_window_polys): tap s of
 // axis t is a smooth function of frac = n x - floor(n x) on [0,1); p(u), u = 2 frac - 1, reproduces it to
-// double rounding, and n * dp/dfrac is the AD-gradient weight (dpsi_s = -n g'(y_s), y_s = s - m - frac).
+// double rounding; the AD-gradient weights dpsi_s have their own polynomials, fitted to the exact derivative formulas
+// (differentiating the interpolant would amplify its error by deg^2).
 // Nodes sitting exactly on a grid line (frac == 0) take the exact path: compactly supported windows jump there.
 template <class R>
 __device__ __forceinline__ void warp_window_eval_poly(const GridGeom<R> &g, const R *poly, const R *nx, const R *fl, int lane,
@@ -89,11 +90,13 @@ __device__ __forceinline__ void warp_window_eval_poly(const GridGeom<R> &g, cons
     const int t = v / c;
     const R u = (R)2 * fr[t] - (R)1;
     const R *a = poly + v;
-    R p = a[g.poly_deg * nv], dp = (R)0;
+    R p = a[g.poly_deg * nv];
     if (want_d) {
-      for (int k = g.poly_deg - 1; k >= 0; k--) { dp = dp * u + p; p = p * u + a[k * nv]; }
+      const R *ad = a + (g.poly_deg + 1) * nv;      // the derivative weights have their own fitted polynomials
+      R dp = ad[g.poly_deg * nv];
+      for (int k = g.poly_deg - 1; k >= 0; k--) { dp = dp * u + ad[k * nv]; p = p * u + a[k * nv]; }
       psi_s[v] = p;
-      dpsi_s[v] = (R)2 * g.n[t] * dp;
+      dpsi_s[v] = dp;
     } else {
       for (int k = g.poly_deg - 1; k >= 0; k--) p = p * u + a[k * nv];
       psi_s[v] = p;
@@ -466,7 +469,7 @@ k_gather_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeom
   Cell *box = reinterpret_cast<Cell *>(smem_raw);
   R *scratch = reinterpret_cast<R *>(smem_raw + Cfg::BOX_BYTES);
   R *poly_s = scratch + kGatherWarps * 6 * C;
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(poly_s + kMaxPolyCoef * 3 * C);
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(poly_s + 2 * kMaxPolyCoef * 3 * C);
 
   const int tile = items[3 * blockIdx.x], begin = items[3 * blockIdx.x + 1], end = items[3 * blockIdx.x + 2];
   const int tz = tile % tg.nt[2], ty = (tile / tg.nt[2]) % tg.nt[1], tx = tile / (tg.nt[2] * tg.nt[1]);
@@ -478,7 +481,7 @@ k_gather_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeom
     mbar_expect_tx(bar, (unsigned)Cfg::BOX_BYTES);
     tma_load_3d(box, &tmap, o2 * NCOMP, o1, o0, bar);
   }
-  if (g.poly) for (int i = threadIdx.x; i < (g.poly_deg + 1) * 3 * C; i += kGatherWarps * 32) poly_s[i] = g.poly[i];
+  if (g.poly) for (int i = threadIdx.x; i < 2 * (g.poly_deg + 1) * 3 * C; i += kGatherWarps * 32) poly_s[i] = g.poly[i];
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -589,7 +592,7 @@ k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeo
   {
     Cell z; zero_cell(z);
     for (int i = threadIdx.x; i < Cfg::BOX_CELLS; i += NT) box[i] = z;
-    if (g.poly) for (int i = threadIdx.x; i < (g.poly_deg + 1) * 3 * C; i += NT) poly_s[i] = g.poly[i];
+    if (g.poly) for (int i = threadIdx.x; i < 2 * (g.poly_deg + 1) * 3 * C; i += NT) poly_s[i] = g.poly[i];
   }
   int off[NCH], l1s[NCH], l2s[NCH];
 #pragma unroll
@@ -641,9 +644,10 @@ k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeo
         if (g.poly && fr != (R)0) {
           const R u = (R)2 * fr - (R)1;
           const R *a = poly_s + r;
+          const R *ad = a + (g.poly_deg + 1) * 3 * C;
           psi = a[g.poly_deg * 3 * C];
-          for (int k = g.poly_deg - 1; k >= 0; k--) { if (GRAD) dpsi = dpsi * u + psi; psi = psi * u + a[k * 3 * C]; }
-          dpsi *= (R)2 * g.n[t];
+          if (GRAD) dpsi = ad[g.poly_deg * 3 * C];
+          for (int k = g.poly_deg - 1; k >= 0; k--) { if (GRAD) dpsi = dpsi * u + ad[k * 3 * C]; psi = psi * u + a[k * 3 * C]; }
         } else if (g.kind == WIN_GAUSSIAN && g.fast_gauss) {
           const R d = nxv - (flv - (R)M_);
           const R e_sqr = m_exp(-(d * d) / g.b[t]), e_lin = m_exp((R)2 * d / g.b[t]);
@@ -702,7 +706,7 @@ k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeo
 template <class R, bool CPLX, int M_, bool GRAD> struct TiledSmem {
   typedef typename CellT<R, CPLX>::type Cell;
   typedef TileCfg<M_, (int)sizeof(Cell)> Cfg;
-  static constexpr size_t poly = (size_t)kMaxPolyCoef * 3 * Cfg::C * sizeof(R);
+  static constexpr size_t poly = (size_t)2 * kMaxPolyCoef * 3 * Cfg::C * sizeof(R);   // psi and dpsi polynomials
   static constexpr size_t gather = (size_t)Cfg::BOX_BYTES + (size_t)kGatherWarps * 6 * Cfg::C * sizeof(R) + poly + 16;
   static constexpr int NB = ScatterCfg<M_>::NB;
   static constexpr size_t scatter = (size_t)Cfg::BOX_BYTES + (size_t)NB * (GRAD ? 6 : 3) * Cfg::C * sizeof(R) +

@@ -79,7 +79,7 @@ k_node_table(GridGeom<R> g, NodeArgs<R> na, int ncomp, int with_vals, R *__restr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R *poly_s = reinterpret_cast<R *>(smem_raw);
   if (g.poly) {
-    for (int i = threadIdx.x; i < (g.poly_deg + 1) * 3 * C; i += blockDim.x) poly_s[i] = g.poly[i];
+    for (int i = threadIdx.x; i < 2 * (g.poly_deg + 1) * 3 * C; i += blockDim.x) poly_s[i] = g.poly[i];
     __syncthreads();
   }
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,18 +101,18 @@ k_node_table(GridGeom<R> g, NodeArgs<R> na, int ncomp, int with_vals, R *__restr
     const R u = (R)2 * fr - (R)1;
     const R *a = poly_s + t * C;
     const int nv = 3 * C;
+    const R *ad = a + (g.poly_deg + 1) * nv;
 #pragma unroll
-    for (int s = 0; s < C; s++) { psi[s] = a[g.poly_deg * nv + s]; if (GRAD) dpsi[s] = (R)0; }
+    for (int s = 0; s < C; s++) { psi[s] = a[g.poly_deg * nv + s]; if (GRAD) dpsi[s] = ad[g.poly_deg * nv + s]; }
     for (int k = g.poly_deg - 1; k >= 0; k--) {
 #pragma unroll
       for (int s = 0; s < C; s++) {
-        if (GRAD) dpsi[s] = dpsi[s] * u + psi[s];
+        if (GRAD) dpsi[s] = dpsi[s] * u + ad[k * nv + s];
         psi[s] = psi[s] * u + a[k * nv + s];
       }
     }
-    const R sc = (R)2 * g.n[t];
 #pragma unroll
-    for (int s = 0; s < C; s++) { rp[s] = psi[s]; if (GRAD) rd[s] = dpsi[s] * sc; }
+    for (int s = 0; s < C; s++) { rp[s] = psi[s]; if (GRAD) rd[s] = dpsi[s]; }
   } else if (g.kind == WIN_BSPLINE) {
     bspline_taps<R>(M_, fr, g.n[t], rp, GRAD ? rd : nullptr);
   } else if (g.kind == WIN_GAUSSIAN && g.fast_gauss) {

@@ -90,7 +90,7 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R *rows = reinterpret_cast<R *>(smem_raw);
   R *poly_s = rows + (size_t)kZm2TabNodes * Row::ROWLEN;
-  if (g.poly) for (int i = threadIdx.x; i < (g.poly_deg + 1) * 3 * C; i += blockDim.x) poly_s[i] = g.poly[i];
+  if (g.poly) for (int i = threadIdx.x; i < (GRAD ? 2 : 1) * (g.poly_deg + 1) * 3 * C; i += blockDim.x) poly_s[i] = g.poly[i];
   __syncthreads();
   const int p0 = blockIdx.x * kZm2TabNodes;
   const int nn = min(kZm2TabNodes, na.M - p0);
@@ -112,19 +112,15 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
       const R u = (R)2 * fr - (R)1;
       const R *a = poly_s + t * C;
       const int nv = 3 * C;
+      const R *ad = a + (g.poly_deg + 1) * nv;      // the derivative weights have their own fitted polynomials
 #pragma unroll
-      for (int s = 0; s < C; s++) { psi[s] = a[g.poly_deg * nv + s]; if (GRAD) dpsi[s] = (R)0; }
+      for (int s = 0; s < C; s++) { psi[s] = a[g.poly_deg * nv + s]; if (GRAD) dpsi[s] = ad[g.poly_deg * nv + s]; }
       for (int k = g.poly_deg - 1; k >= 0; k--) {
 #pragma unroll
         for (int s = 0; s < C; s++) {
-          if (GRAD) dpsi[s] = dpsi[s] * u + psi[s];
+          if (GRAD) dpsi[s] = dpsi[s] * u + ad[k * nv + s];
           psi[s] = psi[s] * u + a[k * nv + s];
         }
-      }
-      if (GRAD) {
-        const R sc = (R)2 * g.n[t];
-#pragma unroll
-        for (int s = 0; s < C; s++) dpsi[s] *= sc;
       }
     } else {
       // exact formulas (nodes on a grid line, windows without a polynomial fit): through a local scratch row

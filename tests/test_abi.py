@@ -22,6 +22,7 @@ def declared_symbols():
     names -= {"plan_s", "nodes_s"}
     plain = set(re.findall(r"^\w[\w\s\*]*?\b(pnfft_b200_\w+)\s*\(", src, flags=re.M))
     mpi = set(re.findall(r"\b(MPI_\w+)\s*\(", open(os.path.join(ROOT, "include", "mpi.h")).read()))
+    mpi |= set(re.findall(r"\b(pfftf?_\w+)\s*\(", open(os.path.join(ROOT, "include", "pfft.h")).read()))
     return names, plain, mpi
 
 
