@@ -156,6 +156,7 @@ template <class R> struct Core {
     g.exp_const = p->d_exp_const;
     g.poly = (p->use_poly && p->poly_deg >= 0) ? p->d_poly : nullptr;
     g.poly_deg = p->poly_deg;
+    g.poly_deg_psi = p->poly_deg_psi;
     return g;
   }
 
@@ -190,6 +191,10 @@ template <class R> struct Core {
   // degree is raised until the next Chebyshev coefficients are below 5e-16 (double) / 1e-9 (float) of the window
   // maximum; if degree 24 is not enough the kernels keep the exact evaluation.
   static void fit_window_polys(P *p) {
+    // Double precision keeps the exact formulas: measured on B200 (C3) the node-table kernel is bound by row assembly
+    // and its HBM write, not by the window evaluation (exact 4.2 / 8.8 ms against 4.4 / 11.8 ms with degree 13 / 21
+    // polynomials), and the exact path follows the reference's arithmetic more closely.  Float uses the polynomials.
+    if (sizeof(R) == 8 && !getenv("PNFFT_B200_POLY_DOUBLE")) { p->poly_deg = p->poly_deg_psi = -1; return; }
     const Layout &L = p->L;
     const int c = L.cutoff, nv = 3 * c, m = L.m;
     const int NP = 48;
@@ -229,6 +234,15 @@ template <class R> struct Core {
       if (ok) deg = D;
     }
     p->poly_deg = deg;
+    // psi alone usually needs a lower degree than the derivative weights (Kaiser-Bessel m=6: 13 against 21)
+    p->poly_deg_psi = deg;
+    for (int D = 2; D < deg; D++) {
+      bool ok = true;
+      for (int v = 0; v < nv && ok; v++)
+        for (int k = D + 1; k <= D + 3; k++)
+          if (fabs(ck[(size_t)v * NP + k]) > rtol * vmax[0]) { ok = false; break; }
+      if (ok) { p->poly_deg_psi = D; break; }
+    }
     if (deg < 0) return;
     // Chebyshev -> monomial coefficients in u; device layout [set][k][v]
     std::vector<R> h((size_t)2 * (deg + 1) * nv);

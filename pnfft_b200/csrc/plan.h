@@ -92,6 +92,7 @@ template <class R> struct GridGeom {
   const R *exp_const;      // fast Gaussian table [3][cutoff] (device)
   const R *poly;           // per-tap window polynomials [deg+1][3*cutoff] in u = 2 frac - 1 (device) or nullptr
   int poly_deg;
+  int poly_deg_psi;        // degree that suffices for psi alone (<= poly_deg)
 };
 
 
@@ -152,7 +153,7 @@ template <class R> struct Plan {
   R *d_invphi_plain[3] = {nullptr, nullptr, nullptr};  // without the sign (for OMIT_FFT paths)
   R *d_exp_const = nullptr;      // [3][cutoff] for FAST_GAUSSIAN
   R *d_poly = nullptr;           // window polynomials (see GridGeom::poly)
-  int poly_deg = -1;
+  int poly_deg = -1, poly_deg_psi = -1;
   int use_poly = 1;
   void *d_grid = nullptr;        // padded grid [ngc0][ngc1][pitch2] of C (c2c) or R (c2r)
   void *d_work[2] = {nullptr, nullptr};  // ping-pong FFT stage buffers

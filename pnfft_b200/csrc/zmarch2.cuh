@@ -107,15 +107,17 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
         psi[s] = na.pre_psi[(size_t)p * 3 * C + t * C + s];
         if (GRAD) dpsi[s] = na.pre_dpsi[(size_t)p * 3 * C + t * C + s];
       }
-    } else if (g.poly && fr != (R)0) {
-      // per-tap polynomials in u = 2 frac - 1 (Core::fit_window_polys); all taps advance together (Horner)
+    } else if (g.poly && fr != (R)0 && (!GRAD || g.poly_deg <= 16)) {
+      // per-tap polynomials in u = 2 frac - 1 (Core::fit_window_polys); all taps advance together (Horner).  With the
+      // gradient the exact formulas are cheaper than two degree > 16 Horner chains per tap (measured).
       const R u = (R)2 * fr - (R)1;
+      const int dg = GRAD ? g.poly_deg : g.poly_deg_psi;
       const R *a = poly_s + t * C;
       const int nv = 3 * C;
       const R *ad = a + (g.poly_deg + 1) * nv;      // the derivative weights have their own fitted polynomials
 #pragma unroll
-      for (int s = 0; s < C; s++) { psi[s] = a[g.poly_deg * nv + s]; if (GRAD) dpsi[s] = ad[g.poly_deg * nv + s]; }
-      for (int k = g.poly_deg - 1; k >= 0; k--) {
+      for (int s = 0; s < C; s++) { psi[s] = a[dg * nv + s]; if (GRAD) dpsi[s] = ad[dg * nv + s]; }
+      for (int k = dg - 1; k >= 0; k--) {
 #pragma unroll
         for (int s = 0; s < C; s++) {
           if (GRAD) dpsi[s] = dpsi[s] * u + ad[k * nv + s];
