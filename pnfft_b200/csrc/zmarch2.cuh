@@ -196,7 +196,7 @@ template <class R, bool CPLX, int M_, bool GRAD> struct Zm2Smem {
   static constexpr int s_off_bar = s_off_ring + SS * s_stage;
   static constexpr int scatter = s_off_bar + 2 * SS * 8;
   // gather: one staging buffer per warp, ring, P stages of per-row partial sums
-  static constexpr int GS = 4, GP = 2;
+  static constexpr int GS = 4, GP = 3;
   static constexpr int GGB = GRAD ? 8 : 16;
   static constexpr int PN = Cfg::C * 16 * (GRAD ? 2 : 1);                 // partial cells per node
   static constexpr int g_stage = kZm2HdrBytes + GGB * RowG::ROWBYTES;
@@ -209,7 +209,7 @@ template <class R, bool CPLX, int M_, bool GRAD> struct Zm2Smem {
 };
 
 // mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of spinning on the issue port
-__device__ __forceinline__ void mbar_wait_park(unsigned long long *bar, unsigned phase) {
+__device__ __forceinline__ void mbar_wait_park(unsigned long long *bar, unsigned phase, unsigned ns = ZM2_PARK_NS) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -218,7 +218,7 @@ __device__ __forceinline__ void mbar_wait_park(unsigned long long *bar, unsigned
       "@p bra DONEP_%=;\n"
       "bra WAITP_%=;\n"
       "DONEP_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(phase), "r"(ZM2_PARK_NS) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase), "r"(ns) : "memory");
 }
 
 // z taps of one node from / into the register window; the z offset picks one of ZS statically indexed variants
@@ -537,62 +537,63 @@ template <int NV, int WIDTH, class R> __device__ __forceinline__ void lanes_redu
   *which = w;
 }
 
-// x-y contraction of the per-row partial sums of FOUR nodes by one warp, one node per quarter warp (8 lanes).  Lane l8
-// of a quarter walks the node's (2m+1) x 16 partials eight at a time: entry e = 8 it + l8 is x row it / 2 (the same for
-// the whole quarter) and y row 8 (it & 1) + l8, so a lane meets two y weights only and applies them once at the end.
-// The 8-lane reduction then leaves one output value per lane (with the gradient: exactly the 8 reals of f and grad f).
-template <class R, bool CPLX, int M_, bool GRAD, class Row, class Cell>
+// x-y contraction of the per-row partial sums of NPP nodes by one warp, LPN = 32 / NPP lanes per node.  Lane l of a
+// group walks the node's (2m+1) x 16 partials LPN at a time: entry e = LPN it + l is x row e / 16 (the same for the
+// whole group) and y row e % 16, so a lane meets 16 / LPN y weights only and applies them once at the end.  The
+// LPN-lane reduction then leaves one output value per lane group slot (lanes_reduce).
+template <int NPP, class R, bool CPLX, int M_, bool GRAD, class Row, class Cell>
 __device__ __forceinline__ void zm2_reduce_quad(const unsigned char *row, const Cell *pp, bool live, int lane, const GatherOut<R> &out) {
   typedef Zm2Cfg<M_> Cfg;
   constexpr int C = Cfg::C, T1 = Cfg::T1, NCOMP = CPLX ? 2 : 1, SZ = (int)sizeof(R);
-  const int l8 = lane & 7;
+  constexpr int LPN = 32 / NPP;          // lanes per node: 8 (four nodes per pass) or 16 (two nodes per pass)
+  constexpr int NY = 16 / LPN;           // y weights a lane meets
+  static_assert(LPN == 8 || LPN == 16, "two or four nodes per pass");
+  const int l = lane & (LPN - 1);
   const int *hd = reinterpret_cast<const int *>(row);
   const int ny = hd[1], j = hd[4];
   const R *rr = reinterpret_cast<const R *>(row);
-  R w1[2], dw1[2];
+  R w1[NY], dw1[NY];
 #pragma unroll
-  for (int b = 0; b < 2; b++) {
-    w1[b] = *reinterpret_cast<const R *>(row + (Row::oY + T1 - 1 + 8 * b + l8) * SZ + ny);
-    dw1[b] = GRAD ? *reinterpret_cast<const R *>(row + (Row::oDY + T1 - 1 + 8 * b + l8) * SZ + ny) : (R)0;
+  for (int b = 0; b < NY; b++) {
+    w1[b] = *reinterpret_cast<const R *>(row + (Row::oY + T1 - 1 + LPN * b + l) * SZ + ny);
+    dw1[b] = GRAD ? *reinterpret_cast<const R *>(row + (Row::oDY + T1 - 1 + LPN * b + l) * SZ + ny) : (R)0;
   }
-  Cell s[2], sd[2], u[2];
+  Cell s[NY], sd[NY], u[NY];
 #pragma unroll
-  for (int b = 0; b < 2; b++) { zero_cell(s[b]); zero_cell(sd[b]); zero_cell(u[b]); }
+  for (int b = 0; b < NY; b++) { zero_cell(s[b]); zero_cell(sd[b]); zero_cell(u[b]); }
 #pragma unroll
-  for (int it = 0; it < 2 * C; it++) {
-    const int i0 = it >> 1, b = it & 1;
+  for (int it = 0; it < NY * C; it++) {
+    const int i0 = it / NY, b = it % NY;
     const R w0 = rr[Row::oX + Cfg::XLEAD + i0];
-    const Cell t = pp[8 * it + l8];
+    const Cell t = pp[LPN * it + l];
     fma_cell(s[b], w0, t);
     if (GRAD) {
       const R dw0 = rr[Row::oDX + Cfg::XLEAD + i0];
-      const Cell td = pp[C * 16 + 8 * it + l8];
+      const Cell td = pp[C * 16 + LPN * it + l];
       fma_cell(sd[b], dw0, t);
       fma_cell(u[b], w0, td);
     }
   }
   constexpr int NVAL = NCOMP * (GRAD ? 4 : 1);
   R v[NVAL];
-  Cell af = scale_cell(w1[0], s[0]);
-  fma_cell(af, w1[1], s[1]);
+  Cell af = scale_cell(w1[0], s[0]), a0, a1, a2;
+  zero_cell(a0); zero_cell(a1); zero_cell(a2);
+  if (GRAD) { a0 = scale_cell(w1[0], sd[0]); a1 = scale_cell(dw1[0], s[0]); a2 = scale_cell(w1[0], u[0]); }
+#pragma unroll
+  for (int b = 1; b < NY; b++) {
+    fma_cell(af, w1[b], s[b]);
+    if (GRAD) { fma_cell(a0, w1[b], sd[b]); fma_cell(a1, dw1[b], s[b]); fma_cell(a2, w1[b], u[b]); }
+  }
   if constexpr (CPLX) {
     v[0] = af.x; v[1] = af.y;
-    if constexpr (GRAD) {
-      Cell a0 = scale_cell(w1[0], sd[0]), a1 = scale_cell(dw1[0], s[0]), a2 = scale_cell(w1[0], u[0]);
-      fma_cell(a0, w1[1], sd[1]); fma_cell(a1, dw1[1], s[1]); fma_cell(a2, w1[1], u[1]);
-      v[2] = a0.x; v[3] = a0.y; v[4] = a1.x; v[5] = a1.y; v[6] = a2.x; v[7] = a2.y;
-    }
+    if constexpr (GRAD) { v[2] = a0.x; v[3] = a0.y; v[4] = a1.x; v[5] = a1.y; v[6] = a2.x; v[7] = a2.y; }
   } else {
     v[0] = af;
-    if constexpr (GRAD) {
-      Cell a0 = scale_cell(w1[0], sd[0]), a1 = scale_cell(dw1[0], s[0]), a2 = scale_cell(w1[0], u[0]);
-      fma_cell(a0, w1[1], sd[1]); fma_cell(a1, dw1[1], s[1]); fma_cell(a2, w1[1], u[1]);
-      v[1] = a0; v[2] = a1; v[3] = a2;
-    }
+    if constexpr (GRAD) { v[1] = a0; v[2] = a1; v[3] = a2; }
   }
   int which;
-  lanes_reduce<NVAL, 8>(v, lane, &which);
-  if (live && (l8 & (8 / NVAL - 1)) == 0) {
+  lanes_reduce<NVAL, LPN>(v, lane, &which);
+  if (live && (l & (LPN / NVAL - 1)) == 0) {
     R *o = nullptr;
     if (which < NCOMP) { if (out.f) o = out.f + ((size_t)j * out.f_stride + out.f_off) * NCOMP + which; }
     else if (GRAD) o = out.grad + (size_t)j * 3 * NCOMP + (which - NCOMP);
@@ -722,17 +723,18 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
     const int st = kr % S, ps = kr % P;
     unsigned char *sp = ring + (size_t)st * STAGE;
     int *h = reinterpret_cast<int *>(sp);
-    mbar_wait_park(&pfull[ps], ((unsigned)(kr / P)) & 1u);
+    mbar_wait_park(&pfull[ps], ((unsigned)(kr / P)) & 1u, 50u);   // the reduction latency is on the critical path
     const int cnt = h[1];
     if (helper) {
       for (;;) {
         int i = 0;
-        if (lane == 0) i = atomicAdd(&h[3], 4);
+        constexpr int NPP = 4;     // nodes per warp pass (2: half a warp each, measured no faster)
+        if (lane == 0) i = atomicAdd(&h[3], NPP);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= cnt) break;
-        const int mine = i + (lane >> 3);
+        const int mine = i + lane / (32 / NPP);
         const int ic = mine < cnt ? mine : cnt - 1;
-        zm2_reduce_quad<R, CPLX, M_, GRAD, Row>(sp + kZm2HdrBytes + (size_t)ic * ROWBYTES, part + (size_t)(ps * GB + ic) * PN, mine < cnt, lane, out);
+        zm2_reduce_quad<NPP, R, CPLX, M_, GRAD, Row>(sp + kZm2HdrBytes + (size_t)ic * ROWBYTES, part + (size_t)(ps * GB + ic) * PN, mine < cnt, lane, out);
       }
     }
     __syncwarp();
