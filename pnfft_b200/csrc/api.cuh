@@ -454,6 +454,16 @@ void PNX(b200_window_tensor)(PNX(plan) ths, PNX(nodes) nodes, RT *psi, RT *dpsi)
 // 4: shared-memory tile kernels; 8: z-march v1 (CTA-synchronous) instead of the warp-autonomous v2
 void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant) { AS_PLAN(ths)->kernel_variant = variant & 13; AS_PLAN(ths)->use_poly = (variant & 2) ? 0 : 1; }
 int PNX(b200_get_poly_degree)(PNX(plan) ths) { return AS_PLAN(ths)->poly_deg; }
+#ifdef ZM2_TIMING
+// development aid: per-warp cycle accounting of k_gather_zm2 (build with -DZM2_TIMING)
+void PNX(b200_gather_timing)(long long *out96, int reset) {
+  static long long *d = nullptr;
+  if (!d) { cudaMalloc(&d, 96 * 8); cudaMemset(d, 0, 96 * 8); cudaMemcpyToSymbol(pnb::g_zm2_timing, &d, sizeof(d)); }
+  cudaDeviceSynchronize();
+  if (out96) cudaMemcpy(out96, d, 96 * 8, cudaMemcpyDeviceToHost);
+  if (reset) cudaMemset(d, 0, 96 * 8);
+}
+#endif
 void PNX(b200_get_stage_ms)(PNX(plan) ths, int adjoint, double *ms8) { for (int i = 0; i < 8; i++) ms8[i] = AS_PLAN(ths)->stage_ms[adjoint ? 1 : 0][i]; }
 long long PNX(b200_kernel_launches)(PNX(plan) ths) { return AS_PLAN(ths)->launches; }
 long long PNX(b200_library_calls)(PNX(plan) ths) { return AS_PLAN(ths)->lib_launches; }

@@ -601,6 +601,9 @@ __device__ __forceinline__ void zm2_reduce_quad(const unsigned char *row, const 
   }
 }
 
+#ifdef ZM2_TIMING
+__device__ long long *g_zm2_timing = nullptr;   // [warp][6]: wait full, wait pempty, window advance, node loop, arrive+help, loop top
+#endif
 template <class R, bool CPLX, int M_, bool GRAD>
 __global__ void __launch_bounds__((Zm2Cfg<M_>::NCW + 1) * 32, 1)
 k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__restrict__ tab, const int *__restrict__ bin_start,
@@ -723,9 +726,10 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
     const int st = kr % S, ps = kr % P;
     unsigned char *sp = ring + (size_t)st * STAGE;
     int *h = reinterpret_cast<int *>(sp);
-    mbar_wait_park(&pfull[ps], ((unsigned)(kr / P)) & 1u, 50u);   // the reduction latency is on the critical path
-    const int cnt = h[1];
+    // (the critical warps neither reduce nor wait: their arrivals below only count them out of the two stages)
     if (helper) {
+      mbar_wait_park(&pfull[ps], ((unsigned)(kr / P)) & 1u, 50u);   // the reduction latency is on the critical path
+      const int cnt = h[1];
       for (;;) {
         int i = 0;
         constexpr int NPP = 4;     // nodes per warp pass (2: half a warp each, measured no faster)
@@ -743,21 +747,31 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
 
   const int aP = (rbase * 16 + r1);
   int kb = 0;
+#ifdef ZM2_TIMING
+  long long tq[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
+#define ZM2_T(i) do { const long long now_ = clock64(); tq[i] += now_ - tc; tc = now_; } while (0)
+#else
+#define ZM2_T(i) do { } while (0)
+#endif
   for (;; kb++) {
     const int st = kb % S, ps = kb % P;
+    ZM2_T(5);
     mbar_wait_park(&full[st], ((unsigned)(kb / S)) & 1u);
+    ZM2_T(0);
     const unsigned char *sp = ring + (size_t)st * STAGE;
     const int *h = reinterpret_cast<const int *>(sp);
     const int tz = h[0];
     if (tz == INT_MAX) break;
     const int lo = h[4 + dxlo], hi = h[4 + dxhi1];
     mbar_wait_park(&pempty[ps], (((unsigned)(kb / P)) & 1u) ^ 1u);
+    ZM2_T(1);
     if (hi > lo) {
       if (tz != cur) {
         if (pending && tz == cur + 1) advance1();
         else if (pending && tz == cur + 2) { advance1(); advance1(); }
         else reload(tz);
       }
+      ZM2_T(2);
       const unsigned char *row = sp + kZm2HdrBytes + (size_t)lo * ROWBYTES;
       const unsigned char *last = sp + kZm2HdrBytes + (size_t)(hi - 1) * ROWBYTES;
       Cell *pb = part + (size_t)(ps * GB + lo) * PN + aP;
@@ -808,11 +822,16 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
         hd = hn; row = row1;
       }
     }
+    ZM2_T(3);
     __syncwarp();
     if (lane == 0) mbar_arrive(&pfull[ps]);
     if (kb >= 1) help(kb - 1);
+    ZM2_T(4);
   }
   if (kb >= 1) help(kb - 1);
+#ifdef ZM2_TIMING
+  if (lane == 0 && g_zm2_timing) for (int i = 0; i < 6; i++) atomicAdd((unsigned long long *)&g_zm2_timing[warp * 6 + i], (unsigned long long)tq[i]);
+#endif
   drop_pending();    // no TMA write may still be in flight when the CTA retires
 }
 

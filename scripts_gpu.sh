@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for cf in 1 3; do echo "== variant 0 cf $cf"; timeout 300 python tools/quick_bench.py 256 16777216 $cf 6 0 0 2>&1 | tail -3; done
+RPT2=1 python tools/gather_timing.py 3 2>&1 | tail -9
