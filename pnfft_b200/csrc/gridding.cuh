@@ -135,6 +135,13 @@ __global__ void k_bin_nodes(GridGeom<R> g, TileGeom tg, const R *__restrict__ x,
   atomicAdd(&tile_count[tile], 1);
 }
 
+// largest node count of a column tile (z-march v2 load-balance hint): bins of one column are contiguous in tile_start
+static __global__ void k_max_column(const int *__restrict__ tile_start, int ncol, int bins_per_col, int *__restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  atomicMax(out, tile_start[(size_t)(c + 1) * bins_per_col] - tile_start[(size_t)c * bins_per_col]);
+}
+
 static __global__ void k_items_per_tile(TileGeom tg, const int *__restrict__ tile_count, int *__restrict__ n_items) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > tg.ntiles) return;

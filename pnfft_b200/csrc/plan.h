@@ -207,6 +207,8 @@ template <class R> struct Nodes {
   bool binned = false;         // valid for the current x (only kept across calls after precompute_psi)
   const R *d_x_bound = nullptr; // device x the binning / tables were computed from
   long long max_items = 0;     // launch bound for the tiled kernels
+  int *h_maxcol = nullptr;     // pinned: largest column population seen by the last finished binning (load-balance hint)
+  int *d_maxcol = nullptr;
 
   // PNFFT_PRE_PSI tables in sorted order (reference kernel/ndft-parallel.c:1184-1240)
   R *d_pre_psi = nullptr, *d_pre_dpsi = nullptr;
