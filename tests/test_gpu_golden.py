@@ -58,10 +58,10 @@ def test_families_agree(c2r, single, m):
 
 
 @pytest.mark.parametrize("cf", [F, F | G])
-def test_adjointness_large(cf):
-    """<B f_hat, f> == <f_hat, B^H f> with 2^20 nodes on N=64^3 (no oracle involved): the gather and the scatter
-    are transposes of each other to rounding."""
-    N, M = (64, 64, 64), 1 << 20
+def test_adjointness_c2_full_size(cf):
+    """BASELINE config 2 at full size (N=128^3, n=256^3, M=2^21 uniform nodes, Kaiser-Bessel m=6, double):
+    <A f_hat, (f, g)> == <f_hat, A^H (f, g)> for the whole transform pair (D, F and B included), no oracle involved."""
+    N, M = (128, 128, 128), 1 << 21
     x, fh, f, g = make_inputs(N, M, 31)
     run = Run1(N, x, m=6)
     fo, go = run.trafo(fh, cf)
@@ -70,6 +70,84 @@ def test_adjointness_large(cf):
     lhs = np.vdot(f, fo) + (np.vdot(g, go) if cf & G else 0.0)
     rhs = np.vdot(fho, fh)
     assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+
+
+def test_c3_full_size_properties():
+    """BASELINE config 3 (the bench workload) at full size: N=256^3, n=512^3, M=2^24, Kaiser-Bessel m=6, double.
+    Adjointness of the pair, and trafo(F|GRAD_F) agrees with trafo(F) on f (two different kernel instantiations)."""
+    N, M = (256, 256, 256), 1 << 24
+    rng = np.random.default_rng(71)
+    x = np.clip(rng.uniform(-0.5, 0.5, (M, 3)), -0.5, np.nextafter(0.5, 0.0))
+    fh = (rng.uniform(-1, 1, N) + 1j * rng.uniform(-1, 1, N))
+    f = rng.uniform(-1, 1, M) + 1j * rng.uniform(-1, 1, M)
+    run = Run1(N, x, m=6)
+    f1, _ = run.trafo(fh, F)
+    f2, g2 = run.trafo(fh, F | G)
+    fho = run.adj(f, None, F)
+    run.close()
+    assert rel_l2(f2, f1) <= 1e-13
+    assert np.all(np.isfinite(g2.view(np.float64)))
+    lhs, rhs = np.vdot(f, f1), np.vdot(fho, fh)
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+
+
+@pytest.mark.parametrize("win", [A.WINDOW_GAUSSIAN, A.WINDOW_GAUSSIAN | A.FAST_GAUSSIAN, A.WINDOW_BSPLINE])
+def test_c4_clustered_m8(ref, win):
+    """BASELINE config 4 in miniature: strongly clustered (Gaussian blob, sigma = 0.05) nodes, Gaussian / fast Gaussian /
+    B-spline windows with m=8, PRE_PSI against on-the-fly, against the reference on a node subset."""
+    N, M = (64, 64, 64), 1 << 17
+    rng = np.random.default_rng(81)
+    x = np.mod(rng.normal(0.0, 0.05, (M, 3)) + 0.5, 1.0) - 0.5
+    x = np.clip(x, -0.5, np.nextafter(0.5, 0.0))
+    _, fh, f, g = make_inputs(N, M, 82)
+    run = Run1(N, x, m=8, flags=win)
+    f0, g0 = run.trafo(fh, F | G)
+    h0 = run.adj(f, g, F | G)
+    run.plan.precompute_psi(run.nodes, A.PRE_PSI | A.PRE_GRAD_PSI)
+    f1, g1 = run.trafo(fh, F | G)
+    h1 = run.adj(f, g, F | G)
+    run.close()
+    assert rel_l2(f1, f0) <= 1e-13 and rel_l2(g1, g0) <= 1e-13 and rel_l2(h1, h0) <= 1e-13
+    sub = slice(0, 4096)
+    rt = ref.trafo(N, x[sub], fh, m=8, pnfft_flags=win, compute_flags=F | G)
+    assert rel_l2(f0[sub], rt["f"]) <= 1e-13 and rel_l2(g0[sub], rt["grad_f"]) <= 1e-13
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_c5_c2r_variants(single):
+    """BASELINE config 5 in miniature (c2r real input, double and single precision, N=64^3, M=2^18): the real-valued
+    transforms against the complex ones on the same data, and float against double."""
+    N, M = (64, 64, 64), 1 << 18
+    x, fh, f, g = make_inputs(N, M, 91, c2r=True, single=single)
+    # f_hat = A^H f of a real vector is a Hermitian-consistent half spectrum; scale it to O(1) so that the second
+    # transform stays inside the float range (the Kaiser-Bessel window is not normalised: psi ~ 5e10 at m = 6)
+    run = Run1(N, x, m=6, c2r=True, single=single)
+    h1 = run.adj(f, g, F)
+    scale = 1.0 / np.abs(h1).max()
+    # c2r against c2c on the same real data (the reference's own check, tests/simple_test_c2r_c2c_compare_*.c): the stored
+    # half spectrum k2 in [-N2/2, 0] of the real adjoint equals that part of the complex adjoint of (f + 0i)
+    cdt = np.complex64 if single else np.complex128
+    runc = Run1(N, x, m=6, c2r=False, single=single)
+    hc = runc.adj(f.astype(cdt), g.astype(cdt), F)
+    tol = 2e-5 if single else 1e-13
+    assert rel_l2(h1, hc[:, :, :N[2] // 2 + 1]) <= tol, "adjoint: c2r half spectrum vs c2c"
+    # trafo: the planes k_t = -N_t/2 have no mirror partner inside [-N/2, N/2), so only a spectrum without them is
+    # Hermitian in the sense the c2r transform assumes; zero them on both sides, then c2r == Re(c2c), Im(c2c) == 0
+    hz, hcz = (h1 * scale).astype(h1.dtype), (hc * scale).astype(hc.dtype)
+    for a in (hz, hcz):
+        a[0, :, :] = 0; a[:, 0, :] = 0; a[:, :, 0] = 0
+    f1, _ = run.trafo(hz, F)
+    fc, _ = runc.trafo(hcz, F)
+    run.close(); runc.close()
+    assert np.all(np.isfinite(f1))
+    assert rel_l2(f1, fc.real) <= (1e-4 if single else 1e-12), "trafo: c2r vs Re(c2c)"
+    assert np.abs(fc.imag).max() <= (1e-4 if single else 1e-12) * np.abs(fc.real).max(), "trafo: Im(c2c) of a Hermitian spectrum"
+    if single:
+        xd, _, fd, gd = make_inputs(N, M, 91, c2r=True, single=True)
+        rund = Run1(N, xd.astype(np.float64), m=6, c2r=True, single=False)
+        h1d = rund.adj(fd.astype(np.float64), gd.astype(np.float64), F)
+        rund.close()
+        assert rel_l2(h1, h1d) <= 1e-5
 
 
 def test_linearity_and_accumulate():
