@@ -1,2 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests/test_gpu_golden.py -m gpu -x -q -k "c2_full or c3_full or c4_ or c5_" --durations=8 2>&1 | tail -22
+for cf in 1 3; do timeout 300 python tools/quick_bench.py 256 16777216 $cf 6 0 0 2>&1 | tail -3; done
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
