@@ -458,10 +458,10 @@ int PNX(b200_get_poly_degree)(PNX(plan) ths) { return AS_PLAN(ths)->poly_deg; }
 // development aid: per-warp cycle accounting of k_gather_zm2 (build with -DZM2_TIMING)
 void PNX(b200_gather_timing)(long long *out96, int reset) {
   static long long *d = nullptr;
-  if (!d) { cudaMalloc(&d, 96 * 8); cudaMemset(d, 0, 96 * 8); cudaMemcpyToSymbol(pnb::g_zm2_timing, &d, sizeof(d)); }
+  if (!d) { cudaMalloc(&d, 112 * 8); cudaMemset(d, 0, 112 * 8); cudaMemcpyToSymbol(pnb::g_zm2_timing, &d, sizeof(d)); }
   cudaDeviceSynchronize();
-  if (out96) cudaMemcpy(out96, d, 96 * 8, cudaMemcpyDeviceToHost);
-  if (reset) cudaMemset(d, 0, 96 * 8);
+  if (out96) cudaMemcpy(out96, d, 112 * 8, cudaMemcpyDeviceToHost);
+  if (reset) { cudaMemset(d, 0, 96 * 8); cudaMemset(d + 96, 0x3f, 16 * 8); }
 }
 #endif
 void PNX(b200_get_stage_ms)(PNX(plan) ths, int adjoint, double *ms8) { for (int i = 0; i < 8; i++) ms8[i] = AS_PLAN(ths)->stage_ms[adjoint ? 1 : 0][i]; }

@@ -748,7 +748,7 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
   const int aP = (rbase * 16 + r1);
   int kb = 0;
 #ifdef ZM2_TIMING
-  long long tq[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
+  long long tq[6] = {0, 0, 0, 0, 0, 0}, tc = clock64(), tit = 0, itsum = 0, itn = 0, itmin = 1LL << 40;
 #define ZM2_T(i) do { const long long now_ = clock64(); tq[i] += now_ - tc; tc = now_; } while (0)
 #else
 #define ZM2_T(i) do { } while (0)
@@ -785,6 +785,9 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
         if (GRAD) DQ[j] = *reinterpret_cast<const Quad *>(row + (Row::oDZ + j * PER) * SZ);
       }
       for (int i = lo; i < hi; i++, pb += PN) {
+#ifdef ZM2_TIMING
+        { const long long now_ = clock64(); if (i > lo) { const long long d_ = now_ - tit; itsum += d_; itn++; if (d_ < itmin) itmin = d_; } tit = now_; }
+#endif
         const unsigned char *row1 = row + ROWBYTES < last ? row + ROWBYTES : last;
         const int4 hn = *reinterpret_cast<const int4 *>(row1);       // prefetch the next header
         Cell t[RPT], td[RPT], t1[RPT];       // F only: two chains per sum; with the gradient the sums are chains enough
@@ -830,7 +833,12 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
   }
   if (kb >= 1) help(kb - 1);
 #ifdef ZM2_TIMING
-  if (lane == 0 && g_zm2_timing) for (int i = 0; i < 6; i++) atomicAdd((unsigned long long *)&g_zm2_timing[warp * 6 + i], (unsigned long long)tq[i]);
+  if (lane == 0 && g_zm2_timing) {
+    for (int i = 0; i < 6; i++) atomicAdd((unsigned long long *)&g_zm2_timing[warp * 6 + i], (unsigned long long)tq[i]);
+    atomicAdd((unsigned long long *)&g_zm2_timing[72 + warp * 2], (unsigned long long)itsum);
+    atomicAdd((unsigned long long *)&g_zm2_timing[72 + warp * 2 + 1], (unsigned long long)itn);
+    atomicMin((long long *)&g_zm2_timing[96 + warp], itmin);
+  }
 #endif
   drop_pending();    // no TMA write may still be in flight when the CTA retires
 }

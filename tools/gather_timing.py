@@ -15,7 +15,7 @@ comm = A.create_procmesh_2d(1, 1)
 plan = A.Plan.init_guru(N, tuple(2 * v for v in N), (0.5,) * 3, 6, 0, comm)
 nodes = A.Nodes(M, 0); nodes.set_x(x); nodes.set_f(f); nodes.set_grad_f(gr); plan.set_f_hat(fh)
 fn = A.lib().pnfft_b200_gather_timing
-out = np.zeros((16, 6), np.int64)
+out = np.zeros(112, np.int64)
 fn(None, 1)
 plan.trafo(nodes, cf)
 fn(None, 1)
@@ -25,5 +25,8 @@ names = ["wait_full", "wait_pempty", "advance", "node_loop", "arrive+help", "loo
 nblk = (43 if os.environ.get("RPT2") else 52) * 128
 print("kernel b_kernel ms", plan.stage_ms(False)["b_kernel"])
 print("per-warp cycles per CTA-average (kilo-cycles), columns:", names)
+tq = out[:96].reshape(16, 6)
 for w in range(6 if os.environ.get("RPT2") else 11):
-    print(w, ["%8.1f" % (v / nblk / 1e3) for v in out[w]], "total %.1f" % (out[w].sum() / nblk / 1e3))
+    itsum, itn, itmin = out[72 + 2 * w], out[72 + 2 * w + 1], out[96 + w]
+    print(w, ["%8.1f" % (v / nblk / 1e3) for v in tq[w]], "total %.1f" % (tq[w].sum() / nblk / 1e3),
+          "| node iteration: mean %.0f min %d cycles over %d" % (itsum / max(itn, 1), itmin, itn))
