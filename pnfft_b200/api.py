@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpnfft_b200.so")
+LIB_PATH = os.environ.get("PNFFT_B200_LIB") or os.path.join(HERE, "lib", "libpnfft_b200.so")   # (override: development builds)
 
 # ---- flag values (include/pnfft.h == reference api/pnfft.h:302-390) ----
 PRE_PHI_HAT = 1 << 0

@@ -149,6 +149,59 @@ template <class R> PNB_HD void bspline_taps(int m, R frac, R n, R *psi, R *dpsi)
 }
 
 // One tap of a point-wise window: y = l - n x (grid units), z = -y.  want_d: also the AD gradient weight.
+// exp(x) for 0 <= x < 700 without the range / special-case handling of the library routine: x = k ln2 + r with
+// |r| <= ln2 / 2 (two-term Cody-Waite), degree-13 Taylor polynomial (truncation < 2^-57), 2^k through the exponent field.
+PNB_HD double exp_pos(double x) {
+  const double k = rint(x * 1.4426950408889634074);
+  double r = fma(-k, 6.93147180369123816490e-01, x);
+  r = fma(-k, 1.90821492927058770002e-10, r);
+  double p = 1.0 / 6227020800.0;
+  p = fma(p, r, 1.0 / 479001600.0);
+  p = fma(p, r, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(__double_as_longlong(p) + ((long long)(int)k << 52));
+#else
+  return ldexp(p, (int)k);
+#endif
+}
+
+// Kaiser-Bessel tap and derivative in double with ONE exponential and ONE division (kernel/ndft-parallel.c:2241-2269
+// evaluates sinh, cosh and three quotients per tap).  Same formulas, a few ulp from the library-call version; taps with
+// b r < 0.5 (sinh would cancel) fall through to window_tap.
+PNB_HD bool kb_tap_fast(double y, double n, double b, int m, bool want_d, double *psi_out, double *dpsi_out) {
+  const double d = (double)m * (double)m - y * y;
+  const double inv_pi = 0.31830988618379067154;
+  const double r = sqrt(fabs(d)), x = b * r;
+  if (!(x >= 0.5)) return false;
+  if (d < 0.0) {                                   // the tap beyond the main lobe: sin / cos, one argument reduction
+    double sn, cs;
+    sincos(x, &sn, &cs);
+    const double inv_r = 1.0 / r;
+    const double psi = sn * inv_r * inv_pi;
+    *psi_out = psi;
+    if (want_d) *dpsi_out = n * y * (inv_r * inv_r) * (psi - (b * inv_pi) * cs);
+    return true;
+  }
+  const double e = exp_pos(x);
+  const double q = 1.0 / (e * r);
+  const double ei = q * r, inv_r = q * e;          // 1 / e, 1 / r
+  const double psi = (0.5 * (e - ei)) * inv_r * inv_pi;
+  *psi_out = psi;
+  if (want_d) *dpsi_out = n * (-y) * (inv_r * inv_r) * (psi - (b * inv_pi) * (0.5 * (e + ei)));
+  return true;
+}
+
 template <class R> PNB_HD void window_tap(int kind, R y, R n, R b, int m, bool want_d, R *psi_out, R *dpsi_out) {
   const R pi = m_pi<R>();
   R psi = (R)0, dpsi = (R)0;

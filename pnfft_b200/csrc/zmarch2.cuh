@@ -30,6 +30,15 @@ namespace pnb {
 #ifndef ZM2_RPT
 #define ZM2_RPT 1
 #endif
+#ifndef ZM2_DZ_STATIC
+#define ZM2_DZ_STATIC 0     // measured on B200 (C3): 19 % fewer DFMA, but gather F +8 %, scatter F +17 %, gather F+grad -2 %
+#endif
+#ifndef ZM2_GCHAINS
+#define ZM2_GCHAINS 1       // accumulation chains per sum of the gradient gather
+#endif
+#ifndef ZM2_DEPTH
+#define ZM2_DEPTH 4         // z weight quads in flight
+#endif
 template <int M_> struct Zm2Cfg {
   static constexpr int C = 2 * M_ + 1;
   static constexpr int R1 = 16;                  // footprint rows along y: half a warp
@@ -45,6 +54,10 @@ template <int M_> struct Zm2Cfg {
   static constexpr int W = ZS + 2 * M_;          // register window (cells) per row
   static constexpr int NFL = (W + ZS - 1) / ZS;  // flushes until a touched window is all zero again
   static constexpr int XLEAD = XW - 1;           // zero padding in front of the x weights
+  // z taps: true = the table stores psi_z unshifted and the node loops dispatch on the node's z offset inside its
+  // sub-chunk (ZS statically indexed copies of the tap loop, 2m+1 taps each); false = psi_z stored shifted by that
+  // offset and zero padded to W (one branch-free loop over all W window cells, (W - 2m - 1) / W of its FMAs on zeros)
+  static constexpr bool DZS = ZM2_DZ_STATIC != 0;
   static_assert(T1 >= 1 && R0 % XW == 0 && W % ZB == 0 && ZS % ZB == 0 && T0 <= SUB, "unsupported cutoff");
 };
 
@@ -56,8 +69,9 @@ struct Zm2Geom {
 };
 
 // Node-table row (units of R).  hdr = 8 ints {-dx*sizeof(R), -dy*sizeof(R), dz, dx, node index j, 0, 0, 0};
-// X = [0 x XLEAD, psi_x[0..C), 0 x XLEAD...], Y = [0 x (T1-1), psi_y[0..C), 0 x (T1-1)...], Z = [0 x dz, psi_z[0..C), 0...] of length W: the z weights
-// already aligned with the register window of the node's sub-chunk, so the kernels need no per-node dispatch on dz;
+// X = [0 x XLEAD, psi_x[0..C), 0 x XLEAD...], Y = [0 x (T1-1), psi_y[0..C), 0 x (T1-1)...], Z = psi_z[0..C) zero padded to ZP
+// (Cfg::DZS: the node loops dispatch on the header's dz) or [0 x dz, psi_z[0..C), 0...] of length W, already aligned with
+// the register window of the node's sub-chunk (no dispatch, but W instead of 2m+1 taps per node and row);
 // the same three rows of dpsi when GRAD; vals = f (and grad_f) of the node for the adjoint.
 template <class R, int M_, bool GRAD, bool VALS, bool CPLX> struct Zm2Row {
   typedef Zm2Cfg<M_> Cfg;
@@ -91,6 +105,8 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
   R *rows = reinterpret_cast<R *>(smem_raw);
   R *poly_s = rows + (size_t)kZm2TabNodes * Row::ROWLEN;
   if (g.poly) for (int i = threadIdx.x; i < (GRAD ? 2 : 1) * (g.poly_deg + 1) * 3 * C; i += blockDim.x) poly_s[i] = g.poly[i];
+  // the rows are zero padded: clear them once with 16-byte stores, the threads then write the taps only
+  for (int i = threadIdx.x; i < kZm2TabNodes * (Row::ROWBYTES / 16); i += blockDim.x) reinterpret_cast<uint4 *>(rows)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   const int p0 = blockIdx.x * kZm2TabNodes;
   const int nn = min(kZm2TabNodes, na.M - p0);
@@ -101,6 +117,7 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
     const R nxv = mul_rn(g.n[t], na.x[3 * (size_t)j + t]);
     const R flv = m_floor(nxv), fr = nxv - flv;
     R psi[C], dpsi[GRAD ? C : 1];
+    unsigned slow = 0;       // taps to redo with the library-call formulas
     if (na.pre_psi) {
 #pragma unroll
       for (int s = 0; s < C; s++) {
@@ -123,6 +140,16 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
           if (GRAD) dpsi[s] = dpsi[s] * u + ad[k * nv + s];
           psi[s] = psi[s] * u + a[k * nv + s];
         }
+      }
+    } else if (sizeof(R) == 8 && g.kind == WIN_KAISER_BESSEL) {
+      // one exponential and one division per tap (window.h: kb_tap_fast); the rare small-argument taps are redone with
+      // the library-call formulas below, straight into the shared-memory row
+#pragma unroll
+      for (int s = 0; s < C; s++) {
+        double a = 0, b = 0;
+        if (!kb_tap_fast((double)(flv - nxv - (R)M_ + (R)s), (double)g.n[t], (double)g.b[t], M_, GRAD, &a, &b)) slow |= 1u << s;
+        psi[s] = (R)a;
+        if (GRAD) dpsi[s] = (R)b;
       }
     } else {
       // exact formulas (nodes on a grid line, windows without a polynomial fit): through a local scratch row
@@ -152,19 +179,26 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
     }
     R *row = rows + (size_t)ln * Row::ROWLEN;
     const int off = t == 0 ? Row::oX : (t == 1 ? Row::oY : Row::oZ);
-    const int len = t == 0 ? Row::XP : (t == 1 ? Row::YP : Row::ZP);
     const int cell = (int)flv - g.los[t];
     const int T = t == 0 ? Cfg::T0 : (t == 1 ? Cfg::T1 : Cfg::ZS);
     const int d = cell - (cell / T) * T;
-    const int lead = t == 0 ? Cfg::XLEAD : (t == 1 ? Cfg::T1 - 1 : min(max(d, 0), Cfg::ZS - 1));
-    for (int i = 0; i < len; i++) { row[off + i] = (R)0; if (GRAD) row[off + (Row::oDX - Row::oX) + i] = (R)0; }
+    const int dzc = min(max(d, 0), Cfg::ZS - 1);
+    const int lead = t == 0 ? Cfg::XLEAD : (t == 1 ? Cfg::T1 - 1 : (Cfg::DZS ? 0 : dzc));
 #pragma unroll
     for (int s = 0; s < C; s++) { row[off + lead + s] = psi[s]; if (GRAD) row[off + (Row::oDX - Row::oX) + lead + s] = dpsi[s]; }
+    while (slow) {
+      const int s = __ffs(slow) - 1;
+      slow &= slow - 1;
+      R a = (R)0, b = (R)0;
+      window_tap<R>(WIN_KAISER_BESSEL, flv - nxv - (R)M_ + (R)s, g.n[t], g.b[t], M_, GRAD, &a, &b);
+      row[off + lead + s] = a;
+      if (GRAD) row[off + (Row::oDX - Row::oX) + lead + s] = b;
+    }
     // cell offset inside the (T0, T1, ZS) tile
     int *h = reinterpret_cast<int *>(row);
     if (t == 0) { h[0] = -d * (int)sizeof(R); h[3] = d; h[4] = j; }
     else if (t == 1) { h[1] = -d * (int)sizeof(R); h[5] = 0; }
-    else { h[2] = d; h[6] = 0; h[7] = 0; }
+    else { h[2] = dzc; h[6] = 0; h[7] = 0; }
     if (VALS && t == 0) {
       R *v = row + Row::oV;
       for (int c = 0; c < Row::NV; c++) v[c] = (R)0;
@@ -335,7 +369,7 @@ template <> struct ZQuad<float> { typedef float4 type; static constexpr int PER 
 __device__ __forceinline__ double zq_get(const double2 &q, int e) { return e == 0 ? q.x : q.y; }
 __device__ __forceinline__ float zq_get(const float4 &q, int e) { return e == 0 ? q.x : (e == 1 ? q.y : (e == 2 ? q.z : q.w)); }
 template <int NQT, bool GRAD> constexpr int zm2_depth() {
-  constexpr int dmax = 4;   // (two quads in flight measured 2 % slower for the gradient gather, splitting its sums into two chains 3 % slower)
+  constexpr int dmax = ZM2_DEPTH;   // (two quads in flight measured 2 % slower for the gradient gather, splitting its sums into two chains 3 % slower)
   return (dmax >= 4 && NQT % 4 == 0) ? 4 : ((dmax >= 3 && NQT % 3 == 0) ? 3 : ((NQT % 2 == 0) ? 2 : 1));
 }
 
@@ -482,26 +516,38 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
         const unsigned char *row2 = row1 + ROWBYTES < last ? row1 + ROWBYTES : last;
         const int4 hn2 = *reinterpret_cast<const int4 *>(row2);
         fetch(row1, hn, op);
+        auto ztaps = [&](auto dz_tag) {
+          constexpr int DZ = decltype(dz_tag)::value;     // first window cell of the node's taps
+          constexpr int NT = Cfg::DZS ? C : W;
 #pragma unroll
-        for (int j = 0; j < NQT; j++) {
-          const Quad w = Q[j % D];
-          Quad dw = w;
-          if (GRAD) dw = DQ[j % D];
-          const unsigned char *src = (j + D < NQT) ? row : row1;
-          const int jq = (j + D < NQT) ? j + D : j + D - NQT;
-          Q[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oZ + jq * PER) * SZ);
-          if (GRAD) DQ[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oDZ + jq * PER) * SZ);
+          for (int j = 0; j < NQT; j++) {
+            const Quad w = Q[j % D];
+            Quad dw = w;
+            if (GRAD) dw = DQ[j % D];
+            const unsigned char *src = (j + D < NQT) ? row : row1;
+            const int jq = (j + D < NQT) ? j + D : j + D - NQT;
+            Q[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oZ + jq * PER) * SZ);
+            if (GRAD) DQ[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oDZ + jq * PER) * SZ);
 #pragma unroll
-          for (int e = 0; e < PER; e++) {
-            const int k = j * PER + e;
-            if (k < W) {
+            for (int e = 0; e < PER; e++) {
+              const int k = j * PER + e;
+              if (k < NT) {
 #pragma unroll
-              for (int r = 0; r < RPT; r++) {
-                fma_cell(win[r][k], zq_get(w, e), A[r]);
-                if (GRAD) fma_cell(win[r][k], zq_get(dw, e), B[r]);
+                for (int r = 0; r < RPT; r++) {
+                  fma_cell(win[r][DZ + k], zq_get(w, e), A[r]);
+                  if (GRAD) fma_cell(win[r][DZ + k], zq_get(dw, e), B[r]);
+                }
               }
             }
           }
+        };
+        if constexpr (Cfg::DZS) {
+          const int dz = hd.z;
+#define ZM2_CALL(d_) ztaps(std::integral_constant<int, (d_)>())
+          ZM2_TREE(dz, ZM2_CALL);
+#undef ZM2_CALL
+        } else {
+          ztaps(std::integral_constant<int, 0>());
         }
         hd = hn; hn = hn2; row = row1; row1 = row2;
       }
@@ -790,36 +836,53 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
 #endif
         const unsigned char *row1 = row + ROWBYTES < last ? row + ROWBYTES : last;
         const int4 hn = *reinterpret_cast<const int4 *>(row1);       // prefetch the next header
-        Cell t[RPT], td[RPT], t1[RPT];       // F only: two chains per sum; with the gradient the sums are chains enough
+        Cell t[RPT], td[RPT], t1[RPT], td1[RPT];       // F only: two chains per sum; with the gradient the sums are chains enough
 #pragma unroll
-        for (int r = 0; r < RPT; r++) { zero_cell(t[r]); zero_cell(td[r]); zero_cell(t1[r]); }
+        for (int r = 0; r < RPT; r++) { zero_cell(t[r]); zero_cell(td[r]); zero_cell(t1[r]); zero_cell(td1[r]); }
+        auto ztaps = [&](auto dz_tag) {
+          constexpr int DZ = decltype(dz_tag)::value;     // first window cell of the node's taps
+          constexpr int NT = Cfg::DZS ? C : W;
 #pragma unroll
-        for (int j = 0; j < NQT; j++) {
-          const Quad w = Q[j % D];
-          Quad dw = w;
-          if (GRAD) dw = DQ[j % D];
-          const unsigned char *src = (j + D < NQT) ? row : row1;
-          const int jq = (j + D < NQT) ? j + D : j + D - NQT;
-          Q[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oZ + jq * PER) * SZ);
-          if (GRAD) DQ[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oDZ + jq * PER) * SZ);
+          for (int j = 0; j < NQT; j++) {
+            const Quad w = Q[j % D];
+            Quad dw = w;
+            if (GRAD) dw = DQ[j % D];
+            const unsigned char *src = (j + D < NQT) ? row : row1;
+            const int jq = (j + D < NQT) ? j + D : j + D - NQT;
+            Q[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oZ + jq * PER) * SZ);
+            if (GRAD) DQ[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oDZ + jq * PER) * SZ);
 #pragma unroll
-          for (int e = 0; e < PER; e++) {
-            const int k = j * PER + e;
-            if (k < W) {
+            for (int e = 0; e < PER; e++) {
+              const int k = j * PER + e;
+              if (k < NT) {
 #pragma unroll
-              for (int r = 0; r < RPT; r++) {
-                if (GRAD) { fma_cell(t[r], zq_get(w, e), win[r][k]); fma_cell(td[r], zq_get(dw, e), win[r][k]); }
-                else if (k & 1) fma_cell(t1[r], zq_get(w, e), win[r][k]);
-                else fma_cell(t[r], zq_get(w, e), win[r][k]);
+                for (int r = 0; r < RPT; r++) {
+                  if (GRAD && ZM2_GCHAINS == 2) {
+                    if (k & 1) { fma_cell(t1[r], zq_get(w, e), win[r][DZ + k]); fma_cell(td1[r], zq_get(dw, e), win[r][DZ + k]); }
+                    else { fma_cell(t[r], zq_get(w, e), win[r][DZ + k]); fma_cell(td[r], zq_get(dw, e), win[r][DZ + k]); }
+                  }
+                  else if (GRAD) { fma_cell(t[r], zq_get(w, e), win[r][DZ + k]); fma_cell(td[r], zq_get(dw, e), win[r][DZ + k]); }
+                  else if (k & 1) fma_cell(t1[r], zq_get(w, e), win[r][DZ + k]);
+                  else fma_cell(t[r], zq_get(w, e), win[r][DZ + k]);
+                }
               }
             }
           }
+        };
+        if constexpr (Cfg::DZS) {
+          const int dz = hd.z;
+#define ZM2_CALL(d_) ztaps(std::integral_constant<int, (d_)>())
+          ZM2_TREE(dz, ZM2_CALL);
+#undef ZM2_CALL
+        } else {
+          ztaps(std::integral_constant<int, 0>());
         }
         const int i0 = rbase - hd.w;
         Cell *p = pb - hd.w * 16;
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
-          if (!GRAD) add_cell(t[r], t1[r]);
+          if (!GRAD || ZM2_GCHAINS == 2) add_cell(t[r], t1[r]);
+          if (GRAD && ZM2_GCHAINS == 2) add_cell(td[r], td1[r]);
           if ((unsigned)(i0 + r) < (unsigned)C) { p[16 * r] = t[r]; if (GRAD) p[C * 16 + 16 * r] = td[r]; }
         }
         hd = hn; row = row1;

@@ -1,4 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 200 gpurun_out/bench_n1.json
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 200 gpurun_out/bench_n2.json
+tools/variant_bench.sh kbfast=pnfft_b200/lib/libpnfft_b200.so rpt2=pnfft_b200/lib/variants/rpt2.so
+(time timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -8) > gpurun_out/pytest_gpu.log 2>&1
+cat gpurun_out/pytest_gpu.log
