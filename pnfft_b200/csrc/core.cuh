@@ -308,6 +308,8 @@ template <class R> struct Core {
       }
     PNB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; i++) PNB_CUDA(cudaEventCreate(&p->ev[i]));
+    PNB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) PNB_CUDA(cudaEventCreateWithFlags(&p->ev_copy[i], cudaEventDisableTiming));
     memset(p->timer_trafo, 0, sizeof p->timer_trafo);
     memset(p->timer_adj, 0, sizeof p->timer_adj);
     memset(p->stage_ms, 0, sizeof p->stage_ms);
@@ -366,6 +368,8 @@ template <class R> struct Core {
     for (int t = 0; t < 3; t++) cudaFree(p->d_invphi[t]);
     for (int i = 0; i < 16; i++) cudaEventDestroy(p->ev[i]);
     cudaStreamDestroy(p->stream);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    for (int i = 0; i < 2; i++) if (p->ev_copy[i]) cudaEventDestroy(p->ev_copy[i]);
     MPI_Comm_free(&p->comm);
     delete p;
   }
@@ -830,6 +834,16 @@ template <class R> struct Core {
     const size_t M = (size_t)nd->local_M;
     const R *dx;
     if (nd->binned && nd->d_x_bound) dx = nd->d_x_bound;
+    else if (p->x_via_copy_stream && nd->x && !is_device_ptr(nd->x) && M) {
+      // host-resident coordinates travel on the copy stream, right behind f_hat on the bus, while D and F run on the
+      // plan's stream (trafo recorded ev_copy[0] after the f_hat upload)
+      ensure(&nd->d_x, &nd->cap_x, 3 * M);
+      PNB_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_copy[0], 0));
+      PNB_CUDA(cudaMemcpyAsync(nd->d_x, nd->x, sizeof(R) * 3 * M, cudaMemcpyHostToDevice, p->copy_stream));
+      PNB_CUDA(cudaEventRecord(p->ev_copy[1], p->copy_stream));
+      PNB_CUDA(cudaStreamWaitEvent(p->stream, p->ev_copy[1], 0));
+      dx = nd->d_x;
+    }
     else dx = dev_in(p, nd->x, &nd->d_x, &nd->cap_x, 3 * M, true);
     if (ev_after_copy >= 0) PNB_CUDA(cudaEventRecord(p->ev[ev_after_copy], p->stream));
     if (!nd->binned) bin_nodes(p, nd, dx);
@@ -911,11 +925,15 @@ template <class R> struct Core {
       else { PNB_CUDA(cudaMemcpyAsync(p->d_f_hat, p->f_hat, sizeof(C) * nloc, cudaMemcpyHostToDevice, st)); fh = p->d_f_hat; }
     }
     rec(p, 1);
+    // the x upload of this call may overtake D and F (prepare_nodes); PNFFT_B200_NO_PREFETCH=1 keeps the single queue
+    const size_t M = nd ? (size_t)nd->local_M : 0;
+    static const bool no_prefetch = getenv("PNFFT_B200_NO_PREFETCH") && atoi(getenv("PNFFT_B200_NO_PREFETCH")) != 0;
+    PNB_CUDA(cudaEventRecord(p->ev_copy[0], st));
+    p->x_via_copy_stream = !no_prefetch;
     if (fh) run_deconv(p, fh, nullptr, false);
     rec(p, 2);
 
     // node-side preparation is shared by all B passes of this call
-    const size_t M = nd ? (size_t)nd->local_M : 0;
     R *df = nullptr, *dg = nullptr;
     const R *dx = nullptr;
     const bool conv = !(cf & C_OMIT_CONV);
@@ -972,6 +990,7 @@ template <class R> struct Core {
       if (dg && !is_device_ptr(nd->grad_f)) PNB_CUDA(cudaMemcpyAsync(nd->grad_f, dg, sizeof(R) * 3 * NC * M, cudaMemcpyDeviceToHost, st));
     }
     rec(p, 8);
+    p->x_via_copy_stream = false;
     PNB_CUDA(cudaStreamSynchronize(st));
     finish_timers(p, false, ik);
   }

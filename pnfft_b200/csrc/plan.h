@@ -148,6 +148,9 @@ template <class R> struct Plan {
 
   // device state
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // second H2D queue: node coordinates travel while D and F run (Core::trafo)
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  bool x_via_copy_stream = false;       // set by trafo around prepare_nodes: ev_copy[0] marks where the x upload may start
   C *d_f_hat = nullptr;          // staging copy when the user's f_hat is a host pointer
   R *d_invphi[3] = {nullptr, nullptr, nullptr};  // 1/phi_hat tables incl. the (-1)^k fft-shift sign, [local_N[t]]
   R *d_invphi_plain[3] = {nullptr, nullptr, nullptr};  // without the sign (for OMIT_FFT paths)

@@ -1,5 +1,13 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-tools/variant_bench.sh kbfast=pnfft_b200/lib/libpnfft_b200.so rpt2=pnfft_b200/lib/variants/rpt2.so
-(time timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -8) > gpurun_out/pytest_gpu.log 2>&1
+(timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -4) > gpurun_out/pytest_gpu.log 2>&1
 cat gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 300 gpurun_out/bench_n1.err
+PNFFT_B200_NO_PREFETCH=1 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_noprefetch.json 2> gpurun_out/bench_n1_noprefetch.err
+python - <<'PY'
+import json
+for f in ("bench_n1","bench_n1_noprefetch"):
+    d=json.loads(open("gpurun_out/%s.json"%f).read().strip().splitlines()[-1])
+    print(f, "value %.4g ms %.2f e2e %.4g e2e_ms %.2f"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d["e2e"]["ms_per_step"]), "frac", d["roofline"]["frac"], d["roofline"].get("gridding_frac"))
+    print({k:round(v,2) for k,v in d["stage_ms"]["trafo_e2e"].items()})
+PY
