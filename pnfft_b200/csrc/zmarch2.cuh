@@ -44,7 +44,11 @@ template <int M_> struct Zm2Cfg {
   static constexpr int R1 = 16;                  // footprint rows along y: half a warp
   static constexpr int T1 = R1 - 2 * M_;         // column tile, cells (m=6: 4, m=4: 8)
   static constexpr int RPT = ZM2_RPT;            // x rows per thread (register blocking)
+#ifdef ZM2_T0
+  static constexpr int T0 = ZM2_T0;
+#else
   static constexpr int T0 = RPT == 2 ? 12 : 10;  // R0 = 24 (m=6): 6 consumer warps of 4 x rows / R0 = 22: 11 warps of 2 rows
+#endif
   static constexpr int SUB = 16;                 // x-offset bins per tile in the sort key (>= T0)
   static constexpr int ZS = 4;                   // z sub-chunk == window advance
   static constexpr int ZB = 4;                   // z extent of one TMA box
@@ -368,6 +372,25 @@ template <> struct ZQuad<double> { typedef double2 type; static constexpr int PE
 template <> struct ZQuad<float> { typedef float4 type; static constexpr int PER = 4; };
 __device__ __forceinline__ double zq_get(const double2 &q, int e) { return e == 0 ? q.x : q.y; }
 __device__ __forceinline__ float zq_get(const float4 &q, int e) { return e == 0 ? q.x : (e == 1 ? q.y : (e == 2 ? q.z : q.w)); }
+// 16-byte shared-memory load the compiler may not move past its neighbours of the same kind (keeps the weight refills
+// where the source puts them: interleaved with the taps, not bunched at the end of the node loop)
+#ifndef ZM2_ASM_LDS
+#define ZM2_ASM_LDS 0
+#endif
+__device__ __forceinline__ double2 lds_pinned(const double2 *p) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ float4 lds_pinned(const float4 *p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+template <class Q> __device__ __forceinline__ Q zm2_ldq(const void *p) {
+  if (ZM2_ASM_LDS) return lds_pinned(reinterpret_cast<const Q *>(p));
+  return *reinterpret_cast<const Q *>(p);
+}
 template <int NQT, bool GRAD> constexpr int zm2_depth() {
   constexpr int dmax = ZM2_DEPTH;   // (two quads in flight measured 2 % slower for the gradient gather, splitting its sums into two chains 3 % slower)
   return (dmax >= 4 && NQT % 4 == 0) ? 4 : ((dmax >= 3 && NQT % 3 == 0) ? 3 : ((NQT % 2 == 0) ? 2 : 1));
@@ -849,8 +872,8 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
             if (GRAD) dw = DQ[j % D];
             const unsigned char *src = (j + D < NQT) ? row : row1;
             const int jq = (j + D < NQT) ? j + D : j + D - NQT;
-            Q[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oZ + jq * PER) * SZ);
-            if (GRAD) DQ[j % D] = *reinterpret_cast<const Quad *>(src + (Row::oDZ + jq * PER) * SZ);
+            Q[j % D] = zm2_ldq<Quad>(src + (Row::oZ + jq * PER) * SZ);
+            if (GRAD) DQ[j % D] = zm2_ldq<Quad>(src + (Row::oDZ + jq * PER) * SZ);
 #pragma unroll
             for (int e = 0; e < PER; e++) {
               const int k = j * PER + e;

@@ -1,13 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-(timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -4) > gpurun_out/pytest_gpu.log 2>&1
-cat gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 300 gpurun_out/bench_n1.err
-PNFFT_B200_NO_PREFETCH=1 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_noprefetch.json 2> gpurun_out/bench_n1_noprefetch.err
-python - <<'PY'
-import json
-for f in ("bench_n1","bench_n1_noprefetch"):
-    d=json.loads(open("gpurun_out/%s.json"%f).read().strip().splitlines()[-1])
-    print(f, "value %.4g ms %.2f e2e %.4g e2e_ms %.2f"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d["e2e"]["ms_per_step"]), "frac", d["roofline"]["frac"], d["roofline"].get("gridding_frac"))
-    print({k:round(v,2) for k,v in d["stage_ms"]["trafo_e2e"].items()})
-PY
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_(scatter|gather)_zm2|k_node_table2' -s 12 -c 4 -f -o gpurun_out/prof_r1b_step python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_step.log 2>&1
+ls -la gpurun_out/*.ncu-rep | tail -2
+tail -3 gpurun_out/ncu_step.log
