@@ -1,6 +1,9 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_(scatter|gather)_zm2|k_node_table2' -s 12 -c 4 -f -o gpurun_out/prof_r1b_step python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_step.log 2>&1
-ls -la gpurun_out/*.ncu-rep | tail -2
-tail -3 gpurun_out/ncu_step.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tools/mgpu_parity.py > gpurun_out/mgpu2.log 2>&1; tail -2 gpurun_out/mgpu2.log | cut -c1-600
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 400 gpurun_out/bench_n2.json | cut -c1-400
+python -c "
+import json
+d=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1])
+print('N=2 value %.4g ms %.2f e2e %.4g'%(d['value'],d['ms_per_step'],d['e2e']['value']))
+"
