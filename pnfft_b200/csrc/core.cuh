@@ -333,7 +333,7 @@ template <class R> struct Core {
       const size_t h1 = (size_t)(L.gcb[1] + L.gca[1]) * L.ngc[0] * L.pitch2 * cell_bytes(p) * 2;
       p->work_bytes = std::max(p->work_bytes, std::max(h0, h1));
     }
-    for (int i = 0; i < 2; i++) PNB_CUDA(cudaMalloc(&p->d_work[i], p->work_bytes));
+    for (int i = 0; i < 3; i++) PNB_CUDA(cudaMalloc(&p->d_work[i], p->work_bytes));
     upload_window_tables(p);
     make_fft_plans(p);
     PNB_CUDA(cudaStreamSynchronize(p->stream));
@@ -364,7 +364,7 @@ template <class R> struct Core {
     if (p->fft_z_bwd && p->fft_z_bwd != p->fft_z_fwd) cufftDestroy(p->fft_z_bwd);
     if (p->owns_f_hat && (flags & F_MALLOC_F_HAT) && p->f_hat) cudaFreeHost(p->f_hat);
     cudaFree(p->d_f_hat); cudaFree(p->d_g1); cudaFree(p->d_g1_buffer); cudaFree(p->d_grid);
-    cudaFree(p->d_work[0]); cudaFree(p->d_work[1]); cudaFree(p->d_exp_const); cudaFree(p->d_sort_tmp); cudaFree(p->d_poly);
+    cudaFree(p->d_work[0]); cudaFree(p->d_work[1]); cudaFree(p->d_work[2]); cudaFree(p->d_exp_const); cudaFree(p->d_sort_tmp); cudaFree(p->d_poly);
     for (int t = 0; t < 3; t++) cudaFree(p->d_invphi[t]);
     for (int i = 0; i < 16; i++) cudaEventDestroy(p->ev[i]);
     cudaStreamDestroy(p->stream);
@@ -381,12 +381,12 @@ template <class R> struct Core {
     const Layout &L = p->L;
     const PipeGeom &G = p->pipe;
     cudaStream_t st = p->stream;
-    C *W0 = (C *)p->d_work[0], *W1 = (C *)p->d_work[1];
-    run_stage_forward<C>(G.st[0], p->mesh, p->d_g1, W0, W1, st, &p->launches);       // L1 in W1
+    C *W0 = (C *)p->d_work[0], *W1 = (C *)p->d_work[1], *PK = (C *)p->d_work[2];
+    run_stage_forward<C>(G.st[0], p->mesh, p->d_g1, W0, W1, PK, st, &p->launches);       // L1 in W1
     if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_FORWARD); p->lib_launches++; }
-    run_stage_forward<C>(G.st[1], p->mesh, W1, W1, W0, st, &p->launches);            // L3 in W0
+    run_stage_forward<C>(G.st[1], p->mesh, W1, W1, W0, PK, st, &p->launches);            // L3 in W0
     if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_FORWARD); p->lib_launches++; }
-    run_stage_forward<C>(G.st[2], p->mesh, W0, W0, W1, st, &p->launches);            // L4 in W1
+    run_stage_forward<C>(G.st[2], p->mesh, W0, W0, W1, PK, st, &p->launches);            // L4 in W1
     const long long lno0 = L.local_no[0], lno1 = L.local_no[1];
     if (!L.c2r) {
       if (p->fft_z_fwd) { FftType<R>::exec_c2c(p->fft_z_fwd, W1, CUFFT_FORWARD); p->lib_launches++; }
@@ -406,7 +406,7 @@ template <class R> struct Core {
     const Layout &L = p->L;
     const PipeGeom &G = p->pipe;
     cudaStream_t st = p->stream;
-    C *W0 = (C *)p->d_work[0], *W1 = (C *)p->d_work[1];
+    C *W0 = (C *)p->d_work[0], *W1 = (C *)p->d_work[1], *PK = (C *)p->d_work[2];
     const long long lno0 = L.local_no[0], lno1 = L.local_no[1];
     const bool pruned2 = L.no[2] < L.n[2];
     if (!L.c2r) {
@@ -424,14 +424,14 @@ template <class R> struct Core {
     }
     // L4 in W1 -> L3 in W0
     if (L.no[1] < L.n[1]) stage_backward_zero(p, G.st[2], W1, W0, W0, G.L3_elems);
-    else run_stage_backward<C>(G.st[2], p->mesh, W1, W0, W0, st, &p->launches);
+    else run_stage_backward<C>(G.st[2], p->mesh, W1, W0, W0, PK, st, &p->launches);
     if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_INVERSE); p->lib_launches++; }
     // L3 in W0 -> L1 in W1
     if (L.no[0] < L.n[0]) stage_backward_zero(p, G.st[1], W0, W1, W1, G.L1_elems);
-    else run_stage_backward<C>(G.st[1], p->mesh, W0, W1, W1, st, &p->launches);
+    else run_stage_backward<C>(G.st[1], p->mesh, W0, W1, W1, PK, st, &p->launches);
     if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_INVERSE); p->lib_launches++; }
     // L1 in W1 -> g1
-    run_stage_backward<C>(G.st[0], p->mesh, W1, W0, p->d_g1, st, &p->launches);
+    run_stage_backward<C>(G.st[0], p->mesh, W1, W0, p->d_g1, PK, st, &p->launches);
   }
 
   // backward stage whose source-side array has rows outside the pruned output range: they must be zero

@@ -220,14 +220,14 @@ inline PipeGeom build_pipe(const Layout &L, const Mesh &M) {
 // exchange of the chunk buffers
 // -----------------------------------------------------------------------------------------------
 template <class C>
-inline void exchange_chunks(const Stage &S, const Mesh &M, C *from, C *to, bool forward, cudaStream_t st) {
+inline void exchange_chunks(const Stage &S, const Mesh &M, C *from, C *to, bool forward, cudaStream_t st, bool copy_self = true) {
   const bool multi = M.size > 1;
   if (multi) PNB_NCCL(nccl_api().GroupStart());
   for (const auto &T : S.tr) {
     const long long ns = forward ? T.send_elems : T.recv_elems, nr = forward ? T.recv_elems : T.send_elems;
     const long long os = forward ? T.send_off : T.recv_off, orr = forward ? T.recv_off : T.send_off;
     if (T.peer == M.rank) {
-      if (ns > 0) PNB_CUDA(cudaMemcpyAsync(to + orr, from + os, sizeof(C) * (size_t)ns, cudaMemcpyDeviceToDevice, st));
+      if (copy_self && ns > 0) PNB_CUDA(cudaMemcpyAsync(to + orr, from + os, sizeof(C) * (size_t)ns, cudaMemcpyDeviceToDevice, st));
     } else {
       if (ns > 0) PNB_NCCL(nccl_api().Send(from + os, (size_t)ns * sizeof(C), ncclChar, T.peer, world_nccl(), st));
       if (nr > 0) PNB_NCCL(nccl_api().Recv(to + orr, (size_t)nr * sizeof(C), ncclChar, T.peer, world_nccl(), st));
@@ -236,42 +236,46 @@ inline void exchange_chunks(const Stage &S, const Mesh &M, C *from, C *to, bool 
   if (multi) PNB_NCCL(nccl_api().GroupEnd());
 }
 
-// forward: src array A -> (pack) bufB -> (exchange) bufA' -> (unpack) dst array.  Caller provides
-// src (may be bufX or g1), two scratch buffers; returns the destination array pointer (= w1).
+// forward: src array -> (pack) pk -> (exchange) w0 -> (unpack) w1 = the destination array.  src may alias w0 (it is dead
+// after the pack).  The chunk a rank sends to itself never moves: it is unpacked straight from the pack buffer (with one
+// rank the whole re-distribution is pack + unpack, no device copy in between).
 template <class C>
-inline void run_stage_forward(const Stage &S, const Mesh &M, C *src, C *w0, C *w1, cudaStream_t st, long long *launches) {
-  // pack src -> w1 ; exchange w1 -> w0 ; zero w1 ; unpack w0 -> w1  (src may alias w0: it is dead after the pack)
+inline void run_stage_forward(const Stage &S, const Mesh &M, C *src, C *w0, C *w1, C *pk, cudaStream_t st, long long *launches) {
   for (const auto &T : S.tr)
     for (const auto &bm0 : T.send_maps) {
       BoxMap bm = bm0; bm.c_off += T.send_off;
-      box_copy<C>(st, src, w1, bm, BOX_A2C, T.send_sign, launches);
+      box_copy<C>(st, src, pk, bm, BOX_A2C, T.send_sign, launches);
     }
-  exchange_chunks<C>(S, M, w1, w0, true, st);
+  exchange_chunks<C>(S, M, pk, w0, true, st, false);
   if (S.zero_all) PNB_CUDA(cudaMemsetAsync(w1, 0, sizeof(C) * (size_t)S.dst_elems, st));
   else if (S.zero_len > 0) PNB_CUDA(cudaMemsetAsync(w1 + S.zero_off, 0, sizeof(C) * (size_t)S.zero_len, st));
-  for (const auto &T : S.tr)
+  for (const auto &T : S.tr) {
+    const bool self = T.peer == M.rank;
     for (const auto &bm0 : T.recv_maps) {
-      BoxMap bm = bm0; bm.c_off += T.recv_off;
-      box_copy<C>(st, w1, w0, bm, BOX_C2A, false, launches);
+      BoxMap bm = bm0; bm.c_off += self ? T.send_off : T.recv_off;
+      box_copy<C>(st, w1, self ? pk : w0, bm, BOX_C2A, false, launches);
     }
+  }
 }
 
-// backward: dst-side array (in `arr`) -> chunks in `w` -> exchange -> chunks in `arr`'s buffer -> src-side array `out`
-// arr and w are the two work buffers; out may alias w (it is written after w's chunks were sent... no: see below)
+// backward: dst-side array `arr` -> (pack, recv-side chunks) pk -> (exchange) arr's buffer (arr is dead after the pack)
+// -> (unpack) src-side array `out` (any buffer but pk and arr; w is kept in the signature for the callers' ping-pong)
 template <class C>
-inline void run_stage_backward(const Stage &S, const Mesh &M, C *arr, C *w, C *out, cudaStream_t st, long long *launches) {
-  // pack arr -> w (recv-side chunks); exchange w -> arr (arr is dead after the pack); unpack arr -> out (out == w allowed)
+inline void run_stage_backward(const Stage &S, const Mesh &M, C *arr, C *w, C *out, C *pk, cudaStream_t st, long long *launches) {
+  (void)w;
   for (const auto &T : S.tr)
     for (const auto &bm0 : T.recv_maps) {
       BoxMap bm = bm0; bm.c_off += T.recv_off;
-      box_copy<C>(st, arr, w, bm, BOX_A2C, false, launches);
+      box_copy<C>(st, arr, pk, bm, BOX_A2C, false, launches);
     }
-  exchange_chunks<C>(S, M, w, arr, false, st);
-  for (const auto &T : S.tr)
+  exchange_chunks<C>(S, M, pk, arr, false, st, false);
+  for (const auto &T : S.tr) {
+    const bool self = T.peer == M.rank;
     for (const auto &bm0 : T.send_maps) {
-      BoxMap bm = bm0; bm.c_off += T.send_off;
-      box_copy<C>(st, out, arr, bm, BOX_C2A, T.send_sign, launches);
+      BoxMap bm = bm0; bm.c_off += self ? T.recv_off : T.send_off;
+      box_copy<C>(st, out, self ? pk : arr, bm, BOX_C2A, T.send_sign, launches);
     }
+  }
 }
 
 // -----------------------------------------------------------------------------------------------

@@ -159,7 +159,7 @@ template <class R> struct Plan {
   int poly_deg = -1, poly_deg_psi = -1;
   int use_poly = 1;
   void *d_grid = nullptr;        // padded grid [ngc0][ngc1][pitch2] of C (c2c) or R (c2r)
-  void *d_work[2] = {nullptr, nullptr};  // ping-pong FFT stage buffers
+  void *d_work[3] = {nullptr, nullptr, nullptr};  // ping-pong FFT stage buffers + the pack buffer of the re-distributions
   size_t work_bytes = 0, grid_bytes = 0;
   C *d_g1 = nullptr;             // compact FFT-input-side array (local_N block) used with OMIT_* flags / ik
   C *d_g1_buffer = nullptr;      // ik differentiation buffer

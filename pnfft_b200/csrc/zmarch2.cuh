@@ -94,7 +94,10 @@ template <class R, int M_, bool GRAD, bool VALS, bool CPLX> struct Zm2Row {
 };
 
 constexpr int kZm2HdrBytes = 128;    // chunk header: {tz, count, first sorted index, 0, start[0..T0]}
-constexpr int kZm2TabNodes = 64;     // nodes per block of the table kernel
+#ifndef ZM2_TABNODES
+#define ZM2_TABNODES 64
+#endif
+constexpr int kZm2TabNodes = ZM2_TABNODES;     // nodes per block of the table kernel
 
 // ------------------------------------------------------------------------------------------------
 // node table: one thread per (node, axis); rows assembled in shared memory, written out coalesced
