@@ -67,6 +67,37 @@ template <class F> inline void wrap_segments(INT k_start, INT len, INT n, F f) {
   if (len - neg > 0) f(neg, len - neg, k_start + neg);
 }
 
+// A rank's own chunk needs no chunk: compose "source array <-> dense send chunk" with "destination array <-> sub-box of
+// that chunk" into one map destination array (a side) <-> source array (c side).  False if the sub-box does not follow
+// the dense chunk's axes (the caller then keeps pack + unpack).
+inline bool compose_self_map(const BoxMap &sm, const BoxMap &rm, BoxMap *out) {
+  if (sm.c_str[2] != 1 || sm.c_str[1] != sm.dims[2] || sm.c_str[0] != sm.dims[1] * sm.dims[2]) return false;
+  long long rel = rm.c_off - sm.c_off;
+  if (rel < 0) return false;
+  long long o[3];
+  o[0] = sm.c_str[0] > 0 ? rel / sm.c_str[0] : 0; rel -= o[0] * sm.c_str[0];
+  o[1] = sm.c_str[1] > 0 ? rel / sm.c_str[1] : 0; rel -= o[1] * sm.c_str[1];
+  o[2] = rel;
+  *out = rm;
+  bool used[3] = {false, false, false};
+  for (int k = 0; k < 3; k++) {
+    int pick = -1;
+    for (int d = 0; d < 3 && pick < 0; d++)
+      if (!used[d] && sm.c_str[d] == rm.c_str[k] && o[d] + rm.dims[k] <= sm.dims[d]) pick = d;
+    if (pick < 0) {
+      if (rm.dims[k] != 1) return false;
+      out->c_str[k] = 0;
+      continue;
+    }
+    used[pick] = true;
+    out->c_str[k] = sm.a_str[pick];
+  }
+  for (int d = 0; d < 3; d++) if (o[d] >= sm.dims[d]) return false;
+  out->c_off = sm.a_off + o[0] * sm.a_str[0] + o[1] * sm.a_str[1] + o[2] * sm.a_str[2];
+  out->parity = (int)((sm.parity + o[0] + o[1] + o[2]) & 1);
+  return true;
+}
+
 inline PipeGeom build_pipe(const Layout &L, const Mesh &M) {
   PipeGeom G;
   const int p0 = M.np[0], p1 = M.np[1], a = M.co[0], b = M.co[1];
@@ -204,8 +235,20 @@ inline PipeGeom build_pipe(const Layout &L, const Mesh &M) {
     }
   }
   long long need = std::max(std::max(G.L1_elems, G.L3_elems), G.L4_elems);
+  static const bool no_self = getenv("PNFFT_B200_NO_SELF_MAPS") && atoi(getenv("PNFFT_B200_NO_SELF_MAPS")) != 0;
   for (int s = 0; s < 3; s++) {
     Stage &S = G.st[s];
+    for (auto &T : S.tr) {
+      if (no_self || T.peer != M.rank || T.send_maps.size() != 1 || T.recv_maps.empty() || T.send_elems != T.recv_elems) continue;
+      std::vector<BoxMap> sm;
+      bool ok = true;
+      for (const auto &rm : T.recv_maps) {
+        BoxMap c;
+        ok = ok && compose_self_map(T.send_maps[0], rm, &c);
+        if (ok) sm.push_back(c);
+      }
+      if (ok) T.self_maps = sm;
+    }
     long long so = 0, ro = 0;
     for (auto &T : S.tr) { T.send_off = so; T.recv_off = ro; so += T.send_elems; ro += T.recv_elems; }
     S.send_total = so; S.recv_total = ro;
@@ -237,19 +280,25 @@ inline void exchange_chunks(const Stage &S, const Mesh &M, C *from, C *to, bool 
 }
 
 // forward: src array -> (pack) pk -> (exchange) w0 -> (unpack) w1 = the destination array.  src may alias w0 (it is dead
-// after the pack).  The chunk a rank sends to itself never moves: it is unpacked straight from the pack buffer (with one
-// rank the whole re-distribution is pack + unpack, no device copy in between).
+// once the exchange starts).  The chunk a rank sends to itself is one strided copy src -> w1 (Transfer::self_maps), or,
+// where the maps do not compose, is unpacked straight from the pack buffer: with one rank a re-distribution is a single
+// pass over the data.
 template <class C>
 inline void run_stage_forward(const Stage &S, const Mesh &M, C *src, C *w0, C *w1, C *pk, cudaStream_t st, long long *launches) {
-  for (const auto &T : S.tr)
+  for (const auto &T : S.tr) {
+    if (!T.self_maps.empty()) continue;
     for (const auto &bm0 : T.send_maps) {
       BoxMap bm = bm0; bm.c_off += T.send_off;
       box_copy<C>(st, src, pk, bm, BOX_A2C, T.send_sign, launches);
     }
-  exchange_chunks<C>(S, M, pk, w0, true, st, false);
+  }
   if (S.zero_all) PNB_CUDA(cudaMemsetAsync(w1, 0, sizeof(C) * (size_t)S.dst_elems, st));
   else if (S.zero_len > 0) PNB_CUDA(cudaMemsetAsync(w1 + S.zero_off, 0, sizeof(C) * (size_t)S.zero_len, st));
+  for (const auto &T : S.tr)
+    for (const auto &bm : T.self_maps) box_copy<C>(st, w1, src, bm, BOX_C2A, T.send_sign, launches);
+  exchange_chunks<C>(S, M, pk, w0, true, st, false);
   for (const auto &T : S.tr) {
+    if (!T.self_maps.empty()) continue;
     const bool self = T.peer == M.rank;
     for (const auto &bm0 : T.recv_maps) {
       BoxMap bm = bm0; bm.c_off += self ? T.send_off : T.recv_off;
@@ -258,18 +307,25 @@ inline void run_stage_forward(const Stage &S, const Mesh &M, C *src, C *w0, C *w
   }
 }
 
-// backward: dst-side array `arr` -> (pack, recv-side chunks) pk -> (exchange) arr's buffer (arr is dead after the pack)
-// -> (unpack) src-side array `out` (any buffer but pk and arr; w is kept in the signature for the callers' ping-pong)
+// backward: dst-side array `arr` -> (pack, recv-side chunks) pk -> (exchange) arr's buffer (arr is dead once the exchange
+// starts) -> (unpack) src-side array `out` (any buffer but pk and arr; w is kept in the signature for the callers'
+// ping-pong).  The rank's own chunk goes arr -> out in one strided copy before the exchange overwrites arr.
 template <class C>
 inline void run_stage_backward(const Stage &S, const Mesh &M, C *arr, C *w, C *out, C *pk, cudaStream_t st, long long *launches) {
   (void)w;
-  for (const auto &T : S.tr)
+  for (const auto &T : S.tr) {
+    if (!T.self_maps.empty()) {
+      for (const auto &bm : T.self_maps) box_copy<C>(st, arr, out, bm, BOX_A2C, T.send_sign, launches);
+      continue;
+    }
     for (const auto &bm0 : T.recv_maps) {
       BoxMap bm = bm0; bm.c_off += T.recv_off;
       box_copy<C>(st, arr, pk, bm, BOX_A2C, false, launches);
     }
+  }
   exchange_chunks<C>(S, M, pk, arr, false, st, false);
   for (const auto &T : S.tr) {
+    if (!T.self_maps.empty()) continue;
     const bool self = T.peer == M.rank;
     for (const auto &bm0 : T.send_maps) {
       BoxMap bm = bm0; bm.c_off += self ? T.recv_off : T.send_off;

@@ -112,6 +112,7 @@ struct Transfer {
   long long send_elems = 0, recv_elems = 0;  // complex elements
   long long send_off = 0, recv_off = 0;      // offsets inside the chunk buffers
   std::vector<BoxMap> send_maps, recv_maps;  // source array <-> send chunk ; destination array <-> recv chunk
+  std::vector<BoxMap> self_maps;             // peer == me: destination array (a side) <-> source array (c side), no chunk
   bool send_sign = false;
 };
 
