@@ -9,3 +9,4 @@ d=json.loads(open("gpurun_out/bench_n1.json").read().strip().splitlines()[-1])
 print("value %.4g ms %.2f e2e %.4g e2e_ms %.2f"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d["e2e"]["ms_per_step"]), "frac", d["roofline"]["frac"], d["roofline"].get("gridding_frac"))
 print({k:round(v,2) for k,v in d["stage_ms"]["trafo"].items()}); print({k:round(v,2) for k,v in d["stage_ms"]["adj"].items()})
 PY
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
