@@ -186,6 +186,9 @@ typedef float pnfftf_complex[2];
   /* kernels of this library launched so far / cuFFT, CUB and NCCL calls issued so far */        \
   long long PNX(b200_kernel_launches)(PNX(plan) ths);                                               \
   long long PNX(b200_library_calls)(PNX(plan) ths);                                                 \
+  /* host-only self check of the pencil FFT's composed "own chunk" maps for rank (c0, c1) of a p0 x p1 \
+   * mesh: self transfers checked, -1 on a mismatch, -2 if one did not compose (no GPU needed) */       \
+  int PNX(b200_check_self_maps)(const ptrdiff_t *N, const ptrdiff_t *n, int m, int p0, int p1, int c0, int c1, int c2r); \
   /* the plan's cudaStream_t (all work of trafo/adj is issued on it; calls synchronise it on return) */ \
   void *PNX(b200_get_stream)(PNX(plan) ths);
 

@@ -464,6 +464,55 @@ void PNX(b200_gather_timing)(long long *out96, int reset) {
   if (reset) { cudaMemset(d, 0, 96 * 8); cudaMemset(d + 96, 0x3f, 16 * 8); }
 }
 #endif
+// Host-only check of the pencil FFT's composed self maps (fftpipe.cuh: compose_self_map) for one rank of a p0 x p1 mesh:
+// every re-distribution stage is emulated on index arrays, once through pack -> chunk -> unpack and once through the
+// composed map, forward and backward.  Returns the number of self transfers checked, -1 on a mismatch, -2 if a self
+// transfer did not compose.  Needs no GPU (tests/test_abi.py).
+int PNX(b200_check_self_maps)(const INT *N, const INT *n, int m, int p0, int p1, int c0, int c1, int c2r) {
+  pnb::Mesh M;
+  M.np[0] = p0; M.np[1] = p1; M.co[0] = c0; M.co[1] = c1; M.size = p0 * p1; M.rank = M.rank_of(c0, c1);
+  pnb::Layout L;
+  const RT xm[3] = {(RT)0.5, (RT)0.5, (RT)0.5};
+  pnb::compute_layout<RT>(L, M, N, n, xm, m, c2r != 0, 0u);
+  const pnb::PipeGeom G = pnb::build_pipe(L, M);
+  auto apply = [](std::vector<long long> &A, std::vector<long long> &Cb, const pnb::BoxMap &bm, bool a2c, bool sign) {
+    for (long long i0 = 0; i0 < bm.dims[0]; i0++)
+      for (long long i1 = 0; i1 < bm.dims[1]; i1++)
+        for (long long i2 = 0; i2 < bm.dims[2]; i2++) {
+          const long long ia = bm.a_off + i0 * bm.a_str[0] + i1 * bm.a_str[1] + i2 * bm.a_str[2];
+          const long long ic = bm.c_off + i0 * bm.c_str[0] + i1 * bm.c_str[1] + i2 * bm.c_str[2];
+          const bool neg = sign && ((i0 + i1 + i2 + bm.parity) & 1);
+          if (a2c) Cb.at((size_t)ic) = neg ? -A.at((size_t)ia) : A.at((size_t)ia);
+          else A.at((size_t)ia) = neg ? -Cb.at((size_t)ic) : Cb.at((size_t)ic);
+        }
+  };
+  int checked = 0;
+  for (int s = 0; s < 3; s++) {
+    const pnb::Stage &S = G.st[s];
+    for (const auto &T : S.tr) {
+      if (T.peer != M.rank || T.send_elems == 0) continue;
+      if (T.self_maps.empty()) return -2;
+      const size_t ns = (size_t)std::max(S.src_elems, G.buf_elems), nd = (size_t)std::max(S.dst_elems, G.buf_elems);
+      // forward: src -> chunk -> dst  against  src -> dst
+      std::vector<long long> src(ns), chunk((size_t)T.send_elems, 0), d1(nd, 0), d2(nd, 0);
+      for (size_t i = 0; i < ns; i++) src[i] = (long long)i + 1;
+      for (const auto &bm : T.send_maps) apply(src, chunk, bm, true, T.send_sign);
+      for (const auto &bm : T.recv_maps) apply(d1, chunk, bm, false, false);
+      for (const auto &bm : T.self_maps) apply(d2, src, bm, false, T.send_sign);
+      if (d1 != d2) return -1;
+      // backward: dst-side array -> chunk -> src-side array  against  the composed copy
+      std::vector<long long> arr(nd), o1(ns, 0), o2(ns, 0);
+      for (size_t i = 0; i < nd; i++) arr[i] = (long long)i + 1;
+      std::fill(chunk.begin(), chunk.end(), 0);
+      for (const auto &bm : T.recv_maps) apply(arr, chunk, bm, true, false);
+      for (const auto &bm : T.send_maps) apply(o1, chunk, bm, false, T.send_sign);
+      for (const auto &bm : T.self_maps) apply(arr, o2, bm, true, T.send_sign);
+      if (o1 != o2) return -1;
+      checked++;
+    }
+  }
+  return checked;
+}
 void PNX(b200_get_stage_ms)(PNX(plan) ths, int adjoint, double *ms8) { for (int i = 0; i < 8; i++) ms8[i] = AS_PLAN(ths)->stage_ms[adjoint ? 1 : 0][i]; }
 long long PNX(b200_kernel_launches)(PNX(plan) ths) { return AS_PLAN(ths)->launches; }
 long long PNX(b200_library_calls)(PNX(plan) ths) { return AS_PLAN(ths)->lib_launches; }

@@ -75,3 +75,23 @@ def test_missing_gpu_fails_loudly():
     comm = A.create_procmesh_2d(1, 1)
     with pytest.raises(RuntimeError):
         A.Plan.init_guru((16, 16, 16), (32, 32, 32), (0.5,) * 3, 6, 0, comm)   # NULL + message, never a CPU fallback
+
+
+@pytest.mark.parametrize("c2r", [0, 1])
+@pytest.mark.parametrize("mesh", [(1, 1), (1, 2), (2, 2), (2, 4), (3, 2)])
+@pytest.mark.parametrize("N,n,m", [((16, 16, 16), (32, 32, 32), 6), ((12, 20, 16), (24, 40, 32), 4), ((10, 14, 18), (32, 32, 40), 4)])
+def test_fft_self_maps_equal_pack_unpack(N, n, m, mesh, c2r):
+    """The chunk a rank sends to itself in a pencil re-distribution moves in ONE composed strided copy (csrc/fftpipe.cuh,
+    compose_self_map); on index arrays it must land exactly where pack -> chunk -> unpack puts it, forward and backward,
+    for every rank of even and ragged meshes (host-only entry point, no GPU)."""
+    fn = A.lib().pnfft_b200_check_self_maps
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(C.c_ssize_t), C.POINTER(C.c_ssize_t)] + [C.c_int] * 6
+    Nv, nv = (C.c_ssize_t * 3)(*N), (C.c_ssize_t * 3)(*n)
+    total = 0
+    for c0 in range(mesh[0]):
+        for c1 in range(mesh[1]):
+            r = fn(Nv, nv, m, mesh[0], mesh[1], c0, c1, c2r)
+            assert r >= 0, "rank (%d,%d): %s" % (c0, c1, "mismatch" if r == -1 else "self transfer did not compose")
+            total += r
+    assert total > 0
