@@ -237,8 +237,14 @@ template <class R, bool CPLX, int M_, bool GRAD> struct Zm2Smem {
   static constexpr int s_off_bar = s_off_ring + SS * s_stage;
   static constexpr int scatter = s_off_bar + 2 * SS * 8;
   // gather: one staging buffer per warp, ring, P stages of per-row partial sums
-  static constexpr int GS = 4, GP = 3;
-  static constexpr int GGB = GRAD ? 8 : 16;
+#ifndef ZM2_GP
+#define ZM2_GP 3
+#endif
+#ifndef ZM2_GGB
+#define ZM2_GGB 8
+#endif
+  static constexpr int GS = 4, GP = ZM2_GP;
+  static constexpr int GGB = GRAD ? ZM2_GGB : 2 * ZM2_GGB;
   static constexpr int PN = Cfg::C * 16 * (GRAD ? 2 : 1);                 // partial cells per node
   static constexpr int g_stage = kZm2HdrBytes + GGB * RowG::ROWBYTES;
   static constexpr int g_off_ring = Cfg::NCW * WARP_BOX;
