@@ -309,6 +309,7 @@ template <class R> struct Core {
     PNB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; i++) PNB_CUDA(cudaEventCreate(&p->ev[i]));
     PNB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    PNB_CUDA(cudaStreamCreateWithFlags(&p->node_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) PNB_CUDA(cudaEventCreateWithFlags(&p->ev_copy[i], cudaEventDisableTiming));
     memset(p->timer_trafo, 0, sizeof p->timer_trafo);
     memset(p->timer_adj, 0, sizeof p->timer_adj);
@@ -369,6 +370,7 @@ template <class R> struct Core {
     for (int i = 0; i < 16; i++) cudaEventDestroy(p->ev[i]);
     cudaStreamDestroy(p->stream);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    if (p->node_stream) cudaStreamDestroy(p->node_stream);
     for (int i = 0; i < 2; i++) if (p->ev_copy[i]) cudaEventDestroy(p->ev_copy[i]);
     MPI_Comm_free(&p->comm);
     delete p;
@@ -752,16 +754,24 @@ template <class R> struct Core {
       const unsigned ntb = (unsigned)((na.M + kZm2TabNodes - 1) / kZm2TabNodes);
       if (!scatter) {
         typedef typename Sm::RowG Row;
-        ensure(&nd->d_wtab, &nd->cap_wtab, (size_t)na.M * Row::ROWLEN + 64);
-        auto kt = k_node_table2<R, M_, GRAD, false, CPLX>;
-        const size_t tsm = (size_t)kZm2TabNodes * Row::ROWBYTES + psm;
-        PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-        kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, na, nd->d_wtab);
-        GatherOut<R> out;
-        out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
-        auto kern = k_gather_zm2<R, CPLX, M_, GRAD>;
-        PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
-        kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, nd->d_wtab, nd->d_tile_start, out);
+        if (p->b_phase & 1) {
+          ensure(&nd->d_wtab, &nd->cap_wtab, (size_t)na.M * Row::ROWLEN + 64);
+          auto kt = k_node_table2<R, M_, GRAD, false, CPLX>;
+          const size_t tsm = (size_t)kZm2TabNodes * Row::ROWBYTES + psm;
+          PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+          kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, na, nd->d_wtab);
+          p->launches++;
+        }
+        if (p->b_phase & 2) {
+          GatherOut<R> out;
+          out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
+          auto kern = k_gather_zm2<R, CPLX, M_, GRAD>;
+          PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
+          kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, nd->d_wtab, nd->d_tile_start, out);
+          p->launches++;
+        }
+        PNB_CUDA(cudaGetLastError());
+        return;
       } else {
         typedef typename Sm::RowS Row;
         ensure(&nd->d_wtab, &nd->cap_wtab, (size_t)na.M * Row::ROWLEN + 64);
@@ -954,9 +964,40 @@ template <class R> struct Core {
     };
 
     if (!ik) {
+      // z-march v2: the node side of the call (x upload, binning, node table) needs nothing from the grid, so it runs on
+      // its own stream while D, F and the halo exchange run here; the gather waits for both.
+      // On by default for multi-rank plans, where F and the halo exchange are latency bound (measured on 1x2 B200:
+      // step 36.57 -> 36.35 ms); on one GPU the two sides only compete for HBM (65.4 vs 65.5 ms) and the stage timers
+      // stay cleaner without it.  PNFFT_B200_SIDE_STREAM=0 / 1 forces it off / on.
+      static const int side_env = getenv("PNFFT_B200_SIDE_STREAM") ? atoi(getenv("PNFFT_B200_SIDE_STREAM")) : -1;
+      const bool want_side = side_env >= 0 ? side_env != 0 : p->mesh.size > 1;
+      p->side_nodes = want_side && conv && M > 0 && kernel_family(p) == 2 && (cf & (C_F | C_GRAD_F));
+      NodeArgs<R> na_side;
+      if (p->side_nodes) {
+        p->stream = p->node_stream;
+        rec(p, 11);
+        node_setup();                 // records ev[4] (x on the device) and ev[5] (binned) on the node stream
+        rec(p, 9);
+        na_side = base_args();
+        na_side.f = df; na_side.grad = dg;
+        if (na_side.grad && na_side.pre_psi && !na_side.pre_dpsi) na_side.pre_psi = nullptr;
+        p->b_phase = 1;
+        if (df || dg) launch_B_any(p, nd, na_side, false);
+        p->b_phase = 3;
+        rec(p, 10);
+        p->stream = st;
+      }
       if (!(cf & C_OMIT_FFT)) fft_forward(p);
       rec(p, 3);
-      if (conv) {
+      if (p->side_nodes) {
+        halo(p, false);
+        rec(p, 6);
+        PNB_CUDA(cudaStreamWaitEvent(st, p->ev[10], 0));
+        p->b_phase = 2;
+        if (df || dg) launch_B_any(p, nd, na_side, false);
+        p->b_phase = 3;
+        rec(p, 7);
+      } else if (conv) {
         node_setup();
         halo(p, false);
         rec(p, 6);
@@ -967,6 +1008,7 @@ template <class R> struct Core {
         rec(p, 7);
       } else { rec(p, 4); rec(p, 5); rec(p, 6); rec(p, 7); }
     } else {
+      p->side_nodes = false;
       // ik differentiation: 1 (f) + 3 (grad) passes of F and B (reference api-basic.c:100-167)
       if ((cf & C_GRAD_F) && !(cf & C_OMIT_DECONV))
         PNB_CUDA(cudaMemcpyAsync(p->d_g1_buffer, p->d_g1, sizeof(C) * nloc, cudaMemcpyDeviceToDevice, st));
@@ -1081,6 +1123,9 @@ template <class R> struct Core {
     if (!adjoint) {
       s[0] = ms(p, 6, 7); s[1] = ms(p, 4, 5); s[2] = ms(p, 5, 6); s[3] = ms(p, 2, 3); s[4] = ms(p, 1, 2);
       s[5] = ms(p, 0, 1) + ms(p, 3, 4); s[6] = ms(p, 7, 8); s[7] = ms(p, 0, 8);
+      if (p->side_nodes) {   // node side on its own stream: x upload ev[11]->ev[4], binning ev[4]->ev[5], node table ev[9]->ev[10]
+        s[0] = ms(p, 6, 7) + ms(p, 9, 10); s[1] = ms(p, 4, 5); s[2] = ms(p, 3, 6); s[5] = ms(p, 0, 1) + ms(p, 11, 4);
+      }
     } else {
       s[0] = ms(p, 3, 4); s[1] = ms(p, 1, 2); s[2] = ms(p, 2, 3) + ms(p, 4, 5); s[3] = ms(p, 5, 6); s[4] = ms(p, 6, 7);
       s[5] = ms(p, 0, 1); s[6] = ms(p, 7, 8); s[7] = ms(p, 0, 8);

@@ -151,6 +151,9 @@ template <class R> struct Plan {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // second H2D queue: node coordinates travel while D and F run (Core::trafo)
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaStream_t node_stream = nullptr;   // trafo: binning + node table run here while D, F and the halo exchange run on `stream`
+  int b_phase = 3;                      // what launch_B does: bit 0 = node table, bit 1 = gridding kernel (z-march v2 only)
+  bool side_nodes = false;              // the current trafo ran its node side on node_stream (stage timers: ev[9..12])
   bool x_via_copy_stream = false;       // set by trafo around prepare_nodes: ev_copy[0] marks where the x upload may start
   C *d_f_hat = nullptr;          // staging copy when the user's f_hat is a host pointer
   R *d_invphi[3] = {nullptr, nullptr, nullptr};  // 1/phi_hat tables incl. the (-1)^k fft-shift sign, [local_N[t]]
