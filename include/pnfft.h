@@ -186,6 +186,9 @@ typedef float pnfftf_complex[2];
   /* kernels of this library launched so far / cuFFT, CUB and NCCL calls issued so far */        \
   long long PNX(b200_kernel_launches)(PNX(plan) ths);                                               \
   long long PNX(b200_library_calls)(PNX(plan) ths);                                                 \
+  /* host evaluation of the Kaiser-Bessel taps as the double-precision node-table kernel computes them:      \
+   * psi / dpsi are [M][3][2m+1] for nodes x[M][3], oversampled sizes n[3], shape parameters b[3] */           \
+  void PNX(b200_kb_taps_host)(const double *x, ptrdiff_t M, const ptrdiff_t *n, const double *b, int m, double *psi, double *dpsi); \
   /* host-only self check of the pencil FFT's composed "own chunk" maps for rank (c0, c1) of a p0 x p1 \
    * mesh: self transfers checked, -1 on a mismatch, -2 if one did not compose (no GPU needed) */       \
   int PNX(b200_check_self_maps)(const ptrdiff_t *N, const ptrdiff_t *n, int m, int p0, int p1, int c0, int c1, int c2r); \

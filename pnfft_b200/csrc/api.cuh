@@ -464,6 +464,24 @@ void PNX(b200_gather_timing)(long long *out96, int reset) {
   if (reset) { cudaMemset(d, 0, 96 * 8); cudaMemset(d + 96, 0x3f, 16 * 8); }
 }
 #endif
+// Host evaluation of the Kaiser-Bessel taps exactly as k_node_table2 computes them in double (csrc/window.h: kb_tap_fast,
+// small-argument taps through window_tap): psi / dpsi are [M][3][2m+1].  Lets the CPU tests pin the one-exponential
+// arithmetic against the reference's tensors without a GPU.
+void PNX(b200_kb_taps_host)(const double *x, INT M, const INT *n, const double *b, int m, double *psi, double *dpsi) {
+  const int c = 2 * m + 1;
+  for (INT j = 0; j < M; j++)
+    for (int t = 0; t < 3; t++) {
+      const double nxv = (double)n[t] * x[3 * j + t], flv = floor(nxv);
+      for (int s = 0; s < c; s++) {
+        const double y = flv - nxv - (double)m + (double)s;
+        double a = 0, d = 0;
+        if (!pnb::kb_tap_fast(y, (double)n[t], b[t], m, true, &a, &d))
+          pnb::window_tap<double>(pnb::WIN_KAISER_BESSEL, y, (double)n[t], b[t], m, true, &a, &d);
+        psi[((size_t)j * 3 + t) * c + s] = a;
+        if (dpsi) dpsi[((size_t)j * 3 + t) * c + s] = d;
+      }
+    }
+}
 // Host-only check of the pencil FFT's composed self maps (fftpipe.cuh: compose_self_map) for one rank of a p0 x p1 mesh:
 // every re-distribution stage is emulated on index arrays, once through pack -> chunk -> unpack and once through the
 // composed map, forward and backward.  Returns the number of self transfers checked, -1 on a mismatch, -2 if a self

@@ -102,3 +102,38 @@ def test_adjointness():
     a = po.adj(N, x, f=f, compute_flags=1, m=4)["f_hat"]
     lhs, rhs = np.vdot(f, t), np.vdot(a, fh)
     assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+
+
+@pytest.mark.parametrize("m", [4, 6])
+def test_fast_kaiser_bessel_taps_match_reference(m):
+    """The node-table kernel evaluates the double-precision Kaiser-Bessel taps with one exponential and one division per
+    tap (csrc/window.h kb_tap_fast; reference formulas kernel/ndft-parallel.c:2241-2269).  The same arithmetic, run on the
+    host through pnfft_b200_kb_taps_host, against the reference's pre_psi / pre_dpsi tensors (:1782-1797, :1800-1953)
+    for random nodes, nodes on grid lines and nodes an ulp away from them."""
+    import ctypes as C
+    from pnfft_b200 import api as A
+    N, n = (16, 16, 16), (32, 32, 32)
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-0.5, 0.5, (4000, 3))
+    x[:6] = np.array([[-0.5, 0.25, 0.0], [0.0, 0.0, 0.0], [0.125, -0.125, 0.375], [-0.25, 0.46875, -0.5],
+                      [0.03125, 0.0625, 0.09375], [0.4, 0.0, -0.3]])
+    x[6:12] = np.nextafter(x[:6], 1.0)
+    x[12:18] = np.nextafter(x[:6], -1.0)
+    x[18:24] = x[:6] + 1e-5          # small sinh / sin arguments: the library-call fallback
+    x = np.clip(x, -0.5, np.nextafter(0.5, 0.0))
+    impl = checker.get(False)
+    psi_r, dpsi_r = impl.probe_tensor(x, N, m=m, pnfft_flags=0)
+    fn = A.lib().pnfft_b200_kb_taps_host
+    fn.restype = None
+    P = C.POINTER(C.c_double)
+    fn.argtypes = [P, C.c_ssize_t, C.POINTER(C.c_ssize_t), P, C.c_int, P, P]
+    b = np.array([np.pi * (2.0 - N[t] / n[t]) for t in range(3)])
+    psi, dpsi = np.zeros_like(psi_r), np.zeros_like(dpsi_r)
+    xs = np.ascontiguousarray(x)
+    fn(xs.ctypes.data_as(P), len(x), (C.c_ssize_t * 3)(*n), b.ctypes.data_as(P), m, psi.ctypes.data_as(P), dpsi.ctypes.data_as(P))
+    assert np.abs(psi - psi_r).max() <= 2e-14 * np.abs(psi_r).max()
+    assert rel_l2(psi, psi_r) <= 1e-15
+    # one ulp off a grid line the reference's own derivative formula cancels catastrophically (DESIGN.md section 2)
+    far = np.ones(len(x), bool); far[6:18] = False
+    assert np.abs(dpsi[far] - dpsi_r[far]).max() <= 2e-13 * np.abs(dpsi_r).max()
+    assert rel_l2(dpsi[far], dpsi_r[far]) <= 1e-14
