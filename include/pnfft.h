@@ -177,8 +177,13 @@ typedef float pnfftf_complex[2];
   void PNX(b200_window_tensor)(PNX(plan) ths, PNX(nodes) nodes, R *psi /* [M][3][2m+1] */, R *dpsi); \
   /* select kernels (default 0 = z-marching register kernels): bit 0 = generic global-memory gridding  \
    * kernels; bit 1 = exact window evaluation instead of the per-tap polynomials fitted at plan time; \
-   * bit 2 = shared-memory tile kernels (first implementation, kept for comparison) */                \
+   * bit 3 = z-marching v1 (CTA-synchronous) kernels instead of the warp-autonomous v2 */            \
   void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant);                                    \
+  /* promise that the node coordinates stay unchanged until the next pnfft_set_x: their upload and   \
+   * binning are then done once and reused by every pnfft_trafo / pnfft_adj on these nodes (the      \
+   * reference re-reads x every call, api/api-basic.c:199-244).  PNFFT_B200_X_STATIC=1 sets it for    \
+   * all node sets of an unmodified caller */                                                         \
+  void PNX(b200_nodes_x_static)(PNX(nodes) nodes, int on);                                           \
   int PNX(b200_get_poly_degree)(PNX(plan) ths);                                                     \
   /* device time (ms) of the last trafo/adj stages: [0]=B gather/scatter kernel only,              \
    * [1]=binning, [2]=halo, [3]=F, [4]=D, [5]=H2D, [6]=D2H, [7]=whole */                            \

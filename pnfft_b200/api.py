@@ -166,6 +166,10 @@ class Nodes:
         self._keep["g"] = g
         self.P.fn("set_grad_f", None, [C.c_void_p, C.c_void_p])(_ptr(g), self.h)
 
+    def x_static(self, on=True):
+        """pnfft_b200_nodes_x_static: promise that x stays unchanged until the next set_x (upload and binning are reused)."""
+        self.P.fn("b200_nodes_x_static", None, [C.c_void_p, C.c_int])(self.h, int(bool(on)))
+
     def free(self, flags=0):
         if self.h:
             self.P.fn("free_nodes", None, [C.c_void_p, C.c_uint])(self.h, flags)

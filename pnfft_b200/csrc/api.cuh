@@ -106,7 +106,14 @@ void PNX(set_hessian_f)(CT *h, PNX(nodes) nodes) { AS_NODES(nodes)->hessian_f = 
 void PNX(set_f_real)(RT *f, PNX(nodes) nodes) { AS_NODES(nodes)->f = f; }
 void PNX(set_grad_f_real)(RT *grad_f, PNX(nodes) nodes) { AS_NODES(nodes)->grad_f = grad_f; }
 void PNX(set_hessian_f_real)(RT *h, PNX(nodes) nodes) { AS_NODES(nodes)->hessian_f = h; }
-void PNX(set_x)(RT *x, PNX(nodes) nodes) { AS_NODES(nodes)->x = x; AS_NODES(nodes)->binned = false; AS_NODES(nodes)->d_x_bound = nullptr; }
+void PNX(set_x)(RT *x, PNX(nodes) nodes) {
+  // new coordinates: whatever was derived from the old ones (upload, bins) is void
+  NodesT *nd = AS_NODES(nodes);
+  nd->x = x;
+  nd->binned = nd->il.binned = false;
+  nd->d_x_bound = nd->il.d_x_bound = nullptr;
+  nd->x_uploaded = false;
+}
 void PNX(set_f_hat)(CT *f_hat, PNX(plan) ths) { AS_PLAN(ths)->f_hat = (PlanT::C *)f_hat; }
 void PNX(set_f_hat_real)(RT *f_hat, PNX(plan) ths) { AS_PLAN(ths)->f_hat = (PlanT::C *)f_hat; }
 void PNX(set_b)(RT b0, RT b1, RT b2, PNX(plan) ths) {
@@ -326,7 +333,7 @@ void PNX(get_args)(int argc, char **argv, const char *name, int neededArgs, unsi
 void PNX(check_init_parameters)(int argc, char **argv, INT *N, INT *n, INT *local_M, int *m, unsigned *pnfft_flags,
                                 unsigned *compute_flags, double *x_max, int *np, int *compare_direct, int *debug) {
   int window = 4, fast_gaussian = 0, intpol = -1, interlaced = 0, diff_ik = 0, tr_f_hat = 0;
-  int cf = 1, cg = 1, ch = 1;
+  int cf = 1, cg = 1, ch = 0;      // the Hessian is outside the accelerated path: off unless asked for
   N[0] = N[1] = N[2] = 16; n[0] = n[1] = n[2] = 0; *local_M = 0; *m = 6;
   x_max[0] = x_max[1] = x_max[2] = 0.5;
   np[0] = np[1] = np[2] = 2;
@@ -451,8 +458,15 @@ void PNX(b200_window_tensor)(PNX(plan) ths, PNX(nodes) nodes, RT *psi, RT *dpsi)
 }
 
 // variant bit 0: generic global-memory kernels; bit 1: exact window evaluation instead of the fitted polynomials;
-// 4: shared-memory tile kernels; 8: z-march v1 (CTA-synchronous) instead of the warp-autonomous v2
-void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant) { AS_PLAN(ths)->kernel_variant = variant & 13; AS_PLAN(ths)->use_poly = (variant & 2) ? 0 : 1; }
+// 8: z-march v1 (CTA-synchronous) instead of the warp-autonomous v2
+void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant) { AS_PLAN(ths)->kernel_variant = variant & 9; AS_PLAN(ths)->use_poly = (variant & 2) ? 0 : 1; }
+// "the node coordinates will not change until I call pnfft_set_x again": the upload of x and its binning are reused by
+// every following pnfft_trafo / pnfft_adj on these nodes (the reference re-reads x every call, api/api-basic.c:199-244)
+void PNX(b200_nodes_x_static)(PNX(nodes) nodes, int on) {
+  NodesT *nd = AS_NODES(nodes);
+  nd->x_static = on != 0;
+  if (!on) { nd->binned = nd->il.binned = false; nd->x_uploaded = false; }
+}
 int PNX(b200_get_poly_degree)(PNX(plan) ths) { return AS_PLAN(ths)->poly_deg; }
 #ifdef ZM2_TIMING
 // development aid: per-warp cycle accounting of k_gather_zm2 (build with -DZM2_TIMING)

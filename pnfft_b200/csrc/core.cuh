@@ -17,7 +17,7 @@ void select_device_for_rank();
 enum : unsigned {
   F_PRE_PHI_HAT = 1u << 0, F_FAST_GAUSSIAN = 1u << 1, F_MALLOC_F_HAT = 1u << 6, F_INTERLACED = 1u << 8,
   F_TRANSPOSED_F_HAT = 1u << 11, F_DIFF_IK = 1u << 12, F_WIN_GAUSSIAN = 1u << 13, F_WIN_BSPLINE = 1u << 14,
-  F_WIN_SINC_POWER = 1u << 15, F_WIN_BESSEL_I0 = 1u << 16, F_SORT_NODES = 1u << 18
+  F_WIN_SINC_POWER = 1u << 15, F_WIN_BESSEL_I0 = 1u << 16, F_USE_FK_GAUSSIAN_T = 1u << 17, F_SORT_NODES = 1u << 18
 };
 enum : unsigned { N_MALLOC_X = 1u << 0, N_MALLOC_F = 1u << 1, N_MALLOC_GRAD_F = 1u << 2, N_MALLOC_HESSIAN_F = 1u << 3 };
 enum : unsigned { P_PRE_FULL = 1u << 0, P_PRE_PSI = 1u << 1, P_PRE_GRAD_PSI = 1u << 2 };
@@ -74,12 +74,18 @@ inline void compute_layout(Layout &L, const Mesh &M, const INT *N, const INT *n,
     L.gca[t] = L.cutoff - m - 1 + ((flags & F_INTERLACED) ? 1 : 0);
   }
   L.Nc2 = c2r ? N[2] / 2 + 1 : N[2];
+  L.transposed = (flags & F_TRANSPOSED_F_HAT) != 0;
   const INT ext[3] = {N[0], N[1], L.Nc2};
-  for (int t = 0; t < 2; t++) {
-    block_1d(ext[t], M.np[t], M.co[t], &L.local_N[t], &L.local_N_start[t]);
-    block_1d(L.no[t], M.np[t], M.co[t], &L.local_no[t], &L.local_no_start[t]);
+  if (!L.transposed) {
+    for (int t = 0; t < 2; t++) block_1d(ext[t], M.np[t], M.co[t], &L.local_N[t], &L.local_N_start[t]);
+    L.local_N[2] = ext[2]; L.local_N_start[2] = 0;
+  } else {
+    // k1 over mesh dim 0, k2 over mesh dim 1, k0 whole (PFFT_TRANSPOSED_IN of a 2-d mesh, reference doc/intro.tex:39-44)
+    block_1d(ext[1], M.np[0], M.co[0], &L.local_N[1], &L.local_N_start[1]);
+    block_1d(ext[2], M.np[1], M.co[1], &L.local_N[2], &L.local_N_start[2]);
+    L.local_N[0] = ext[0]; L.local_N_start[0] = 0;
   }
-  L.local_N[2] = ext[2]; L.local_N_start[2] = 0;
+  for (int t = 0; t < 2; t++) block_1d(L.no[t], M.np[t], M.co[t], &L.local_no[t], &L.local_no_start[t]);
   L.local_no[2] = L.no[2]; L.local_no_start[2] = 0;
   for (int t = 0; t < 3; t++) {
     L.local_N_start[t] -= N[t] / 2;
@@ -157,6 +163,10 @@ template <class R> struct Core {
     g.poly = (p->use_poly && p->poly_deg >= 0) ? p->d_poly : nullptr;
     g.poly_deg = p->poly_deg;
     g.poly_deg_psi = p->poly_deg_psi;
+    const bool il = (p->pnfft_flags & F_INTERLACED) != 0;
+    g.il_on = (il && p->il_pass == 1) ? 1 : 0;
+    for (int t = 0; t < 3; t++) g.il[t] = 0.5 / (double)p->L.n[t];
+    g.wscale = il ? (R)0.5 : (R)1;
     return g;
   }
 
@@ -279,8 +289,11 @@ template <class R> struct Core {
       if (n[t] < N[t]) { fprintf(stderr, "pnfft-b200: n < N\n"); return nullptr; }
     }
     if (m < 1 || m > kMaxM) { fprintf(stderr, "pnfft-b200: window cutoff m must be in [1,%d]\n", kMaxM); return nullptr; }
-    if (pnfft_flags & F_TRANSPOSED_F_HAT) { fprintf(stderr, "pnfft-b200: PNFFT_TRANSPOSED_F_HAT is not supported\n"); return nullptr; }
-    if (pnfft_flags & F_INTERLACED) { fprintf(stderr, "pnfft-b200: PNFFT_INTERLACED is not supported\n"); return nullptr; }
+    if ((pnfft_flags & F_USE_FK_GAUSSIAN_T) && (pnfft_flags & F_WIN_GAUSSIAN)) {
+      // the truncated-Gaussian Fourier coefficients need the complex error function (reference kernel/matrix_D.c:195-217, cerf/)
+      fprintf(stderr, "pnfft-b200: PNFFT_WINDOW_GAUSSIAN_T (truncated-Gaussian phi_hat) is not supported; use PNFFT_WINDOW_GAUSSIAN\n");
+      return nullptr;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
       fprintf(stderr, "pnfft-b200: no CUDA device -- this library has no CPU path\n");
@@ -301,10 +314,22 @@ template <class R> struct Core {
       p->sigma[t] = (R)n[t] / (R)N[t];
       p->b[t] = window_shape<R>(p->kind, m, p->sigma[t]);
     }
+    // every rank evaluates the condition for EVERY block of the split axes, so that all ranks refuse together (a rank
+    // that alone returned NULL would leave the others waiting in the first exchange)
     for (int t = 0; t < 2; t++)
-      if (mesh.np[t] > 1 && (L.local_no[t] < L.gcb[t] || L.local_no[t] < L.gca[t])) {
-        fprintf(stderr, "pnfft-b200: local grid block (%td) narrower than the halo (%d) along a split axis\n", L.local_no[t], m);
-        delete p; return nullptr;
+      if (mesh.np[t] > 1) {
+        const INT need = std::max(L.gcb[t], L.gca[t]);
+        for (int c = 0; c < mesh.np[t]; c++) {
+          INT len, start;
+          block_1d(L.no[t], mesh.np[t], c, &len, &start);
+          if (len < need) {
+            if (mesh.rank == 0)
+              fprintf(stderr, "pnfft-b200: grid block %d of axis %d (%td cells) is narrower than the halo (%td): use fewer ranks along it\n",
+                      c, t, len, need);
+            MPI_Comm_free(&p->comm);
+            delete p; return nullptr;
+          }
+        }
       }
     PNB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; i++) PNB_CUDA(cudaEventCreate(&p->ev[i]));
@@ -557,11 +582,14 @@ template <class R> struct Core {
     if ((flags & N_MALLOC_F) && nd->f) { if (is_device_ptr(nd->f)) cudaFree(nd->f); else cudaFreeHost(nd->f); }
     if ((flags & N_MALLOC_GRAD_F) && nd->grad_f) { if (is_device_ptr(nd->grad_f)) cudaFree(nd->grad_f); else cudaFreeHost(nd->grad_f); }
     if ((flags & N_MALLOC_HESSIAN_F) && nd->hessian_f) cudaFreeHost(nd->hessian_f);
-    cudaFree(nd->d_x); cudaFree(nd->d_f); cudaFree(nd->d_grad_f);
-    cudaFree(nd->d_tile); cudaFree(nd->d_tile_sorted); cudaFree(nd->d_perm); cudaFree(nd->d_idx);
-    cudaFree(nd->d_tile_count); cudaFree(nd->d_tile_start); cudaFree(nd->d_item); cudaFree(nd->d_nitems);
-    cudaFree(nd->d_pre_psi); cudaFree(nd->d_pre_dpsi); cudaFree(nd->d_wtab);
-    if (nd->h_maxcol) { cudaFreeHost(nd->h_maxcol); cudaFree(nd->d_maxcol); }
+    cudaFree(nd->d_x); cudaFree(nd->d_f); cudaFree(nd->d_grad_f); cudaFree(nd->d_wtab);
+    for (int k = 0; k < 2; k++) {
+      BinState<R> &b = k ? nd->il : *static_cast<BinState<R> *>(nd);
+      cudaFree(b.d_tile); cudaFree(b.d_tile_sorted); cudaFree(b.d_perm); cudaFree(b.d_idx);
+      cudaFree(b.d_tile_count); cudaFree(b.d_tile_start); cudaFree(b.d_pre_psi); cudaFree(b.d_pre_dpsi);
+      if (b.h_maxcol) { cudaFreeHost(b.h_maxcol); cudaFree(b.d_maxcol); }
+    }
+    if (nd->h_hash) { cudaFreeHost(nd->h_hash); cudaFree(nd->d_hash); }
     delete nd;
   }
 
@@ -582,14 +610,12 @@ template <class R> struct Core {
   }
 
   // kernel families: 2 = warp-autonomous z-marching register kernels (default for m = 4, 6), 0 = z-marching v1
-  // (CTA-synchronous; default for m = 8, variant 8 forces it), 1 = generic global-memory kernels,
-  // 4 = shared-memory tile kernels (the first implementation, kept for comparison)
+  // (CTA-synchronous; m = 8, and variant 8 forces it), 1 = generic global-memory kernels (any m; variant 1 forces them)
   static int kernel_family(const P *p) {
     const int m = p->L.m;
     const bool fits = (m == 4 || m == 6 || m == 8);
-    const int kv = p->kernel_variant & 13;
+    const int kv = p->kernel_variant & 9;
     if (kv == 1 || !fits) return 1;
-    if (kv == 4) return 4;
     if (kv == 8 || m == 8) return 0;
     return 2;
   }
@@ -600,11 +626,12 @@ template <class R> struct Core {
     tg.sub = 1;
     if (fam == 2) { tg.T[0] = Zm2Cfg<6>::T0; tg.T[1] = 16 - 2 * m; tg.T[2] = Zm2Cfg<6>::ZS; tg.sub = Zm2Cfg<6>::SUB; }   // == Zm2Cfg<m>::T0, T1, ZS
     else if (fam == 0) { tg.T[0] = (m <= 6) ? 16 : 8; tg.T[1] = 4; tg.T[2] = (m <= 6) ? 8 : 4; }   // == ZmCfg<m>::T0, T1, ZS
-    else { tg.T[0] = (m <= 6) ? 8 : 6; tg.T[1] = tg.T[0]; tg.T[2] = (m <= 6) ? 16 : 8; }
-    for (int t = 0; t < 3; t++) tg.nt[t] = (int)((p->L.local_no[t] + tg.T[t] - 1) / tg.T[t]);
+    else { tg.T[0] = 8; tg.T[1] = 8; tg.T[2] = 16; }    // generic kernels: the bins only order the nodes for locality
+    // a shifted node of an interlaced plan may sit one cell past the block (the extra ghost cell above)
+    const int extra = (p->pnfft_flags & F_INTERLACED) ? 1 : 0;
+    for (int t = 0; t < 3; t++) tg.nt[t] = (int)((p->L.local_no[t] + extra + tg.T[t] - 1) / tg.T[t]);
     for (int t = 0; t < 3; t++) if (tg.nt[t] < 1) tg.nt[t] = 1;
     tg.ntiles = tg.nt[0] * tg.nt[1] * tg.nt[2];
-    tg.chunk = 512;
     if (tiled_ok) *tiled_ok = fam != 1;
     tg.family = fam;
     return tg;
@@ -626,20 +653,12 @@ template <class R> struct Core {
     const size_t nt1 = (size_t)tg.ntiles * tg.sub + 2;
     if (nd->cap_tiles < nt1) {
       cudaFree(nd->d_tile_count); cudaFree(nd->d_tile_start);
-      PNB_CUDA(cudaMalloc((void **)&nd->d_tile_count, sizeof(int) * 2 * nt1));   // counts | items per tile
-      PNB_CUDA(cudaMalloc((void **)&nd->d_tile_start, sizeof(int) * 2 * nt1));   // tile starts | item starts
+      PNB_CUDA(cudaMalloc((void **)&nd->d_tile_count, sizeof(int) * nt1));
+      PNB_CUDA(cudaMalloc((void **)&nd->d_tile_start, sizeof(int) * nt1));
       nd->cap_tiles = nt1;
     }
-    const size_t max_items = (size_t)std::min<long long>(tg.ntiles, M) + (size_t)M / tg.chunk + 2;
-    if (nd->cap_items < max_items) {
-      cudaFree(nd->d_item);
-      PNB_CUDA(cudaMalloc((void **)&nd->d_item, sizeof(int) * 3 * max_items));
-      nd->cap_items = max_items;
-    }
-    if (!nd->d_nitems) PNB_CUDA(cudaMalloc((void **)&nd->d_nitems, sizeof(int)));
-    PNB_CUDA(cudaMemsetAsync(nd->d_tile_count, 0, sizeof(int) * 2 * nt1, st));
-    PNB_CUDA(cudaMemsetAsync(nd->d_nitems, 0, sizeof(int), st));
-    if (M == 0) { nd->max_items = 0; return; }
+    PNB_CUDA(cudaMemsetAsync(nd->d_tile_count, 0, sizeof(int) * nt1, st));
+    if (M == 0) return;
     const GridGeom<R> g = geom(p);
     k_bin_nodes<R><<<(M + 255) / 256, 256, 0, st>>>(g, tg, d_x, M, nd->d_tile, nd->d_idx, nd->d_tile_count);
     int bits = 1;
@@ -655,18 +674,9 @@ template <class R> struct Core {
       p->sort_tmp_bytes = tmp;
     }
     cub::DeviceRadixSort::SortPairs(p->d_sort_tmp, tmp, nd->d_tile, nd->d_tile_sorted, nd->d_idx, nd->d_perm, M, 0, bits, st);
-    int *n_items = nd->d_tile_count + nt1, *item_start = nd->d_tile_start + nt1;
     cub::DeviceScan::ExclusiveSum(p->d_sort_tmp, tmp, nd->d_tile_count, nd->d_tile_start, (int)nt1, st);
     p->launches += 1;       // k_bin_nodes
     p->lib_launches += 2;   // cub radix sort + scan
-    if (kernel_family(p) == 4) {   // (tile, node-chunk) work items of the shared-memory tile kernels
-      k_items_per_tile<<<(tg.ntiles + 256) / 256, 256, 0, st>>>(tg, nd->d_tile_count, n_items);
-      cub::DeviceScan::ExclusiveSum(p->d_sort_tmp, tmp, n_items, item_start, (int)nt1, st);
-      k_fill_items<<<(tg.ntiles + 255) / 256, 256, 0, st>>>(tg, nd->d_tile_count, nd->d_tile_start, item_start, nd->d_item, nd->d_nitems);
-      p->launches += 2;
-      p->lib_launches += 1;
-    }
-    nd->max_items = (long long)max_items;
     if (kernel_family(p) == 2) {
       // load-balance hint for the NEXT gridding launches: lands in pinned host memory by an async copy that nobody waits
       // for (the host reads whatever the last finished binning left there: the old value or the new one, never a zero)
@@ -749,68 +759,72 @@ template <class R> struct Core {
       while (nseg < nseg_min && nseg * 2 <= tg.nt[2]) nseg *= 2;
       zg.zseg = (tg.nt[2] + nseg - 1) / nseg;
       zg.nseg = (tg.nt[2] + zg.zseg - 1) / zg.zseg;
-      const unsigned nblk = (unsigned)(ncol * zg.nseg);
       const size_t psm = g.poly ? sizeof(R) * (size_t)2 * (g.poly_deg + 1) * 3 * Cfg::C : 0;
-      const unsigned ntb = (unsigned)((na.M + kZm2TabNodes - 1) / kZm2TabNodes);
-      if (!scatter) {
-        typedef typename Sm::RowG Row;
-        if (p->b_phase & 1) {
-          ensure(&nd->d_wtab, &nd->cap_wtab, (size_t)na.M * Row::ROWLEN + 64);
-          auto kt = k_node_table2<R, M_, GRAD, false, CPLX>;
-          const size_t tsm = (size_t)kZm2TabNodes * Row::ROWBYTES + psm;
+      typedef typename Sm::RowG RowG;
+      typedef typename Sm::RowS RowS;
+      const size_t rowlen = scatter ? RowS::ROWLEN : RowG::ROWLEN;
+      // The node table (rowlen * M reals) is built and consumed in column batches when it would not fit the budget
+      // (PNFFT_B200_TABLE_GB, default 24 GB): 2^27 nodes on one GPU need 58 - 116 GB of rows otherwise.
+      static const double cap_gb = getenv("PNFFT_B200_TABLE_GB") ? atof(getenv("PNFFT_B200_TABLE_GB")) : 24.0;
+      const double need_gb = (double)na.M * rowlen * sizeof(R) / 1073741824.0;
+      int nbatch = 1;
+      if (need_gb > cap_gb && !(p->b_phase != 3)) nbatch = std::min(ncol, (int)std::ceil(2.0 * need_gb / cap_gb));
+      std::vector<int> cb((size_t)nbatch + 1), nb((size_t)nbatch + 1);
+      for (int k = 0; k <= nbatch; k++) cb[(size_t)k] = (int)((long long)ncol * k / nbatch);
+      nb[0] = 0; nb[(size_t)nbatch] = na.M;
+      if (nbatch > 1) {          // first sorted node of every batch: the bins of a column are contiguous in tile_start
+        const size_t per_col = (size_t)tg.nt[2] * Cfg::SUB;
+        for (int k = 1; k < nbatch; k++)
+          PNB_CUDA(cudaMemcpyAsync(&nb[(size_t)k], nd->d_tile_start + (size_t)cb[(size_t)k] * per_col, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        PNB_CUDA(cudaStreamSynchronize(p->stream));
+      }
+      size_t max_rows = 0;
+      for (int k = 0; k < nbatch; k++) max_rows = std::max(max_rows, (size_t)(nb[(size_t)k + 1] - nb[(size_t)k]));
+      ensure(&nd->d_wtab, &nd->cap_wtab, max_rows * rowlen + 64);
+      for (int k = 0; k < nbatch; k++) {
+        const int first = nb[(size_t)k], last = nb[(size_t)k + 1];
+        if (last <= first) continue;
+        NodeArgs<R> nb_args = na;
+        nb_args.M = last;
+        R *tab = nd->d_wtab - (size_t)first * rowlen;        // rows are addressed by their absolute sorted position
+        zg.col0 = cb[(size_t)k];
+        const unsigned nblk = (unsigned)((cb[(size_t)k + 1] - cb[(size_t)k]) * zg.nseg);
+        const unsigned ntb = (unsigned)((last - first + kZm2TabNodes - 1) / kZm2TabNodes);
+        if (!scatter) {
+          if (p->b_phase & 1) {
+            auto kt = k_node_table2<R, M_, GRAD, false, CPLX>;
+            const size_t tsm = (size_t)kZm2TabNodes * RowG::ROWBYTES + psm;
+            PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+            kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, nb_args, tab, first);
+            p->launches++;
+          }
+          if (p->b_phase & 2) {
+            GatherOut<R> out;
+            out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
+            auto kern = k_gather_zm2<R, CPLX, M_, GRAD>;
+            PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
+            kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
+            p->launches++;
+          }
+        } else {
+          auto kt = k_node_table2<R, M_, GRAD, true, CPLX>;
+          const size_t tsm = (size_t)kZm2TabNodes * RowS::ROWBYTES + psm;
           PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-          kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, na, nd->d_wtab);
-          p->launches++;
+          kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, nb_args, tab, first);
+          auto kern = k_scatter_zm2<R, CPLX, M_, GRAD>;
+          PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
+          kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::scatter, p->stream>>>(tm, zg, tab, nd->d_tile_start);
+          p->launches += 2;
         }
-        if (p->b_phase & 2) {
-          GatherOut<R> out;
-          out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
-          auto kern = k_gather_zm2<R, CPLX, M_, GRAD>;
-          PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
-          kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, nd->d_wtab, nd->d_tile_start, out);
-          p->launches++;
-        }
-        PNB_CUDA(cudaGetLastError());
-        return;
-      } else {
-        typedef typename Sm::RowS Row;
-        ensure(&nd->d_wtab, &nd->cap_wtab, (size_t)na.M * Row::ROWLEN + 64);
-        auto kt = k_node_table2<R, M_, GRAD, true, CPLX>;
-        const size_t tsm = (size_t)kZm2TabNodes * Row::ROWBYTES + psm;
-        PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-        kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, na, nd->d_wtab);
-        auto kern = k_scatter_zm2<R, CPLX, M_, GRAD>;
-        PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
-        kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::scatter, p->stream>>>(tm, zg, nd->d_wtab, nd->d_tile_start);
       }
       PNB_CUDA(cudaGetLastError());
-      p->launches += 2;
     }
   }
 
   template <bool CPLX, int M_, bool GRAD>
-  static void launch_tiled(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
-    if (kernel_family(p) == 2) { launch_zm2<CPLX, M_, GRAD>(p, nd, na, scatter); return; }
-    if (kernel_family(p) == 0) { launch_zm<CPLX, M_, GRAD>(p, nd, na, scatter); return; }
-    typedef typename CellT<R, CPLX>::type Cell;
-    typedef TileCfg<M_, (int)sizeof(Cell)> Cfg;
-    typedef TiledSmem<R, CPLX, M_, GRAD> Sm;
-    const TileGeom tg = tile_geom(p, nullptr);
-    const GridGeom<R> g = geom(p);
-    const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::BX, Cfg::BY, Cfg::BZ);
-    const unsigned nblk = (unsigned)nd->max_items;
-    if (nblk == 0) return;
-    if (!scatter) {
-      auto kern = k_gather_tiled<R, CPLX, M_, GRAD>;
-      PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
-      kern<<<nblk, kGatherWarps * 32, Sm::gather, p->stream>>>(tm, g, tg, nullptr, na, nd->d_item, nd->d_nitems);
-    } else {
-      auto kern = k_scatter_tiled<R, CPLX, M_, GRAD>;
-      PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
-      kern<<<nblk, (2 * M_ + 1) * 32, Sm::scatter, p->stream>>>(tm, g, tg, na, nd->d_item, nd->d_nitems);
-    }
-    PNB_CUDA(cudaGetLastError());
-    p->launches++;
+  static void launch_zmarch(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
+    if (kernel_family(p) == 2) launch_zm2<CPLX, M_, GRAD>(p, nd, na, scatter);
+    else launch_zm<CPLX, M_, GRAD>(p, nd, na, scatter);
   }
 
   template <bool CPLX> static void launch_B(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
@@ -820,9 +834,9 @@ template <class R> struct Core {
     if (na.M == 0) return;
     if (tiled) {
       switch (p->L.m) {
-        case 4: if (grad) launch_tiled<CPLX, 4, true>(p, nd, na, scatter); else launch_tiled<CPLX, 4, false>(p, nd, na, scatter); return;
-        case 6: if (grad) launch_tiled<CPLX, 6, true>(p, nd, na, scatter); else launch_tiled<CPLX, 6, false>(p, nd, na, scatter); return;
-        case 8: if (grad) launch_tiled<CPLX, 8, true>(p, nd, na, scatter); else launch_tiled<CPLX, 8, false>(p, nd, na, scatter); return;
+        case 4: if (grad) launch_zmarch<CPLX, 4, true>(p, nd, na, scatter); else launch_zmarch<CPLX, 4, false>(p, nd, na, scatter); return;
+        case 6: if (grad) launch_zmarch<CPLX, 6, true>(p, nd, na, scatter); else launch_zmarch<CPLX, 6, false>(p, nd, na, scatter); return;
+        case 8: if (grad) launch_zmarch<CPLX, 8, true>(p, nd, na, scatter); else launch_zmarch<CPLX, 8, false>(p, nd, na, scatter); return;
         default: break;
       }
     }
@@ -839,12 +853,48 @@ template <class R> struct Core {
     if (p->L.c2r) launch_B<false>(p, nd, na, scatter); else launch_B<true>(p, nd, na, scatter);
   }
 
-  // x on the device + binning (skipped when precompute_psi pinned the node set)
-  static const R *prepare_nodes(P *p, Nd *nd, int ev_after_copy, int ev_after_bin) {
+  // -------------------------------------------------------------------------------------------
+  // node coordinates on the device, binning, and when both may be reused
+  //   * pnfft_precompute_psi pins the node set (the reference's own contract: tables belong to the x they were made from)
+  //   * nodes->x_static (extension pnfft_b200_nodes_x_static, or PNFFT_B200_X_STATIC=1) promises that x does not change
+  //     between calls: the upload and the binning of the first call are reused until pnfft_set_x
+  //   * device-resident x: a 64-bit content hash (one streaming pass, ~0.1 ms for 2^24 nodes) tells whether the bins of
+  //     the previous call still belong to these coordinates (PNFFT_B200_X_HASH=0 switches it off)
+  // -------------------------------------------------------------------------------------------
+  static bool env_flag(const char *name, bool dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) != 0 : dflt;
+  }
+  static unsigned long long hash_device_x(P *p, Nd *nd, const R *dx) {
+    const size_t n = 3 * (size_t)nd->local_M;
+    if (!nd->h_hash) {
+      PNB_CUDA(cudaHostAlloc((void **)&nd->h_hash, sizeof(unsigned long long), cudaHostAllocDefault));
+      PNB_CUDA(cudaMalloc((void **)&nd->d_hash, sizeof(unsigned long long)));
+    }
+    PNB_CUDA(cudaMemsetAsync(nd->d_hash, 0, sizeof(unsigned long long), p->copy_stream));
+    if (n) k_hash_words<R><<<148 * 8, 256, 0, p->copy_stream>>>(dx, (long long)n, nd->d_hash);
+    PNB_CUDA(cudaMemcpyAsync(nd->h_hash, nd->d_hash, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->copy_stream));
+    PNB_CUDA(cudaStreamSynchronize(p->copy_stream));
+    p->launches++;
+    return *nd->h_hash | 1ull;      // never 0 (0 = "no hash")
+  }
+  // dx_known: the coordinates are on the device already (second interlacing pass)
+  static const R *prepare_nodes(P *p, Nd *nd, int ev_after_copy, int ev_after_bin, const R *dx_known = nullptr) {
     const size_t M = (size_t)nd->local_M;
+    static const bool env_static = env_flag("PNFFT_B200_X_STATIC", false);
+    static const bool use_hash = env_flag("PNFFT_B200_X_HASH", true);
+    const bool is_static = nd->x_static || env_static;
+    const bool pinned = (nd->precompute_flags & P_PRE_PSI) != 0;
+    const int fam = kernel_family(p);
     const R *dx;
-    if (nd->binned && nd->d_x_bound) dx = nd->d_x_bound;
-    else if (p->x_via_copy_stream && nd->x && !is_device_ptr(nd->x) && M) {
+    unsigned long long h = 0;
+    if (dx_known) dx = dx_known;
+    else if ((pinned || is_static) && nd->binned && nd->d_x_bound && nd->bin_plan == (const void *)p) dx = nd->d_x_bound;
+    else if (nd->x && is_device_ptr(nd->x)) {
+      dx = nd->x;
+      if (use_hash && !pinned && M) h = hash_device_x(p, nd, dx);
+    } else if (is_static && nd->x_uploaded && nd->d_x) dx = nd->d_x;
+    else if (p->x_via_copy_stream && nd->x && M) {
       // host-resident coordinates travel on the copy stream, right behind f_hat on the bus, while D and F run on the
       // plan's stream (trafo recorded ev_copy[0] after the f_hat upload)
       ensure(&nd->d_x, &nd->cap_x, 3 * M);
@@ -853,66 +903,127 @@ template <class R> struct Core {
       PNB_CUDA(cudaEventRecord(p->ev_copy[1], p->copy_stream));
       PNB_CUDA(cudaStreamWaitEvent(p->stream, p->ev_copy[1], 0));
       dx = nd->d_x;
+      nd->x_uploaded = true;
+    } else {
+      dx = dev_in(p, nd->x, &nd->d_x, &nd->cap_x, 3 * M, true);
+      nd->x_uploaded = true;
     }
-    else dx = dev_in(p, nd->x, &nd->d_x, &nd->cap_x, 3 * M, true);
     if (ev_after_copy >= 0) PNB_CUDA(cudaEventRecord(p->ev[ev_after_copy], p->stream));
-    if (!nd->binned) bin_nodes(p, nd, dx);
+    bool valid = nd->binned && nd->bin_plan == (const void *)p && nd->bin_family == fam && nd->d_x_bound == dx;
+    if (valid && !pinned && !is_static) valid = h != 0 && nd->bin_hash == h;     // device x: same content as last time?
+    if (!valid) {
+      bin_nodes(p, nd, dx);
+      nd->bin_plan = p; nd->bin_family = fam; nd->d_x_bound = dx; nd->bin_hash = h;
+      nd->binned = pinned || is_static || h != 0;
+      if (pinned && nd->d_pre_psi) fill_pre_psi(p, nd, dx);    // the tables are stored in sorted order: redo them with the bins
+    }
     if (ev_after_bin >= 0) PNB_CUDA(cudaEventRecord(p->ev[ev_after_bin], p->stream));
     return dx;
   }
 
+  static void fill_pre_psi(P *p, Nd *nd, const R *dx) {
+    const size_t M = (size_t)nd->local_M;
+    if (!M) return;
+    const GridGeom<R> g = geom(p);
+    k_precompute_psi<R><<<(unsigned)((M * 32 + 255) / 256), 256, 0, p->stream>>>(g, dx, nd->d_perm, (int)M, nd->d_pre_psi, nd->d_pre_dpsi);
+    p->launches++;
+  }
+
   static void precompute_psi(P *p, Nd *nd, unsigned pre_flags) {
     if (!p || !nd) return;
-    cudaFree(nd->d_pre_psi); cudaFree(nd->d_pre_dpsi);
-    nd->d_pre_psi = nd->d_pre_dpsi = nullptr;
-    nd->precompute_flags = pre_flags;
-    nd->binned = false; nd->d_x_bound = nullptr;
+    for (int k = 0; k < 2; k++) {
+      BinState<R> &b = k ? nd->il : *static_cast<BinState<R> *>(nd);
+      cudaFree(b.d_pre_psi); cudaFree(b.d_pre_dpsi);
+      b.d_pre_psi = b.d_pre_dpsi = nullptr;
+      b.binned = false; b.d_x_bound = nullptr;
+    }
+    nd->precompute_flags = 0;
+    nd->x_uploaded = false;
     if (!(pre_flags & P_PRE_PSI)) return;
     if (pre_flags & P_PRE_FULL) {
       fprintf(stderr, "pnfft-b200: PNFFT_PRE_FULL is not supported; using the tensor-product tables (PNFFT_PRE_PSI)\n");
-      nd->precompute_flags &= ~P_PRE_FULL;
+      pre_flags &= ~P_PRE_FULL;
     }
     const size_t M = (size_t)nd->local_M;
-    const R *dx = prepare_nodes(p, nd, -1, -1);
-    nd->binned = true; nd->d_x_bound = dx;
     const int c = p->L.cutoff;
     // the reference never fills pre_dpsi (PNFFT_DIFF_AD == 0 makes its test always false, SURVEY 8a defect 2);
     // here PRE_GRAD_PSI is honoured whenever the gradient is taken analytically
     const bool want_d = (pre_flags & P_PRE_GRAD_PSI) && !(p->pnfft_flags & F_DIFF_IK);
-    PNB_CUDA(cudaMalloc((void **)&nd->d_pre_psi, sizeof(R) * 3 * c * (M ? M : 1)));
-    if (want_d) PNB_CUDA(cudaMalloc((void **)&nd->d_pre_dpsi, sizeof(R) * 3 * c * (M ? M : 1)));
-    if (M) {
-      const GridGeom<R> g = geom(p);
-      k_precompute_psi<R><<<(unsigned)((M * 32 + 255) / 256), 256, 0, p->stream>>>(g, dx, nd->d_perm, (int)M, nd->d_pre_psi, nd->d_pre_dpsi);
-      p->launches++;
+    const int npass = (p->pnfft_flags & F_INTERLACED) ? 2 : 1;    // reference pre_psi / pre_psi_il (ndft-parallel.c:1184-1240)
+    const R *dx = nullptr;
+    for (int pass = 0; pass < npass; pass++) {
+      p->il_pass = pass;
+      if (pass) nd->swap_il();
+      dx = prepare_nodes(p, nd, -1, -1, dx);
+      nd->binned = true;
+      PNB_CUDA(cudaMalloc((void **)&nd->d_pre_psi, sizeof(R) * 3 * c * (M ? M : 1)));
+      if (want_d) PNB_CUDA(cudaMalloc((void **)&nd->d_pre_dpsi, sizeof(R) * 3 * c * (M ? M : 1)));
+      fill_pre_psi(p, nd, dx);
+      if (pass) nd->swap_il();
     }
+    p->il_pass = 0;
+    nd->precompute_flags = pre_flags;
     PNB_CUDA(cudaStreamSynchronize(p->stream));
   }
 
   // -------------------------------------------------------------------------------------------
   // D / D^H and ik scaling launches
   // -------------------------------------------------------------------------------------------
+  // the local f_hat block in memory order: (k0, k1, k2), or (k1, k2, k0) for PNFFT_TRANSPOSED_F_HAT
+  static void fhat_axes(const P *p, int ax[3]) {
+    if (p->L.transposed) { ax[0] = 1; ax[1] = 2; ax[2] = 0; } else { ax[0] = 0; ax[1] = 1; ax[2] = 2; }
+  }
+  static FhatGeom fhat_geom(const P *p, int il_sign) {
+    FhatGeom fg;
+    int ax[3];
+    fhat_axes(p, ax);
+    for (int k = 0; k < 3; k++) {
+      fg.l[k] = (int)p->L.local_N[ax[k]]; fg.s[k] = (int)p->L.local_N_start[ax[k]]; fg.n[k] = (double)p->L.n[ax[k]];
+    }
+    fg.il_sign = il_sign;
+    return fg;
+  }
   static void run_deconv(P *p, const C *src_f_hat, C *f_hat_acc, bool adjoint) {
-    const Layout &L = p->L;
-    const int l0 = (int)L.local_N[0], l1 = (int)L.local_N[1], l2 = (int)L.local_N[2];
-    if (l0 <= 0 || l1 <= 0 || l2 <= 0) return;
-    const int bs = l2 >= 128 ? 128 : 32;
-    if (!adjoint) k_deconv_fwd<R, C><<<grid3(l0, l1, l2, bs), bs, 0, p->stream>>>(src_f_hat, p->d_g1, p->d_invphi[0], p->d_invphi[1], p->d_invphi[2], l0, l1, l2);
-    else k_deconv_adj<R, C><<<grid3(l0, l1, l2, bs), bs, 0, p->stream>>>(f_hat_acc, p->d_g1, p->d_invphi[0], p->d_invphi[1], p->d_invphi[2], l0, l1, l2);
+    // second pass of an interlaced plan: exp(+ pi i sum k/n) after D, exp(- pi i sum k/n) before D^H (reference matrix_D.c:247-262)
+    const bool il = (p->pnfft_flags & F_INTERLACED) && p->il_pass == 1;
+    const FhatGeom fg = fhat_geom(p, il ? (adjoint ? -1 : +1) : 0);
+    if (fg.l[0] <= 0 || fg.l[1] <= 0 || fg.l[2] <= 0) return;
+    int ax[3];
+    fhat_axes(p, ax);
+    const int bs = fg.l[2] >= 128 ? 128 : 32;
+    const R *cA = p->d_invphi[ax[0]], *cB = p->d_invphi[ax[1]], *cC = p->d_invphi[ax[2]];
+    if (!adjoint) k_deconv_fwd<R, C><<<grid3(fg.l[0], fg.l[1], fg.l[2], bs), bs, 0, p->stream>>>(src_f_hat, p->d_g1, cA, cB, cC, fg);
+    else k_deconv_adj<R, C><<<grid3(fg.l[0], fg.l[1], fg.l[2], bs), bs, 0, p->stream>>>(f_hat_acc, p->d_g1, cA, cB, cC, fg);
     p->launches++;
   }
   static void run_ik(P *p, const C *in, C *out, int mode, int dim) {
-    const Layout &L = p->L;
-    const int l0 = (int)L.local_N[0], l1 = (int)L.local_N[1], l2 = (int)L.local_N[2];
-    if (l0 <= 0 || l1 <= 0 || l2 <= 0) return;
-    const int bs = l2 >= 128 ? 128 : 32;
-    k_ik_scale<R, C><<<grid3(l0, l1, l2, bs), bs, 0, p->stream>>>(in, out, mode, dim, (int)L.local_N_start[0], (int)L.local_N_start[1],
-                                                                     (int)L.local_N_start[2], l0, l1, l2);
+    const FhatGeom fg = fhat_geom(p, 0);
+    if (fg.l[0] <= 0 || fg.l[1] <= 0 || fg.l[2] <= 0) return;
+    int ax[3], axis = 0;
+    fhat_axes(p, ax);
+    for (int k = 0; k < 3; k++) if (ax[k] == dim) axis = k;
+    const int bs = fg.l[2] >= 128 ? 128 : 32;
+    k_ik_scale<R, C><<<grid3(fg.l[0], fg.l[1], fg.l[2], bs), bs, 0, p->stream>>>(in, out, mode, axis, fg);
     p->launches++;
   }
 
   static void rec(P *p, int i) { PNB_CUDA(cudaEventRecord(p->ev[i], p->stream)); }
   static double ms(P *p, int a, int b) { float t = 0; cudaEventElapsedTime(&t, p->ev[a], p->ev[b]); return (double)t; }
+
+  // PNFFT_COMPUTE_HESSIAN_F is outside the accelerated path: say so once, and leave zeros like the reference's own
+  // zeroing of the output arrays (api/api-basic.c:210-222) instead of stale memory
+  static void hessian_unsupported(P *p, Nd *nd, unsigned cf) {
+    if (!(cf & C_HESSIAN_F)) return;
+    if (!p->warned_hessian) {
+      fprintf(stderr, "pnfft-b200: PNFFT_COMPUTE_HESSIAN_F is not part of the accelerated path; hessian_f is zero-filled\n");
+      p->warned_hessian = true;
+    }
+    if (nd && nd->hessian_f && !(cf & C_ACCUMULATED)) {
+      const size_t bytes = sizeof(R) * 6 * (p->L.c2r ? 1 : 2) * (size_t)nd->local_M;
+      if (is_device_ptr(nd->hessian_f)) PNB_CUDA(cudaMemsetAsync(nd->hessian_f, 0, bytes, p->stream));
+      else memset(nd->hessian_f, 0, bytes);
+    }
+  }
 
   // -------------------------------------------------------------------------------------------
   // trafo  (reference api/api-basic.c:170-244)
@@ -926,8 +1037,10 @@ template <class R> struct Core {
     const size_t nloc = (size_t)local_N_total(p);
     const int NC = L.c2r ? 1 : 2;
     const bool ik = (p->pnfft_flags & F_DIFF_IK) != 0;
+    const int npass = (p->pnfft_flags & F_INTERLACED) ? 2 : 1;   // reference api-basic.c:233-240
+    hessian_unsupported(p, nd, cf);
     rec(p, 0);
-    // ---- D ----
+    // ---- f_hat on the device ----
     const C *fh = nullptr;
     if (!(cf & C_OMIT_DECONV)) {
       if (!p->f_hat) { fprintf(stderr, "pnfft-b200: f_hat is not set\n"); return; }
@@ -940,92 +1053,103 @@ template <class R> struct Core {
     static const bool no_prefetch = getenv("PNFFT_B200_NO_PREFETCH") && atoi(getenv("PNFFT_B200_NO_PREFETCH")) != 0;
     PNB_CUDA(cudaEventRecord(p->ev_copy[0], st));
     p->x_via_copy_stream = !no_prefetch;
-    if (fh) run_deconv(p, fh, nullptr, false);
-    rec(p, 2);
 
-    // node-side preparation is shared by all B passes of this call
     R *df = nullptr, *dg = nullptr;
     const R *dx = nullptr;
     const bool conv = !(cf & C_OMIT_CONV);
     const bool acc = (cf & C_ACCUMULATED) != 0;
-    auto node_setup = [&]() {
-      dx = prepare_nodes(p, nd, 4, 5);
-      if (cf & C_F) df = dev_in(p, nd->f, &nd->d_f, &nd->cap_f, (size_t)NC * M, acc);
-      if (cf & C_GRAD_F) dg = dev_in(p, nd->grad_f, &nd->d_grad_f, &nd->cap_grad, (size_t)3 * NC * M, acc);
-    };
-    auto base_args = [&]() {
-      NodeArgs<R> na;
-      na.x = dx; na.perm = nd->d_perm; na.M = (int)M; na.f = nullptr; na.f_stride = 1; na.f_off = 0; na.grad = nullptr;
-      na.accumulate = acc ? 1 : 0;
-      const bool use_pre = (nd->precompute_flags & P_PRE_PSI) && nd->d_pre_psi;
-      na.pre_psi = use_pre ? nd->d_pre_psi : nullptr;
-      na.pre_dpsi = use_pre ? nd->d_pre_dpsi : nullptr;
-      return na;
-    };
-
-    if (!ik) {
-      // z-march v2: the node side of the call (x upload, binning, node table) needs nothing from the grid, so it runs on
-      // its own stream while D, F and the halo exchange run here; the gather waits for both.
-      // On by default for multi-rank plans, where F and the halo exchange are latency bound (measured on 1x2 B200:
-      // step 36.57 -> 36.35 ms); on one GPU the two sides only compete for HBM (65.4 vs 65.5 ms) and the stage timers
-      // stay cleaner without it.  PNFFT_B200_SIDE_STREAM=0 / 1 forces it off / on.
-      static const int side_env = getenv("PNFFT_B200_SIDE_STREAM") ? atoi(getenv("PNFFT_B200_SIDE_STREAM")) : -1;
-      const bool want_side = side_env >= 0 ? side_env != 0 : p->mesh.size > 1;
-      p->side_nodes = want_side && conv && M > 0 && kernel_family(p) == 2 && (cf & (C_F | C_GRAD_F));
-      NodeArgs<R> na_side;
-      if (p->side_nodes) {
-        p->stream = p->node_stream;
-        rec(p, 11);
-        node_setup();                 // records ev[4] (x on the device) and ev[5] (binned) on the node stream
-        rec(p, 9);
-        na_side = base_args();
-        na_side.f = df; na_side.grad = dg;
-        if (na_side.grad && na_side.pre_psi && !na_side.pre_dpsi) na_side.pre_psi = nullptr;
-        p->b_phase = 1;
-        if (df || dg) launch_B_any(p, nd, na_side, false);
-        p->b_phase = 3;
-        rec(p, 10);
-        p->stream = st;
-      }
-      if (!(cf & C_OMIT_FFT)) fft_forward(p);
-      rec(p, 3);
-      if (p->side_nodes) {
-        halo(p, false);
-        rec(p, 6);
-        PNB_CUDA(cudaStreamWaitEvent(st, p->ev[10], 0));
-        p->b_phase = 2;
-        if (df || dg) launch_B_any(p, nd, na_side, false);
-        p->b_phase = 3;
-        rec(p, 7);
-      } else if (conv) {
-        node_setup();
-        halo(p, false);
-        rec(p, 6);
-        NodeArgs<R> na = base_args();
-        na.f = df; na.grad = dg;
-        if (na.grad && na.pre_psi && !na.pre_dpsi) na.pre_psi = nullptr;   // no dpsi table: evaluate on the fly
-        if (df || dg) launch_B_any(p, nd, na, false);
-        rec(p, 7);
-      } else { rec(p, 4); rec(p, 5); rec(p, 6); rec(p, 7); }
-    } else {
-      p->side_nodes = false;
-      // ik differentiation: 1 (f) + 3 (grad) passes of F and B (reference api-basic.c:100-167)
-      if ((cf & C_GRAD_F) && !(cf & C_OMIT_DECONV))
-        PNB_CUDA(cudaMemcpyAsync(p->d_g1_buffer, p->d_g1, sizeof(C) * nloc, cudaMemcpyDeviceToDevice, st));
-      rec(p, 3);
-      if (conv) node_setup(); else { rec(p, 4); rec(p, 5); }
-      if (cf & C_F) {
-        if (!(cf & C_OMIT_FFT)) fft_forward(p);
-        if (conv) { halo(p, false); NodeArgs<R> na = base_args(); na.f = df; launch_B_any(p, nd, na, false); }
-      }
-      if (cf & C_GRAD_F)
-        for (int dim = 0; dim < 3; dim++) {
-          if (!(cf & C_OMIT_DECONV)) run_ik(p, p->d_g1_buffer, p->d_g1, 0, dim);
-          if (!(cf & C_OMIT_FFT)) fft_forward(p);
-          if (conv) { halo(p, false); NodeArgs<R> na = base_args(); na.f = dg; na.f_stride = 3; na.f_off = dim; launch_B_any(p, nd, na, false); }
+    p->side_nodes = false;
+    for (int pass = 0; pass < npass; pass++) {
+      p->il_pass = pass;
+      if (pass) nd->swap_il();
+      const bool acc_pass = acc || pass > 0;       // the second pass adds to the first (reference assign.c:689-691)
+      // ---- D ----
+      if (fh) run_deconv(p, fh, nullptr, false);
+      rec(p, 2);
+      // node-side preparation is shared by all B passes of this call
+      auto node_setup = [&]() {
+        dx = prepare_nodes(p, nd, 4, 5, dx);
+        if (pass == 0) {
+          if (cf & C_F) df = dev_in(p, nd->f, &nd->d_f, &nd->cap_f, (size_t)NC * M, acc);
+          if (cf & C_GRAD_F) dg = dev_in(p, nd->grad_f, &nd->d_grad_f, &nd->cap_grad, (size_t)3 * NC * M, acc);
         }
-      rec(p, 6); rec(p, 7);
+      };
+      auto base_args = [&]() {
+        NodeArgs<R> na;
+        na.x = dx; na.perm = nd->d_perm; na.M = (int)M; na.f = nullptr; na.f_stride = 1; na.f_off = 0; na.grad = nullptr;
+        na.accumulate = acc_pass ? 1 : 0;
+        const bool use_pre = (nd->precompute_flags & P_PRE_PSI) && nd->d_pre_psi;
+        na.pre_psi = use_pre ? nd->d_pre_psi : nullptr;
+        na.pre_dpsi = use_pre ? nd->d_pre_dpsi : nullptr;
+        return na;
+      };
+
+      if (!ik) {
+        // z-march v2: the node side of the call (x upload, binning, node table) needs nothing from the grid, so it runs on
+        // its own stream while D, F and the halo exchange run here; the gather waits for both.
+        // On by default for multi-rank plans, where F and the halo exchange are latency bound (measured on 1x2 B200:
+        // step 36.57 -> 36.35 ms); on one GPU the two sides only compete for HBM (65.4 vs 65.5 ms) and the stage timers
+        // stay cleaner without it.  PNFFT_B200_SIDE_STREAM=0 / 1 forces it off / on.
+        static const int side_env = getenv("PNFFT_B200_SIDE_STREAM") ? atoi(getenv("PNFFT_B200_SIDE_STREAM")) : -1;
+        const bool want_side = side_env >= 0 ? side_env != 0 : p->mesh.size > 1;
+        p->side_nodes = want_side && npass == 1 && conv && M > 0 && kernel_family(p) == 2 && (cf & (C_F | C_GRAD_F));
+        NodeArgs<R> na_side;
+        if (p->side_nodes) {
+          p->stream = p->node_stream;
+          PNB_CUDA(cudaStreamWaitEvent(p->node_stream, p->ev_copy[0], 0));   // the node stream starts where this call started
+          rec(p, 11);
+          node_setup();                 // records ev[4] (x on the device) and ev[5] (binned) on the node stream
+          rec(p, 9);
+          na_side = base_args();
+          na_side.f = df; na_side.grad = dg;
+          if (na_side.grad && na_side.pre_psi && !na_side.pre_dpsi) na_side.pre_psi = nullptr;
+          p->b_phase = 1;
+          if (df || dg) launch_B_any(p, nd, na_side, false);
+          p->b_phase = 3;
+          rec(p, 10);
+          p->stream = st;
+        }
+        if (!(cf & C_OMIT_FFT)) fft_forward(p);
+        rec(p, 3);
+        if (p->side_nodes) {
+          halo(p, false);
+          rec(p, 6);
+          PNB_CUDA(cudaStreamWaitEvent(st, p->ev[10], 0));
+          p->b_phase = 2;
+          if (df || dg) launch_B_any(p, nd, na_side, false);
+          p->b_phase = 3;
+          rec(p, 7);
+        } else if (conv) {
+          node_setup();
+          halo(p, false);
+          rec(p, 6);
+          NodeArgs<R> na = base_args();
+          na.f = df; na.grad = dg;
+          if (na.grad && na.pre_psi && !na.pre_dpsi) na.pre_psi = nullptr;   // no dpsi table: evaluate on the fly
+          if (df || dg) launch_B_any(p, nd, na, false);
+          rec(p, 7);
+        } else { rec(p, 4); rec(p, 5); rec(p, 6); rec(p, 7); }
+      } else {
+        // ik differentiation: 1 (f) + 3 (grad) passes of F and B (reference api-basic.c:100-167)
+        if ((cf & C_GRAD_F) && !(cf & C_OMIT_DECONV))
+          PNB_CUDA(cudaMemcpyAsync(p->d_g1_buffer, p->d_g1, sizeof(C) * nloc, cudaMemcpyDeviceToDevice, st));
+        rec(p, 3);
+        if (conv) node_setup(); else { rec(p, 4); rec(p, 5); }
+        if (cf & C_F) {
+          if (!(cf & C_OMIT_FFT)) fft_forward(p);
+          if (conv) { halo(p, false); NodeArgs<R> na = base_args(); na.f = df; launch_B_any(p, nd, na, false); }
+        }
+        if (cf & C_GRAD_F)
+          for (int dim = 0; dim < 3; dim++) {
+            if (!(cf & C_OMIT_DECONV)) run_ik(p, p->d_g1_buffer, p->d_g1, 0, dim);
+            if (!(cf & C_OMIT_FFT)) fft_forward(p);
+            if (conv) { halo(p, false); NodeArgs<R> na = base_args(); na.f = dg; na.f_stride = 3; na.f_off = dim; launch_B_any(p, nd, na, false); }
+          }
+        rec(p, 6); rec(p, 7);
+      }
+      if (pass) nd->swap_il();
     }
+    p->il_pass = 0;
     // ---- results back to the host where the user arrays live ----
     if (conv) {
       if (df && !is_device_ptr(nd->f)) PNB_CUDA(cudaMemcpyAsync(nd->f, df, sizeof(R) * NC * M, cudaMemcpyDeviceToHost, st));
@@ -1052,66 +1176,80 @@ template <class R> struct Core {
     const bool conv = !(cf & C_OMIT_CONV);
     const bool acc = (cf & C_ACCUMULATED) != 0;
     const size_t M = nd ? (size_t)nd->local_M : 0;
+    const int npass = (p->pnfft_flags & F_INTERLACED) ? 2 : 1;   // reference api-basic.c:367-374
+    if ((cf & C_HESSIAN_F) && !p->warned_hessian) {
+      fprintf(stderr, "pnfft-b200: PNFFT_COMPUTE_HESSIAN_F is not part of the accelerated path; hessian_f is ignored\n");
+      p->warned_hessian = true;
+    }
     rec(p, 0);
     R *df = nullptr, *dg = nullptr;
     const R *dx = nullptr;
     if (conv) {
       if (cf & C_F) df = dev_in(p, nd->f, &nd->d_f, &nd->cap_f, (size_t)NC * M, true);
       if (cf & C_GRAD_F) dg = dev_in(p, nd->grad_f, &nd->d_grad_f, &nd->cap_grad, (size_t)3 * NC * M, true);
-      dx = prepare_nodes(p, nd, 1, 2);
-    } else { rec(p, 1); rec(p, 2); }
-    auto base_args = [&]() {
-      NodeArgs<R> na;
-      na.x = dx; na.perm = nd->d_perm; na.M = (int)M; na.f = nullptr; na.f_stride = 1; na.f_off = 0; na.grad = nullptr;
-      na.accumulate = 0;
-      const bool use_pre = (nd->precompute_flags & P_PRE_PSI) && nd->d_pre_psi;
-      na.pre_psi = use_pre ? nd->d_pre_psi : nullptr;
-      na.pre_dpsi = use_pre ? nd->d_pre_dpsi : nullptr;
-      return na;
-    };
-    auto spread = [&](R *fptr, long long stride, long long off, R *gptr, int e_zero, int e_b, int e_h) {
-      PNB_CUDA(cudaMemsetAsync(p->d_grid, 0, p->grid_bytes, st));   // reference ndft-parallel.c:2629-2635
-      if (e_zero >= 0) rec(p, e_zero);
-      NodeArgs<R> na = base_args();
-      na.f = fptr; na.f_stride = stride; na.f_off = off; na.grad = gptr;
-      if (na.grad && na.pre_psi && !na.pre_dpsi) na.pre_psi = nullptr;
-      if (fptr || gptr) launch_B_any(p, nd, na, true);
-      if (e_b >= 0) rec(p, e_b);
-      halo(p, true);
-      if (e_h >= 0) rec(p, e_h);
-    };
-
-    if (!ik) {
-      if (conv) spread(df, 1, 0, dg, 3, 4, 5); else { rec(p, 3); rec(p, 4); rec(p, 5); }
-      if (!(cf & C_OMIT_FFT)) fft_backward(p);
-      rec(p, 6);
-    } else {
-      rec(p, 3); rec(p, 4); rec(p, 5);
-      if (!(cf & C_OMIT_DECONV)) PNB_CUDA(cudaMemsetAsync(p->d_g1_buffer, 0, sizeof(C) * nloc, st));
-      if (cf & C_F) {
-        if (conv) spread(df, 1, 0, nullptr, -1, -1, -1);
-        if (!(cf & C_OMIT_FFT)) fft_backward(p);
-        run_ik(p, p->d_g1, p->d_g1_buffer, 2, 0);
-      }
-      if (cf & C_GRAD_F)
-        for (int dim = 0; dim < 3; dim++) {
-          if (conv) spread(dg, 3, dim, nullptr, -1, -1, -1);
-          if (!(cf & C_OMIT_FFT)) fft_backward(p);
-          if (!(cf & C_OMIT_DECONV)) run_ik(p, p->d_g1, p->d_g1_buffer, 1, dim);
-        }
-      PNB_CUDA(cudaMemcpyAsync(p->d_g1, p->d_g1_buffer, sizeof(C) * nloc, cudaMemcpyDeviceToDevice, st));
-      rec(p, 6);
     }
-    // ---- D^H: f_hat (+)= g1 * 1/phi_hat ----
+    // ---- f_hat accumulator on the device: zeroed (PNX(zero_f_hat), api-basic.c:355) or the caller's values ----
+    C *fh = nullptr;
+    bool fh_dev = false;
     if (p->f_hat) {
-      const bool dev = is_device_ptr(p->f_hat);
-      C *fh = dev ? p->f_hat : p->d_f_hat;
-      if (!acc) PNB_CUDA(cudaMemsetAsync(fh, 0, sizeof(C) * nloc, st));      // PNX(zero_f_hat), api-basic.c:355
-      else if (!dev) PNB_CUDA(cudaMemcpyAsync(fh, p->f_hat, sizeof(C) * nloc, cudaMemcpyHostToDevice, st));
-      if (!(cf & C_OMIT_DECONV)) run_deconv(p, nullptr, fh, true);
-      rec(p, 7);
-      if (!dev) PNB_CUDA(cudaMemcpyAsync(p->f_hat, fh, sizeof(C) * nloc, cudaMemcpyDeviceToHost, st));
-    } else rec(p, 7);
+      fh_dev = is_device_ptr(p->f_hat);
+      fh = fh_dev ? p->f_hat : p->d_f_hat;
+      if (!acc) PNB_CUDA(cudaMemsetAsync(fh, 0, sizeof(C) * nloc, st));
+      else if (!fh_dev) PNB_CUDA(cudaMemcpyAsync(fh, p->f_hat, sizeof(C) * nloc, cudaMemcpyHostToDevice, st));
+    }
+    for (int pass = 0; pass < npass; pass++) {
+      p->il_pass = pass;
+      if (pass) nd->swap_il();
+      if (conv) dx = prepare_nodes(p, nd, 1, 2, dx); else { rec(p, 1); rec(p, 2); }
+      auto base_args = [&]() {
+        NodeArgs<R> na;
+        na.x = dx; na.perm = nd->d_perm; na.M = (int)M; na.f = nullptr; na.f_stride = 1; na.f_off = 0; na.grad = nullptr;
+        na.accumulate = 0;
+        const bool use_pre = (nd->precompute_flags & P_PRE_PSI) && nd->d_pre_psi;
+        na.pre_psi = use_pre ? nd->d_pre_psi : nullptr;
+        na.pre_dpsi = use_pre ? nd->d_pre_dpsi : nullptr;
+        return na;
+      };
+      auto spread = [&](R *fptr, long long stride, long long off, R *gptr, int e_zero, int e_b, int e_h) {
+        PNB_CUDA(cudaMemsetAsync(p->d_grid, 0, p->grid_bytes, st));   // reference ndft-parallel.c:2629-2635
+        if (e_zero >= 0) rec(p, e_zero);
+        NodeArgs<R> na = base_args();
+        na.f = fptr; na.f_stride = stride; na.f_off = off; na.grad = gptr;
+        if (na.grad && na.pre_psi && !na.pre_dpsi) na.pre_psi = nullptr;
+        if (fptr || gptr) launch_B_any(p, nd, na, true);
+        if (e_b >= 0) rec(p, e_b);
+        halo(p, true);
+        if (e_h >= 0) rec(p, e_h);
+      };
+
+      if (!ik) {
+        if (conv) spread(df, 1, 0, dg, 3, 4, 5); else { rec(p, 3); rec(p, 4); rec(p, 5); }
+        if (!(cf & C_OMIT_FFT)) fft_backward(p);
+        rec(p, 6);
+      } else {
+        rec(p, 3); rec(p, 4); rec(p, 5);
+        if (!(cf & C_OMIT_DECONV)) PNB_CUDA(cudaMemsetAsync(p->d_g1_buffer, 0, sizeof(C) * nloc, st));
+        if (cf & C_F) {
+          if (conv) spread(df, 1, 0, nullptr, -1, -1, -1);
+          if (!(cf & C_OMIT_FFT)) fft_backward(p);
+          run_ik(p, p->d_g1, p->d_g1_buffer, 2, 0);
+        }
+        if (cf & C_GRAD_F)
+          for (int dim = 0; dim < 3; dim++) {
+            if (conv) spread(dg, 3, dim, nullptr, -1, -1, -1);
+            if (!(cf & C_OMIT_FFT)) fft_backward(p);
+            if (!(cf & C_OMIT_DECONV)) run_ik(p, p->d_g1, p->d_g1_buffer, 1, dim);
+          }
+        PNB_CUDA(cudaMemcpyAsync(p->d_g1, p->d_g1_buffer, sizeof(C) * nloc, cudaMemcpyDeviceToDevice, st));
+        rec(p, 6);
+      }
+      // ---- D^H: f_hat += g1 * 1/phi_hat ----
+      if (fh && !(cf & C_OMIT_DECONV)) run_deconv(p, nullptr, fh, true);
+      if (pass) nd->swap_il();
+    }
+    p->il_pass = 0;
+    rec(p, 7);
+    if (fh && !fh_dev) PNB_CUDA(cudaMemcpyAsync(p->f_hat, fh, sizeof(C) * nloc, cudaMemcpyDeviceToHost, st));
     rec(p, 8);
     PNB_CUDA(cudaStreamSynchronize(st));
     finish_timers(p, true, ik);

@@ -115,7 +115,7 @@ inline PipeGeom build_pipe(const Layout &L, const Mesh &M) {
   G.L4_elems = (long long)lno0 * lno1 * G.n2z;
 
   // ---- stage 1: g1 -> L1, exchange inside the p0 group (ranks (a', b)) ----
-  {
+  if (!L.transposed) {
     Stage &S = G.st[0];
     S.src_elems = (long long)lN0 * lN1 * Zc;
     S.dst_elems = G.L1_elems;
@@ -146,7 +146,7 @@ inline PipeGeom build_pipe(const Layout &L, const Mesh &M) {
     S.zero_len = (long long)(lo - hi) * G.S1;
   }
   // ---- stage 2: L1 -> L3, exchange between all ranks ----
-  {
+  if (!L.transposed) {
     Stage &S = G.st[1];
     S.src_elems = G.L1_elems;
     S.dst_elems = G.L3_elems;
@@ -187,6 +187,72 @@ inline PipeGeom build_pipe(const Layout &L, const Mesh &M) {
     const INT hi = L.N[1] - L.N[1] / 2, lo = L.n[1] - L.N[1] / 2;
     S.zero_off = (long long)hi * G.S3;
     S.zero_len = (long long)(lo - hi) * G.S3;
+  }
+  // ---- PNFFT_TRANSPOSED_F_HAT (reference kernel/matrix_D.c:331-341, ndft-parallel.c:965-978): the block already holds
+  // every k0 of its (k1, k2) range, memory order [k1][k2][k0], so the x pass needs NO exchange and the y pass only one
+  // inside the p0 group:
+  //   g1 [N1/p0][Z/p1][N0]  --local-->  L1 [n0][N1/p0][Z/p1]  --E2(p0 group)-->  L3 [n1][no0/p0][Z/p1]
+  if (L.transposed) {
+    const INT lN1t = L.local_N[1], lN2t = L.local_N[2];
+    Split SYt(L.N[1], p0);
+    G.S1 = (long long)lN1t * lN2t;
+    G.L1_elems = (long long)L.n[0] * G.S1;
+    {
+      Stage &S = G.st[0];
+      S.src_elems = (long long)L.N[0] * G.S1;
+      S.dst_elems = G.L1_elems;
+      Transfer T;
+      T.peer = M.rank;
+      T.send_sign = true;
+      T.send_elems = T.recv_elems = S.src_elems;
+      if (S.src_elems > 0)
+        wrap_segments(-(L.N[0] / 2), L.N[0], L.n[0], [&](INT ib, INT cnt, INT pos) {
+          BoxMap bm;      // a side: L1 (destination), c side: g1 (source)
+          bm.dims[0] = cnt; bm.dims[1] = lN1t; bm.dims[2] = lN2t;
+          bm.a_off = (long long)pos * G.S1; bm.a_str[0] = G.S1; bm.a_str[1] = lN2t; bm.a_str[2] = 1;
+          bm.c_off = ib; bm.c_str[0] = 1; bm.c_str[1] = (long long)lN2t * L.N[0]; bm.c_str[2] = L.N[0];
+          bm.parity = pmod2((long long)(ib - L.N[0] / 2) + L.local_N_start[1] + L.local_N_start[2]);
+          T.self_maps.push_back(bm);
+        });
+      S.tr.push_back(T);
+      const INT hi = L.N[0] - L.N[0] / 2, lo = L.n[0] - L.N[0] / 2;
+      S.zero_off = (long long)hi * G.S1;
+      S.zero_len = (long long)(lo - hi) * G.S1;
+    }
+    {
+      Stage &S = G.st[1];
+      S.src_elems = G.L1_elems;
+      S.dst_elems = G.L3_elems;
+      for (int ap = 0; ap < p0; ap++) {
+        Transfer T;
+        T.peer = M.rank_of(ap, b);
+        {  // send to a': rows x in XO[a'] (storage offset o_off), my k1 block, my z block
+          const INT xl = XO.len[(size_t)ap];
+          T.send_elems = (long long)xl * lN1t * lN2t;
+          if (T.send_elems > 0)
+            T.send_maps.push_back(dense_map(xl, lN1t, lN2t, lN1t, lN2t, XO.start[(size_t)ap] + L.o_off[0], 0, 0, 0));
+        }
+        {  // receive from a': my x rows, its k1 block, my z block -> position k1 mod n1
+          const INT yl = SYt.len[(size_t)ap], ys = SYt.start[(size_t)ap] - L.N[1] / 2;
+          T.recv_elems = (long long)lno0 * yl * z1len;
+          if (T.recv_elems > 0)
+            wrap_segments(ys, yl, L.n[1], [&](INT ib, INT cnt, INT pos) {
+              BoxMap bm;
+              bm.dims[0] = lno0; bm.dims[1] = cnt; bm.dims[2] = z1len;
+              bm.a_str[0] = z1len; bm.a_str[1] = (long long)lno0 * z1len; bm.a_str[2] = 1;
+              bm.a_off = (long long)pos * lno0 * z1len;
+              bm.c_str[0] = (long long)yl * z1len; bm.c_str[1] = z1len; bm.c_str[2] = 1;
+              bm.c_off = (long long)ib * z1len;
+              bm.parity = 0;
+              T.recv_maps.push_back(bm);
+            });
+        }
+        S.tr.push_back(T);
+      }
+      const INT hi = L.N[1] - L.N[1] / 2, lo = L.n[1] - L.N[1] / 2;
+      S.zero_off = (long long)hi * G.S3;
+      S.zero_len = (long long)(lo - hi) * G.S3;
+    }
   }
   // ---- stage 3: L3 -> L4, exchange inside the p1 group (ranks (a, b')) ----
   {
@@ -239,6 +305,7 @@ inline PipeGeom build_pipe(const Layout &L, const Mesh &M) {
   for (int s = 0; s < 3; s++) {
     Stage &S = G.st[s];
     for (auto &T : S.tr) {
+      if (!T.self_maps.empty()) continue;     // built directly (transposed f_hat, stage 1)
       if (no_self || T.peer != M.rank || T.send_maps.size() != 1 || T.recv_maps.empty() || T.send_elems != T.recv_elems) continue;
       std::vector<BoxMap> sm;
       bool ok = true;

@@ -2,13 +2,10 @@
 // scatter (adjoint).  Replaces reference kernel/ndft-parallel.c:2521-3009 (trafo_B_ad, adjoint_B_ad and
 // their per-node loops) and kernel/assign.c:478-1130 (the (2m+1)^3 inner loops).
 //
-// Tiled kernels (default): nodes are binned by T0 x T1 x T2 tiles of the rank's oversampled-grid block.
-// One CTA handles one (tile, node-chunk) work item: the tile plus its 2m halo is brought into shared
-// memory with ONE TMA tensor load (gather), or accumulated in shared memory and written back with ONE
-// TMA reduce-add (scatter: atomic-free inside the tile, the only contended traffic is the bulk
-// reduction at L2).  Per node the three 1-d window factors are evaluated once per axis; the x axis is
-// contracted in registers (psi_x taps live in registers), lanes sweep the (y,z) face of the stencil.
-// Generic kernels (variant 1): run-time m, straight from global memory, atomics for the scatter.
+// Shared pieces of every kernel family: node projection (grid index, interlacing shift), window evaluation by one warp,
+// binning into (column tile, z sub-chunk, x offset) bins, the integer parity probes, and the generic kernels
+// (kernel_variant 1: one warp per node, run-time m, padded grid in global memory, atomics for the scatter) that serve
+// every cutoff the z-marching kernels (zmarch.cuh, zmarch2.cuh) are not instantiated for.
 #pragma once
 #include <cuda.h>
 #include <cub/cub.cuh>
@@ -33,15 +30,27 @@ template <class R> __device__ __forceinline__ R warp_sum(R v) {
   return v;
 }
 
-// floor(n*x) with a single rounding of the product, exactly like the reference
-// (kernel/ndft-parallel.c:2171: pnfft_floor(n[t]*x[t]))
+// One axis of a node: nx = n x and fl = floor(n x) with a single rounding of the product, exactly like the reference
+// (kernel/ndft-parallel.c:2171: pnfft_floor(n[t]*x[t])), and the interior cell fl - local_no_start.
+// Second pass of an interlaced plan (reference :2732-2753): x += 0.5/n first; the cell comes from the shifted, NOT yet
+// folded coordinate (it may be one past the block: that is the extra ghost cell above), then x >= 0.5 is folded to
+// x - 1 with fl - n, and the window arguments fl - n x use the folded pair.
+template <class R> __device__ __forceinline__ void node_axis(const GridGeom<R> &g, R x, int t, R *nx, R *fl, int *cell) {
+  if (g.il_on) x = (R)((double)x + g.il[t]);
+  R v = mul_rn(g.n[t], x);
+  R f = m_floor(v);
+  *cell = (int)f - g.los[t];   // interior cell == index of tap 0 in the padded array
+  if (g.il_on && x >= (R)0.5) { x -= (R)1; f -= g.n[t]; v = mul_rn(g.n[t], x); }
+  *nx = v; *fl = f;
+}
 template <class R> __device__ __forceinline__ void project_node(const GridGeom<R> &g, const R *x3, R *nx, R *fl, int *cell) {
 #pragma unroll
-  for (int t = 0; t < 3; t++) {
-    nx[t] = mul_rn(g.n[t], x3[t]);
-    fl[t] = m_floor(nx[t]);
-    cell[t] = (int)fl[t] - g.los[t];   // interior cell == index of tap 0 in the padded array
-  }
+  for (int t = 0; t < 3; t++) node_axis(g, x3[t], t, &nx[t], &fl[t], &cell[t]);
+}
+// the 0.5 of an interlaced plan rides on the x-axis factors (exact: a power of two)
+template <class R> __device__ __forceinline__ void warp_scale_x(const GridGeom<R> &g, int lane, R *psi_s, R *dpsi_s, bool want_d) {
+  if (g.wscale == (R)1) return;
+  for (int v = lane; v < g.cutoff; v += 32) { psi_s[v] *= g.wscale; if (want_d) dpsi_s[v] *= g.wscale; }
 }
 
 // 3*(2m+1) window values (and AD-gradient weights) of one node, computed by one warp into psi_s/dpsi_s.
@@ -111,7 +120,6 @@ struct TileGeom {
   int T[3];        // tile extent in cells
   int nt[3];       // tiles per axis
   int ntiles;
-  int chunk;       // max nodes per work item
   int family;      // kernel family the geometry was made for (Core::kernel_family)
   int sub;         // bins per tile: 1, or T[0] when nodes are also ordered by their x offset inside the tile (z-march v2)
 };
@@ -125,7 +133,7 @@ __global__ void k_bin_nodes(GridGeom<R> g, TileGeom tg, const R *__restrict__ x,
   int cell[3];
   project_node(g, xs, nx, fl, cell);
   int tile = tg.ntiles * tg.sub;  // nodes outside the rank's block (undefined behaviour in the reference) are skipped
-  if (cell[0] >= 0 && cell[0] < g.lno[0] && cell[1] >= 0 && cell[1] < g.lno[1] && cell[2] >= 0 && cell[2] < g.lno[2]) {
+  if (cell[0] >= 0 && cell[0] < g.lno[0] + g.il_on && cell[1] >= 0 && cell[1] < g.lno[1] + g.il_on && cell[2] >= 0 && cell[2] < g.lno[2] + g.il_on) {
     const int c0 = cell[0] / tg.T[0];
     tile = (c0 * tg.nt[1] + cell[1] / tg.T[1]) * tg.nt[2] + cell[2] / tg.T[2];
     if (tg.sub > 1) tile = tile * tg.sub + (cell[0] - c0 * tg.T[0]);
@@ -135,31 +143,28 @@ __global__ void k_bin_nodes(GridGeom<R> g, TileGeom tg, const R *__restrict__ x,
   atomicAdd(&tile_count[tile], 1);
 }
 
+// 64-bit content hash of a device array (order sensitive: every word is mixed with its position before the sum), used to
+// tell whether device-resident node coordinates changed since they were binned (Core::prepare_nodes)
+template <class R> __global__ void k_hash_words(const R *__restrict__ v, long long n, unsigned long long *__restrict__ out) {
+  unsigned long long acc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long w;
+    if (sizeof(R) == 8) w = (unsigned long long)__double_as_longlong((double)v[i]);
+    else w = (unsigned long long)__float_as_uint((float)v[i]);
+    unsigned long long z = w + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);      // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    acc += z ^ (z >> 31);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // largest node count of a column tile (z-march v2 load-balance hint): bins of one column are contiguous in tile_start
 static __global__ void k_max_column(const int *__restrict__ tile_start, int ncol, int bins_per_col, int *__restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncol) return;
   atomicMax(out, tile_start[(size_t)(c + 1) * bins_per_col] - tile_start[(size_t)c * bins_per_col]);
-}
-
-static __global__ void k_items_per_tile(TileGeom tg, const int *__restrict__ tile_count, int *__restrict__ n_items) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t > tg.ntiles) return;
-  n_items[t] = t < tg.ntiles ? (tile_count[t] + tg.chunk - 1) / tg.chunk : 0;
-}
-
-static __global__ void k_fill_items(TileGeom tg, const int *__restrict__ tile_count, const int *__restrict__ tile_start,
-                             const int *__restrict__ item_start, int *__restrict__ items, int *__restrict__ nitems) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= tg.ntiles) return;
-  const int cnt = tile_count[t], s = tile_start[t];
-  int it = item_start[t];
-  for (int b = 0; b < cnt; b += tg.chunk, it++) {
-    items[3 * it] = t;
-    items[3 * it + 1] = s + b;
-    items[3 * it + 2] = s + min(cnt, b + tg.chunk);
-  }
-  if (t == tg.ntiles - 1) *nitems = it;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(256) k_gather_generic(GridGeom<R> g, const R *
   int cell[3];
   project_node(g, xs, nx, fl, cell);
   bool inside = true;
-  for (int t = 0; t < 3; t++) inside = inside && cell[t] >= 0 && cell[t] < g.lno[t];
+  for (int t = 0; t < 3; t++) inside = inside && cell[t] >= 0 && cell[t] < g.lno[t] + g.il_on;
   if (na.pre_psi) {
     for (int v = lane; v < 3 * c; v += 32) {
       psi_s[v] = na.pre_psi[(size_t)p * 3 * c + v];
@@ -264,6 +269,8 @@ __global__ void __launch_bounds__(256) k_gather_generic(GridGeom<R> g, const R *
     if (g.poly) warp_window_eval_poly(g, g.poly, nx, fl, lane, psi_s, dpsi_s, want_d);
     else warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, want_d);
   }
+  __syncwarp();
+  warp_scale_x(g, lane, psi_s, dpsi_s, want_d);
   __syncwarp();
   R af[2] = {0, 0}, a0[2] = {0, 0}, a1[2] = {0, 0}, a2[2] = {0, 0};
   if (inside) {
@@ -328,7 +335,7 @@ __global__ void __launch_bounds__(256) k_scatter_generic(GridGeom<R> g, R *__res
   R xs[3] = {na.x[3 * (size_t)j], na.x[3 * (size_t)j + 1], na.x[3 * (size_t)j + 2]}, nx[3], fl[3];
   int cell[3];
   project_node(g, xs, nx, fl, cell);
-  for (int t = 0; t < 3; t++) if (cell[t] < 0 || cell[t] >= g.lno[t]) return;
+  for (int t = 0; t < 3; t++) if (cell[t] < 0 || cell[t] >= g.lno[t] + g.il_on) return;
   if (na.pre_psi) {
     for (int v = lane; v < 3 * c; v += 32) {
       psi_s[v] = na.pre_psi[(size_t)p * 3 * c + v];
@@ -338,6 +345,8 @@ __global__ void __launch_bounds__(256) k_scatter_generic(GridGeom<R> g, R *__res
     if (g.poly) warp_window_eval_poly(g, g.poly, nx, fl, lane, psi_s, dpsi_s, want_d);
     else warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, want_d);
   }
+  __syncwarp();
+  warp_scale_x(g, lane, psi_s, dpsi_s, want_d);
   __syncwarp();
   constexpr int NC = CPLX ? 2 : 1;
   R fv[2] = {0, 0}, g0[2] = {0, 0}, g1[2] = {0, 0}, g2[2] = {0, 0};
@@ -372,33 +381,8 @@ __global__ void __launch_bounds__(256) k_scatter_generic(GridGeom<R> g, R *__res
 }
 
 // ------------------------------------------------------------------------------------------------
-// tiled kernels
+// mbarrier / TMA helpers and cell arithmetic shared by the z-marching kernels (zmarch.cuh, zmarch2.cuh)
 // ------------------------------------------------------------------------------------------------
-template <int M_, int CELLB> struct TileCfg {
-  static constexpr int C = 2 * M_ + 1;
-  // tile extents (cells); chosen so that (T+2m)^3-ish box of 16-byte cells stays below ~200 kB
-  static constexpr int T0 = (M_ <= 6) ? 8 : 6;
-  static constexpr int T1 = (M_ <= 6) ? 8 : 6;
-  static constexpr int T2 = (M_ <= 6) ? 16 : 8;
-  static constexpr int BX = T0 + 2 * M_, BY = T1 + 2 * M_;
-  // z pitch of the shared-memory box: lanes sweep the (y,z) face in flattened order q = l1*C + l2; with
-  // BZ == C (mod 128/CELLB) the address of lane q is == q (mod one 128-byte wavefront) => conflict free.
-  // 8- and 4-byte cells additionally need BZ*CELLB % 16 == 0 (TMA), which costs a 2-way conflict at row ends.
-  static constexpr int W = 128 / CELLB;
-  static constexpr int BZ0 = T2 + 2 * M_;
-  static constexpr int ALIGN = (CELLB >= 16) ? 1 : 16 / CELLB;
-  static constexpr int bz() {
-    int z = BZ0;
-    if (ALIGN == 1) { while (z % W != C % W) z++; }
-    else { while (z % ALIGN != 0 || ((z % W) != ((C + 1) % W) && (z % W) != ((C + W - 1) % W))) z++; }
-    return z;
-  }
-  static constexpr int BZ = bz();
-  static constexpr int BOX_CELLS = BX * BY * BZ;
-  static constexpr int BOX_BYTES = BOX_CELLS * CELLB;
-  static constexpr int NCH = (C * C + 31) / 32;
-};
-
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -459,266 +443,6 @@ __device__ __forceinline__ float2 scale_cell(float w, float2 v) { return make_fl
 __device__ __forceinline__ double scale_cell(double w, double v) { return w * v; }
 __device__ __forceinline__ float scale_cell(float w, float v) { return w * v; }
 
-constexpr int kGatherWarps = 16;
 constexpr int kMaxPolyCoef = 25;   // polynomial degree <= 24
-
-template <class R, bool CPLX, int M_, bool GRAD>
-__global__ void __launch_bounds__(kGatherWarps * 32, 1)
-k_gather_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeom tg, const R *__restrict__ /*unused*/,
-               NodeArgs<R> na, const int *__restrict__ items, const int *__restrict__ nitems) {
-  typedef typename CellT<R, CPLX>::type Cell;
-  typedef TileCfg<M_, (int)sizeof(Cell)> Cfg;
-  constexpr int C = Cfg::C, BY = Cfg::BY, BZ = Cfg::BZ, NCH = Cfg::NCH;
-  constexpr int NCOMP = CPLX ? 2 : 1;
-  if ((int)blockIdx.x >= *nitems) return;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  Cell *box = reinterpret_cast<Cell *>(smem_raw);
-  R *scratch = reinterpret_cast<R *>(smem_raw + Cfg::BOX_BYTES);
-  R *poly_s = scratch + kGatherWarps * 6 * C;
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(poly_s + 2 * kMaxPolyCoef * 3 * C);
-
-  const int tile = items[3 * blockIdx.x], begin = items[3 * blockIdx.x + 1], end = items[3 * blockIdx.x + 2];
-  const int tz = tile % tg.nt[2], ty = (tile / tg.nt[2]) % tg.nt[1], tx = tile / (tg.nt[2] * tg.nt[1]);
-  const int o0 = tx * Cfg::T0, o1 = ty * Cfg::T1, o2 = tz * Cfg::T2;
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar, (unsigned)Cfg::BOX_BYTES);
-    tma_load_3d(box, &tmap, o2 * NCOMP, o1, o0, bar);
-  }
-  if (g.poly) for (int i = threadIdx.x; i < 2 * (g.poly_deg + 1) * 3 * C; i += kGatherWarps * 32) poly_s[i] = g.poly[i];
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  R *psi_s = scratch + warp * 6 * C, *dpsi_s = psi_s + 3 * C;
-
-  // lane -> (l1,l2) of the stencil's (y,z) face, per chunk; node independent
-  int off[NCH], l1s[NCH], l2s[NCH];
-#pragma unroll
-  for (int ch = 0; ch < NCH; ch++) {
-    int q = ch * 32 + lane;
-    if (q >= C * C) q = C * C - 1;
-    l1s[ch] = q / C; l2s[ch] = q - l1s[ch] * C;
-    off[ch] = l1s[ch] * BZ + l2s[ch];
-  }
-
-  bool waited = false;
-  for (int p = begin + warp; p < end; p += kGatherWarps) {
-    const int j = na.perm[p];
-    R xs[3] = {na.x[3 * (size_t)j], na.x[3 * (size_t)j + 1], na.x[3 * (size_t)j + 2]}, nx[3], fl[3];
-    int cell[3];
-    project_node(g, xs, nx, fl, cell);
-    __syncwarp();
-    if (na.pre_psi) {
-      for (int v = lane; v < 3 * C; v += 32) {
-        psi_s[v] = na.pre_psi[(size_t)p * 3 * C + v];
-        if (GRAD) dpsi_s[v] = na.pre_dpsi[(size_t)p * 3 * C + v];
-      }
-    } else {
-      if (g.poly) warp_window_eval_poly(g, poly_s, nx, fl, lane, psi_s, dpsi_s, GRAD);
-      else warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, GRAD);
-    }
-    __syncwarp();
-    if (!waited) { mbar_wait(bar, 0); waited = true; }
-
-    R w0[C], dw0[GRAD ? C : 1];
-#pragma unroll
-    for (int l0 = 0; l0 < C; l0++) { w0[l0] = psi_s[l0]; if (GRAD) dw0[l0] = dpsi_s[l0]; }
-
-    const int base = ((cell[0] - o0) * BY + (cell[1] - o1)) * BZ + (cell[2] - o2);
-    Cell af, a0, a1, a2;
-    zero_cell(af); zero_cell(a0); zero_cell(a1); zero_cell(a2);
-#pragma unroll
-    for (int ch = 0; ch < NCH; ch++) {
-      const bool active = (ch * 32 + lane) < C * C;
-      const Cell *ptr = box + base + off[ch];
-      Cell s, d;
-      zero_cell(s); zero_cell(d);
-#pragma unroll
-      for (int l0 = 0; l0 < C; l0++) {
-        const Cell v = ptr[l0 * BY * BZ];
-        fma_cell(s, w0[l0], v);
-        if (GRAD) fma_cell(d, dw0[l0], v);
-      }
-      const R w1 = psi_s[C + l1s[ch]], w2 = psi_s[2 * C + l2s[ch]];
-      const R w12 = active ? w1 * w2 : (R)0;
-      fma_cell(af, w12, s);
-      if (GRAD) {
-        const R dw1 = dpsi_s[C + l1s[ch]], dw2 = dpsi_s[2 * C + l2s[ch]];
-        fma_cell(a0, w12, d);
-        fma_cell(a1, active ? dw1 * w2 : (R)0, s);
-        fma_cell(a2, active ? w1 * dw2 : (R)0, s);
-      }
-    }
-    af = cell_sum(af);
-    if (GRAD) { a0 = cell_sum(a0); a1 = cell_sum(a1); a2 = cell_sum(a2); }
-    if (lane == 0) {
-      if (na.f) store_out(na.f + ((size_t)j * na.f_stride + na.f_off) * NCOMP, af, na.accumulate);
-      if (GRAD) {
-        R *o = na.grad + (size_t)j * 3 * NCOMP;
-        store_out(o, a0, na.accumulate);
-        store_out(o + NCOMP, a1, na.accumulate);
-        store_out(o + 2 * NCOMP, a2, na.accumulate);
-      }
-    }
-  }
-  if (!waited) mbar_wait(bar, 0);   // never leave with the bulk copy in flight
-}
-
-// scatter: C warps, warp w owns the box planes X with X == w (mod C); every node touches exactly one
-// owned plane per warp, so the read-modify-writes of different warps never meet.
-template <int M_> struct ScatterCfg { static constexpr int NB = (M_ <= 6) ? 32 : 16; };
-
-template <class R, bool CPLX, int M_, bool GRAD>
-__global__ void __launch_bounds__((2 * M_ + 1) * 32, 1)
-k_scatter_tiled(const __grid_constant__ CUtensorMap tmap, GridGeom<R> g, TileGeom tg, NodeArgs<R> na,
-                const int *__restrict__ items, const int *__restrict__ nitems) {
-  typedef typename CellT<R, CPLX>::type Cell;
-  typedef TileCfg<M_, (int)sizeof(Cell)> Cfg;
-  constexpr int C = Cfg::C, BY = Cfg::BY, BZ = Cfg::BZ, NCH = Cfg::NCH;
-  constexpr int NCOMP = CPLX ? 2 : 1;
-  constexpr int NT = C * 32;
-  constexpr int NB = ScatterCfg<M_>::NB;
-  constexpr int WPN = GRAD ? 6 * C : 3 * C;   // weights per node
-  if ((int)blockIdx.x >= *nitems) return;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  Cell *box = reinterpret_cast<Cell *>(smem_raw);
-  R *wts = reinterpret_cast<R *>(smem_raw + Cfg::BOX_BYTES);           // [NB][WPN]
-  Cell *vals = reinterpret_cast<Cell *>(wts + NB * WPN);                 // [NB][4]: f, g0, g1, g2
-  int *hdr = reinterpret_cast<int *>(vals + NB * 4);                     // [NB][2]: box offset of tap (0,0,0); ux
-  R *poly_s = reinterpret_cast<R *>(hdr + NB * 2);
-
-  const int tile = items[3 * blockIdx.x], begin = items[3 * blockIdx.x + 1], end = items[3 * blockIdx.x + 2];
-  const int tz = tile % tg.nt[2], ty = (tile / tg.nt[2]) % tg.nt[1], tx = tile / (tg.nt[2] * tg.nt[1]);
-  const int o0 = tx * Cfg::T0, o1 = ty * Cfg::T1, o2 = tz * Cfg::T2;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  {
-    Cell z; zero_cell(z);
-    for (int i = threadIdx.x; i < Cfg::BOX_CELLS; i += NT) box[i] = z;
-    if (g.poly) for (int i = threadIdx.x; i < 2 * (g.poly_deg + 1) * 3 * C; i += NT) poly_s[i] = g.poly[i];
-  }
-  int off[NCH], l1s[NCH], l2s[NCH];
-#pragma unroll
-  for (int ch = 0; ch < NCH; ch++) {
-    int q = ch * 32 + lane;
-    if (q >= C * C) q = C * C - 1;
-    l1s[ch] = q / C; l2s[ch] = q - l1s[ch] * C;
-    off[ch] = l1s[ch] * BZ + l2s[ch];
-  }
-
-  for (int b0 = begin; b0 < end; b0 += NB) {
-    const int nb = min(NB, end - b0);
-    __syncthreads();   // previous batch fully consumed (and the zero fill is complete)
-    // ---- phase A: headers and window weights of the batch ----
-    if (threadIdx.x < nb) {
-      const int i = threadIdx.x, j = na.perm[b0 + i];
-      R xs[3] = {na.x[3 * (size_t)j], na.x[3 * (size_t)j + 1], na.x[3 * (size_t)j + 2]}, nx[3], fl[3];
-      int cell[3];
-      project_node(g, xs, nx, fl, cell);
-      hdr[2 * i] = ((cell[0] - o0) * BY + (cell[1] - o1)) * BZ + (cell[2] - o2);
-      hdr[2 * i + 1] = cell[0] - o0;
-      Cell z; zero_cell(z);
-      vals[4 * i] = na.f ? load_in(na.f + ((size_t)j * na.f_stride + na.f_off) * NCOMP, z) : z;
-      if (GRAD) {
-        const R *gp = na.grad + (size_t)j * 3 * NCOMP;
-        vals[4 * i + 1] = load_in(gp, z); vals[4 * i + 2] = load_in(gp + NCOMP, z); vals[4 * i + 3] = load_in(gp + 2 * NCOMP, z);
-      }
-    }
-    if (na.pre_psi) {
-      for (int v = threadIdx.x; v < nb * 3 * C; v += NT) {
-        const int i = v / (3 * C), r = v - i * 3 * C;
-        wts[i * WPN + r] = na.pre_psi[(size_t)(b0 + i) * 3 * C + r];
-        if (GRAD) wts[i * WPN + 3 * C + r] = na.pre_dpsi[(size_t)(b0 + i) * 3 * C + r];
-      }
-    } else if (g.kind == WIN_BSPLINE && !g.poly) {
-      for (int v = threadIdx.x; v < nb * 3; v += NT) {
-        const int i = v / 3, t = v - i * 3, j = na.perm[b0 + i];
-        const R nxv = mul_rn(g.n[t], na.x[3 * (size_t)j + t]);
-        const R frac = nxv - m_floor(nxv);
-        bspline_taps<R>(M_, frac, g.n[t], wts + i * WPN + t * C, GRAD ? wts + i * WPN + 3 * C + t * C : nullptr);
-      }
-    } else {
-      for (int v = threadIdx.x; v < nb * 3 * C; v += NT) {
-        const int i = v / (3 * C), r = v - i * 3 * C, t = r / C, s = r - t * C, j = na.perm[b0 + i];
-        const R nxv = mul_rn(g.n[t], na.x[3 * (size_t)j + t]);
-        const R flv = m_floor(nxv);
-        R psi, dpsi = (R)0;
-        const R fr = nxv - flv;
-        if (g.poly && fr != (R)0) {
-          const R u = (R)2 * fr - (R)1;
-          const R *a = poly_s + r;
-          const R *ad = a + (g.poly_deg + 1) * 3 * C;
-          psi = a[g.poly_deg * 3 * C];
-          if (GRAD) dpsi = ad[g.poly_deg * 3 * C];
-          for (int k = g.poly_deg - 1; k >= 0; k--) { if (GRAD) dpsi = dpsi * u + ad[k * 3 * C]; psi = psi * u + a[k * 3 * C]; }
-        } else if (g.kind == WIN_GAUSSIAN && g.fast_gauss) {
-          const R d = nxv - (flv - (R)M_);
-          const R e_sqr = m_exp(-(d * d) / g.b[t]), e_lin = m_exp((R)2 * d / g.b[t]);
-          R tmp = e_sqr;
-          for (int k = 0; k < s; k++) tmp *= e_lin;
-          psi = tmp * g.exp_const[t * C + s];
-          dpsi = (R)(-2.0) * g.n[t] / g.b[t] * (d - (R)s) * psi;
-        } else {
-          window_tap<R>(g.kind, flv - nxv - (R)M_ + (R)s, g.n[t], g.b[t], M_, GRAD, &psi, &dpsi);
-        }
-        wts[i * WPN + r] = psi;
-        if (GRAD) wts[i * WPN + 3 * C + r] = dpsi;
-      }
-    }
-    __syncthreads();
-    // ---- phase B: every warp adds its plane of every node ----
-    for (int i = 0; i < nb; i++) {
-      const R *w = wts + i * WPN;
-      const int ux = hdr[2 * i + 1];
-      int l0 = warp - ux % C;
-      if (l0 < 0) l0 += C;
-      Cell *plane = box + hdr[2 * i] + l0 * BY * BZ;
-      const R wx = w[l0];
-      Cell P = scale_cell(wx, vals[4 * i]), Q1, Q2;
-      if (GRAD) {
-        fma_cell(P, w[3 * C + l0], vals[4 * i + 1]);
-        Q1 = scale_cell(wx, vals[4 * i + 2]);
-        Q2 = scale_cell(wx, vals[4 * i + 3]);
-      }
-#pragma unroll
-      for (int ch = 0; ch < NCH; ch++) {
-        if ((ch * 32 + lane) < C * C) {
-          const R w1 = w[C + l1s[ch]], w2 = w[2 * C + l2s[ch]];
-          Cell v = plane[off[ch]];
-          fma_cell(v, w1 * w2, P);
-          if (GRAD) {
-            const R dw1 = w[4 * C + l1s[ch]], dw2 = w[5 * C + l2s[ch]];
-            fma_cell(v, dw1 * w2, Q1);
-            fma_cell(v, w1 * dw2, Q2);
-          }
-          plane[off[ch]] = v;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    tma_reduce_add_3d(box, &tmap, o2 * NCOMP, o1, o0);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  }
-}
-
-template <class R, bool CPLX, int M_, bool GRAD> struct TiledSmem {
-  typedef typename CellT<R, CPLX>::type Cell;
-  typedef TileCfg<M_, (int)sizeof(Cell)> Cfg;
-  static constexpr size_t poly = (size_t)2 * kMaxPolyCoef * 3 * Cfg::C * sizeof(R);   // psi and dpsi polynomials
-  static constexpr size_t gather = (size_t)Cfg::BOX_BYTES + (size_t)kGatherWarps * 6 * Cfg::C * sizeof(R) + poly + 16;
-  static constexpr int NB = ScatterCfg<M_>::NB;
-  static constexpr size_t scatter = (size_t)Cfg::BOX_BYTES + (size_t)NB * (GRAD ? 6 : 3) * Cfg::C * sizeof(R) +
-                                    (size_t)NB * 4 * sizeof(Cell) + (size_t)NB * 2 * sizeof(int) + poly + 16;
-  static_assert(gather <= 232448 && scatter <= 232448, "shared-memory budget of one CTA exceeded");
-};
 
 }  // namespace pnb

@@ -6,36 +6,66 @@
 
 namespace pnb {
 
-// g1[k] = f_hat[k] * c0[k0] c1[k1] c2[k2]   (overwrite; reference matrix_D.c:319-356 / :397-423)
+// All three kernels walk the local f_hat block in MEMORY order (axes A, B, C; C contiguous): k0, k1, k2 for the plain
+// layout, k1, k2, k0 for PNFFT_TRANSPOSED_F_HAT (reference kernel/matrix_D.c:331-341) -- the host passes the tables,
+// the first frequencies and the FFT sizes in that order.
+struct FhatGeom {
+  int l[3];        // local extents, memory order
+  int s[3];        // first frequency index of each axis, memory order
+  double n[3];     // FFT sizes n_t, memory order (interlacing twiddle)
+  int il_sign;     // 0: none; +1 / -1: multiply by exp(+- pi i (kA/nA + kB/nB + kC/nC)) (reference matrix_D.c:282-317)
+};
+
+// exp(-sign pi i h), h accumulated outer -> inner exactly like the reference's loops (matrix_D.c:296-312)
+template <class R, class C> __device__ __forceinline__ C il_twiddle(const FhatGeom &fg, int iA, int iB, int iC) {
+  const R hA = (R)(fg.s[0] + iA) / (R)fg.n[0];
+  const R hB = hA + (R)(fg.s[1] + iB) / (R)fg.n[1];
+  const R hC = hB + (R)(fg.s[2] + iC) / (R)fg.n[2];
+  const R ang = (R)fg.il_sign * (R)3.14159265358979323846264338327950288 * hC;
+  C w; w.x = m_cos(ang); w.y = m_sin(ang);
+  return w;
+}
+
+// g1[k] = f_hat[k] * cA cB cC (* interlacing twiddle)   (overwrite; reference matrix_D.c:227-252, :319-356 / :397-423)
 template <class R, class C>
-__global__ void k_deconv_fwd(const C *__restrict__ f_hat, C *__restrict__ g1, const R *__restrict__ c0,
-                             const R *__restrict__ c1, const R *__restrict__ c2, int l0, int l1, int l2) {
-  const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i2 >= l2) return;
-  const R w2 = c2[i2];
-  for (int i0 = blockIdx.z; i0 < l0; i0 += gridDim.z)
-    for (int i1 = blockIdx.y; i1 < l1; i1 += gridDim.y) {
-      const size_t i = ((size_t)i0 * l1 + i1) * l2 + i2;
-      const R w = c0[i0] * c1[i1] * w2;
+__global__ void k_deconv_fwd(const C *__restrict__ f_hat, C *__restrict__ g1, const R *__restrict__ cA,
+                             const R *__restrict__ cB, const R *__restrict__ cC, FhatGeom fg) {
+  const int iC = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iC >= fg.l[2]) return;
+  const R wC = cC[iC];
+  for (int iA = blockIdx.z; iA < fg.l[0]; iA += gridDim.z)
+    for (int iB = blockIdx.y; iB < fg.l[1]; iB += gridDim.y) {
+      const size_t i = ((size_t)iA * fg.l[1] + iB) * fg.l[2] + iC;
+      const R w = cA[iA] * cB[iB] * wC;
       C v = f_hat[i];
       v.x *= w; v.y *= w;
+      if (fg.il_sign) {
+        const C t = il_twiddle<R, C>(fg, iA, iB, iC);
+        const R re = v.x * t.x - v.y * t.y, im = v.x * t.y + v.y * t.x;
+        v.x = re; v.y = im;
+      }
       g1[i] = v;
     }
 }
 
-// f_hat[k] += g1[k] * c0 c1 c2   (accumulate; reference matrix_D.c:358-395 / :425-451)
+// f_hat[k] += (g1[k] * interlacing twiddle) * cA cB cC   (accumulate; reference matrix_D.c:255-275, :358-395 / :425-451)
 template <class R, class C>
-__global__ void k_deconv_adj(C *__restrict__ f_hat, const C *__restrict__ g1, const R *__restrict__ c0,
-                             const R *__restrict__ c1, const R *__restrict__ c2, int l0, int l1, int l2) {
-  const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i2 >= l2) return;
-  const R w2 = c2[i2];
-  for (int i0 = blockIdx.z; i0 < l0; i0 += gridDim.z)
-    for (int i1 = blockIdx.y; i1 < l1; i1 += gridDim.y) {
-      const size_t i = ((size_t)i0 * l1 + i1) * l2 + i2;
-      const R w = c0[i0] * c1[i1] * w2;
+__global__ void k_deconv_adj(C *__restrict__ f_hat, const C *__restrict__ g1, const R *__restrict__ cA,
+                             const R *__restrict__ cB, const R *__restrict__ cC, FhatGeom fg) {
+  const int iC = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iC >= fg.l[2]) return;
+  const R wC = cC[iC];
+  for (int iA = blockIdx.z; iA < fg.l[0]; iA += gridDim.z)
+    for (int iB = blockIdx.y; iB < fg.l[1]; iB += gridDim.y) {
+      const size_t i = ((size_t)iA * fg.l[1] + iB) * fg.l[2] + iC;
+      const R w = cA[iA] * cB[iB] * wC;
       C v = f_hat[i];
-      const C g = g1[i];
+      C g = g1[i];
+      if (fg.il_sign) {
+        const C t = il_twiddle<R, C>(fg, iA, iB, iC);
+        const R re = g.x * t.x - g.y * t.y, im = g.x * t.y + g.y * t.x;
+        g.x = re; g.y = im;
+      }
       v.x += g.x * w; v.y += g.y * w;
       f_hat[i] = v;
     }
@@ -44,16 +74,16 @@ __global__ void k_deconv_adj(C *__restrict__ f_hat, const C *__restrict__ g1, co
 // mode 0 (trafo): out = -2 pi i k_dim * in          (reference ndft-parallel.c:3034-3054)
 // mode 1 (adj)  : out += +2 pi i k_dim * in         (reference ndft-parallel.c:3012-3032)
 // mode 2        : out += in
+// axis: the memory axis that carries k_dim
 template <class R, class C>
-__global__ void k_ik_scale(const C *__restrict__ in, C *__restrict__ out, int mode, int dim, int s0, int s1, int s2,
-                           int l0, int l1, int l2) {
-  const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i2 >= l2) return;
+__global__ void k_ik_scale(const C *__restrict__ in, C *__restrict__ out, int mode, int axis, FhatGeom fg) {
+  const int iC = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iC >= fg.l[2]) return;
   const R twopi = (R)(2.0 * 3.14159265358979323846);
-  for (int i0 = blockIdx.z; i0 < l0; i0 += gridDim.z)
-    for (int i1 = blockIdx.y; i1 < l1; i1 += gridDim.y) {
-      const size_t i = ((size_t)i0 * l1 + i1) * l2 + i2;
-      const int k = dim == 0 ? s0 + i0 : (dim == 1 ? s1 + i1 : s2 + i2);
+  for (int iA = blockIdx.z; iA < fg.l[0]; iA += gridDim.z)
+    for (int iB = blockIdx.y; iB < fg.l[1]; iB += gridDim.y) {
+      const size_t i = ((size_t)iA * fg.l[1] + iB) * fg.l[2] + iC;
+      const int k = axis == 0 ? fg.s[0] + iA : (axis == 1 ? fg.s[1] + iB : fg.s[2] + iC);
       const R w = twopi * (R)k;
       const C v = in[i];
       C o;

@@ -66,6 +66,8 @@ struct Layout {
   INT N[3], n[3], no[3];
   int m, cutoff;
   bool c2r;
+  bool transposed;         // PNFFT_TRANSPOSED_F_HAT: f_hat block is local_N[1] x local_N[2] x local_N[0] in memory, k1 split over
+                           // mesh dim 0, k2 over mesh dim 1, k0 whole (reference kernel/matrix_D.c:331-341, doc/intro.tex:39-44)
   INT Nc2;                 // stored extent of f_hat's last dim: N[2] or N[2]/2+1
   INT local_N[3], local_N_start[3];
   INT local_no[3], local_no_start[3];
@@ -93,6 +95,12 @@ template <class R> struct GridGeom {
   const R *poly;           // per-tap window polynomials [deg+1][3*cutoff] in u = 2 frac - 1 (device) or nullptr
   int poly_deg;
   int poly_deg_psi;        // degree that suffices for psi alone (<= poly_deg)
+  // PNFFT_INTERLACED (reference kernel/ndft-parallel.c:2732-2753): in the second pass every node is shifted by half a mesh
+  // width, x_t += 0.5 / n_t, and folded back into [-0.5, 0.5) AFTER its grid index was taken; both passes weigh by 0.5
+  // (kernel/assign.c:481,689), which the kernels fold into the x-axis window factors (a power of two: exact)
+  int il_on;               // this pass shifts the nodes
+  double il[3];            // 0.5 / n_t
+  R wscale;                // 1, or 0.5 for the two passes of an interlaced plan
 };
 
 
@@ -179,6 +187,8 @@ template <class R> struct Plan {
   long long launches = 0;       // kernels of this library launched so far
   long long lib_launches = 0;   // cuFFT / CUB / NCCL calls issued so far
   int kernel_variant = 0;
+  int il_pass = 0;              // which pass of an interlaced transform is being issued (Core::geom)
+  bool warned_hessian = false;
 
   cudaEvent_t ev[16];
 
@@ -187,7 +197,28 @@ template <class R> struct Plan {
   size_t sort_tmp_bytes = 0;
 };
 
-template <class R> struct Nodes {
+// What binning (and PNFFT_PRE_PSI) derive from the node coordinates.  An interlaced plan keeps two of these: one for the
+// nodes as given, one for the nodes shifted by half a mesh width (reference nodes->pre_psi / pre_psi_il).
+template <class R> struct BinState {
+  int *d_tile = nullptr;       // tile id per node
+  int *d_tile_sorted = nullptr;
+  int *d_perm = nullptr;       // sorted position -> node index
+  int *d_idx = nullptr;        // identity
+  int *d_tile_count = nullptr; // [ntiles+1]
+  int *d_tile_start = nullptr; // [ntiles+1]
+  size_t cap_nodes = 0, cap_tiles = 0;
+  bool binned = false;         // valid for the current x (kept across calls after precompute_psi or while x is declared static)
+  const void *bin_plan = nullptr;   // plan whose geometry the bins were made for
+  int bin_family = -1;              // ... and its kernel family (tile shape)
+  unsigned long long bin_hash = 0;  // content hash of the device-resident x the bins were made from (0: none)
+  const R *d_x_bound = nullptr; // device x the binning / tables were computed from
+  int *h_maxcol = nullptr;     // pinned: largest column population seen by the last finished binning (load-balance hint)
+  int *d_maxcol = nullptr;
+  // PNFFT_PRE_PSI tables in sorted order (reference kernel/ndft-parallel.c:1184-1240)
+  R *d_pre_psi = nullptr, *d_pre_dpsi = nullptr;
+};
+
+template <class R> struct Nodes : BinState<R> {
   typedef typename Vec2<R>::type C;
   INT local_M = 0;
   unsigned malloc_flags = 0;
@@ -201,24 +232,15 @@ template <class R> struct Nodes {
   R *d_x = nullptr, *d_f = nullptr, *d_grad_f = nullptr;
   size_t cap_x = 0, cap_f = 0, cap_grad = 0;
 
-  // binning state
-  int *d_tile = nullptr;       // tile id per node
-  int *d_tile_sorted = nullptr;
-  int *d_perm = nullptr;       // sorted position -> node index
-  int *d_idx = nullptr;        // identity
-  int *d_tile_count = nullptr; // [ntiles+1]
-  int *d_tile_start = nullptr; // [ntiles+1]
-  int *d_item = nullptr;       // work items: 3 ints each (tile, begin, end)
-  int *d_nitems = nullptr;
-  size_t cap_nodes = 0, cap_tiles = 0, cap_items = 0;
-  bool binned = false;         // valid for the current x (only kept across calls after precompute_psi)
-  const R *d_x_bound = nullptr; // device x the binning / tables were computed from
-  long long max_items = 0;     // launch bound for the tiled kernels
-  int *h_maxcol = nullptr;     // pinned: largest column population seen by the last finished binning (load-balance hint)
-  int *d_maxcol = nullptr;
+  BinState<R> il;          // the same for the shifted nodes of the second interlacing pass
+  void swap_il() { BinState<R> t = *static_cast<BinState<R> *>(this); *static_cast<BinState<R> *>(this) = il; il = t; }
 
-  // PNFFT_PRE_PSI tables in sorted order (reference kernel/ndft-parallel.c:1184-1240)
-  R *d_pre_psi = nullptr, *d_pre_dpsi = nullptr;
+  // "x has not changed since the last call" (extension pnfft_b200_nodes_x_static / PNFFT_B200_X_STATIC):
+  // the uploaded coordinates and their binning are reused until pnfft_set_x / pnfft_precompute_psi / the switch say otherwise
+  bool x_static = false;
+  bool x_uploaded = false;     // d_x holds the current host x
+  unsigned long long x_hash = 0;   // device-resident x: content hash the binning belongs to (0 = none)
+  unsigned long long *d_hash = nullptr, *h_hash = nullptr;
 
   // per-call node table of the z-marching kernels (zmarch.cuh: ZmTab), grown on demand
   R *d_wtab = nullptr;

@@ -86,8 +86,10 @@ k_node_table(GridGeom<R> g, NodeArgs<R> na, int ncomp, int with_vals, R *__restr
   const int p = (int)(gid / 3), t = (int)(gid - 3LL * p);
   if (p >= na.M) return;
   const int j = na.perm[p];
-  const R nxv = mul_rn(g.n[t], na.x[3 * (size_t)j + t]);
-  const R flv = m_floor(nxv), fr = nxv - flv;
+  R nxv, flv;
+  int cell;
+  node_axis(g, na.x[3 * (size_t)j + t], t, &nxv, &flv, &cell);
+  const R fr = nxv - flv;
   R *row = tab + (size_t)p * Tab::ROWLEN;
   R *rp = row + t * CP, *rd = row + (3 + t) * CP;
   if (na.pre_psi) {
@@ -134,8 +136,9 @@ k_node_table(GridGeom<R> g, NodeArgs<R> na, int ncomp, int with_vals, R *__restr
       if (GRAD) rd[s] = b;
     }
   }
+  if (t == 0 && g.wscale != (R)1)     // the 0.5 of an interlaced plan rides on the x-axis factors
+    for (int s = 0; s < C; s++) { rp[s] *= g.wscale; if (GRAD) rd[s] *= g.wscale; }
   // cell offset inside the (T0, T1, ZS) tile
-  const int cell = (int)flv - g.los[t];
   const int T = t == 0 ? Cfg::T0 : (t == 1 ? Cfg::T1 : Cfg::ZS);
   row[t * CP + C] = int_bits_as(cell - (cell / T) * T, (R)0);
   if (t == 0 && with_vals) {

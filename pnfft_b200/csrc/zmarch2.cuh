@@ -70,6 +70,7 @@ struct Zm2Geom {
   int nt2;         // z sub-chunks per column
   int zseg;        // sub-chunks per work item
   int nseg;        // work items per column
+  int col0;        // first column of this launch (the node table may be built and consumed in column batches)
 };
 
 // Node-table row (units of R).  hdr = 8 ints {-dx*sizeof(R), -dy*sizeof(R), dz, dx, node index j, 0, 0, 0};
@@ -104,7 +105,7 @@ constexpr int kZm2TabNodes = ZM2_TABNODES;     // nodes per block of the table k
 // ------------------------------------------------------------------------------------------------
 template <class R, int M_, bool GRAD, bool VALS, bool CPLX>
 __global__ void __launch_bounds__(3 * kZm2TabNodes)
-k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
+k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab, int first) {
   typedef Zm2Cfg<M_> Cfg;
   typedef Zm2Row<R, M_, GRAD, VALS, CPLX> Row;
   constexpr int C = Cfg::C, NCOMP = CPLX ? 2 : 1;
@@ -115,14 +116,16 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
   // the rows are zero padded: clear them once with 16-byte stores, the threads then write the taps only
   for (int i = threadIdx.x; i < kZm2TabNodes * (Row::ROWBYTES / 16); i += blockDim.x) reinterpret_cast<uint4 *>(rows)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  const int p0 = blockIdx.x * kZm2TabNodes;
+  const int p0 = first + blockIdx.x * kZm2TabNodes;      // rows [first, na.M) of the sorted order; tab is indexed absolutely
   const int nn = min(kZm2TabNodes, na.M - p0);
   const int ln = threadIdx.x / 3, t = threadIdx.x - 3 * ln;
   if (ln < nn) {
     const int p = p0 + ln;
     const int j = na.perm[p];
-    const R nxv = mul_rn(g.n[t], na.x[3 * (size_t)j + t]);
-    const R flv = m_floor(nxv), fr = nxv - flv;
+    R nxv, flv;
+    int cell;
+    node_axis(g, na.x[3 * (size_t)j + t], t, &nxv, &flv, &cell);
+    const R fr = nxv - flv;
     R psi[C], dpsi[GRAD ? C : 1];
     unsigned slow = 0;       // taps to redo with the library-call formulas
     if (na.pre_psi) {
@@ -186,9 +189,12 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
     }
     R *row = rows + (size_t)ln * Row::ROWLEN;
     const int off = t == 0 ? Row::oX : (t == 1 ? Row::oY : Row::oZ);
-    const int cell = (int)flv - g.los[t];
     const int T = t == 0 ? Cfg::T0 : (t == 1 ? Cfg::T1 : Cfg::ZS);
     const int d = cell - (cell / T) * T;
+    if (t == 0 && g.wscale != (R)1) {     // the 0.5 of an interlaced plan rides on the x-axis factors (exact)
+#pragma unroll
+      for (int s = 0; s < C; s++) { psi[s] *= g.wscale; if (GRAD) dpsi[s] *= g.wscale; }
+    }
     const int dzc = min(max(d, 0), Cfg::ZS - 1);
     const int lead = t == 0 ? Cfg::XLEAD : (t == 1 ? Cfg::T1 - 1 : (Cfg::DZS ? 0 : dzc));
 #pragma unroll
@@ -198,6 +204,7 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab) {
       slow &= slow - 1;
       R a = (R)0, b = (R)0;
       window_tap<R>(WIN_KAISER_BESSEL, flv - nxv - (R)M_ + (R)s, g.n[t], g.b[t], M_, GRAD, &a, &b);
+      if (t == 0) { a *= g.wscale; b *= g.wscale; }
       row[off + lead + s] = a;
       if (GRAD) row[off + (Row::oDX - Row::oX) + lead + s] = b;
     }
@@ -424,7 +431,7 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
   unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + Sm::s_off_bar);
   unsigned long long *empty = full + S;
 
-  const int col = blockIdx.x / zg.nseg, seg = blockIdx.x - col * zg.nseg;
+  const int colr = blockIdx.x / zg.nseg, seg = blockIdx.x - colr * zg.nseg, col = zg.col0 + colr;
   const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
   const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
   if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;            // no nodes in this work item
@@ -705,7 +712,7 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
   unsigned long long *pempty = pfull + P;
   unsigned long long *wbar = pempty + P;
 
-  const int col = blockIdx.x / zg.nseg, seg = blockIdx.x - col * zg.nseg;
+  const int colr = blockIdx.x / zg.nseg, seg = blockIdx.x - colr * zg.nseg, col = zg.col0 + colr;
   const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
   const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
   if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;

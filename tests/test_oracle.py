@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import checker, refdrv
-from tests.util import rel_l2
+from tests.util import fixture_kwargs, rel_l2
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "t_*.npz")))
@@ -22,7 +22,7 @@ def _impls(single):
 
 
 def test_golden_present():
-    assert len(CASES) >= 40
+    assert len(CASES) >= 69
     assert os.path.exists(os.path.join(GOLD, "layouts.npz")) and os.path.exists(os.path.join(GOLD, "node_index.npz"))
 
 
@@ -31,17 +31,23 @@ def test_transform_golden(case):
     g = np.load(os.path.join(GOLD, case + ".npz"))
     single, c2r = bool(g["single"]), bool(g["c2r"])
     tol = 1e-5 if single else 1e-13
-    N, m, flags = tuple(int(v) for v in g["N"]), int(g["m"]), int(g["flags"])
+    N, n, x_max, acc = fixture_kwargs(g)
+    m, flags = int(g["m"]), int(g["flags"])
+    kw = dict(n=n, m=m, pnfft_flags=flags, c2r=c2r, x_max=x_max)
     for name, impl in _impls(single):
-        t = impl.trafo(N, g["x"], g["f_hat"], m=m, pnfft_flags=flags, compute_flags=3, c2r=c2r)
-        a = impl.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], m=m, pnfft_flags=flags, compute_flags=3, c2r=c2r)
+        if acc:
+            t = impl.trafo(N, g["x"], g["f_hat"], f=g["f0"], grad_f=g["grad_f0"], compute_flags=3 | 16, **kw)
+            a = impl.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], f_hat=g["f_hat0"], compute_flags=3 | 16, **kw)
+        else:
+            t = impl.trafo(N, g["x"], g["f_hat"], compute_flags=3, **kw)
+            a = impl.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], compute_flags=3, **kw)
         assert rel_l2(t["f"], g["out_f"]) <= tol, name
         # float sinc-power gradient: cot(w) - 1/w cancels catastrophically near w = 0 (reference :1897-1917), the
         # float reference itself is only good to ~1e-4 there
         gtol = 1e-4 if (single and "sinc_power" in case) else tol
         assert rel_l2(t["grad_f"], g["out_grad_f"]) <= gtol, name
         assert rel_l2(a["f_hat"], g["out_f_hat"]) <= gtol, name   # the adjoint spreads grad_f with the same dpsi
-        psi, dpsi = impl.probe_tensor(g["x"][:16], N, m=m, pnfft_flags=flags)
+        psi, dpsi = impl.probe_tensor(g["x"][:16], N, n=n, m=m, x_max=x_max, pnfft_flags=flags & ~(1 << 8))
         assert np.abs(psi - g["psi"]).max() <= tol * max(1.0, np.abs(g["psi"]).max()), name
         assert np.abs(dpsi - g["dpsi"]).max() <= 10 * gtol * max(1.0, np.abs(g["dpsi"]).max()), name
 

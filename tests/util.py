@@ -28,8 +28,18 @@ def make_inputs(N, M, seed, c2r=False, single=False, lo=-0.5, up=0.5):
     return x, fh, f, g
 
 
+def fixture_kwargs(g):
+    """Optional keys of a golden fixture (tools/make_golden.py: extra_cases) with the defaults of the round-1 files."""
+    N = tuple(int(v) for v in g["N"])
+    n = tuple(int(v) for v in g["n"]) if "n" in g.files else tuple(2 * v for v in N)
+    x_max = tuple(float(v) for v in g["x_max"]) if "x_max" in g.files else (0.5, 0.5, 0.5)
+    return N, n, x_max, ("acc" in g.files and bool(g["acc"]))
+
+
 class Run1:
-    """One-rank plan + node set with host (numpy) arrays."""
+    """One-rank plan + node set with host (numpy) arrays.  f_hat goes in and comes out in natural (k0, k1, k2) order;
+    with PNFFT_TRANSPOSED_F_HAT the array handed to the library is its (k1, k2, k0) transpose (reference
+    kernel/matrix_D.c:331-341)."""
 
     def __init__(self, N, x, n=None, m=6, flags=0, c2r=False, single=False, x_max=(0.5, 0.5, 0.5), variant=0):
         self.N = tuple(N)
@@ -50,21 +60,34 @@ class Run1:
         self.nodes.set_f(self.f)
         self.nodes.set_grad_f(self.g)
         Nc = (N[0], N[1], N[2] // 2 + 1) if c2r else self.N
-        self.f_hat = np.zeros(Nc, self.cdt)
+        self.transposed = bool(flags & A.TRANSPOSED_F_HAT)
+        self.f_hat = np.zeros((Nc[1], Nc[2], Nc[0]) if self.transposed else Nc, self.cdt)
         self.plan.set_f_hat(self.f_hat)
 
-    def trafo(self, f_hat, cf):
-        self.f_hat[...] = f_hat
+    def put_f_hat(self, f_hat):
+        self.f_hat[...] = np.transpose(f_hat, (1, 2, 0)) if self.transposed else f_hat
+
+    def get_f_hat(self):
+        return np.ascontiguousarray(np.transpose(self.f_hat, (2, 0, 1))) if self.transposed else self.f_hat.copy()
+
+    def trafo(self, f_hat, cf, f0=None, g0=None):
+        self.put_f_hat(f_hat)
+        if f0 is not None:
+            self.f[...] = f0
+        if g0 is not None:
+            self.g[...] = g0
         self.plan.trafo(self.nodes, cf)
         return self.f.copy(), self.g.copy()
 
-    def adj(self, f, g, cf):
+    def adj(self, f, g, cf, f_hat0=None):
         if f is not None:
             self.f[...] = f
         if g is not None:
             self.g[...] = g
+        if f_hat0 is not None:
+            self.put_f_hat(f_hat0)
         self.plan.adj(self.nodes, cf)
-        return self.f_hat.copy()
+        return self.get_f_hat()
 
     def close(self):
         self.nodes.free(0)

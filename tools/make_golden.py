@@ -36,6 +36,75 @@ def inputs(N, M, seed, c2r, single):
     return x, fh, f, g
 
 
+INTERLACED, TRANSPOSED, ACC = 1 << 8, 1 << 11, 1 << 4
+
+
+def extra_cases(out):
+    """Round-2 fixtures: PNFFT_INTERLACED (all windows; nodes that fold in the shifted pass included), PNFFT_TRANSPOSED_F_HAT
+    (f_hat stored here in natural order; the layout is the caller's business), truncated torus x_max < 0.5 (pruned FFT
+    output no < n), PNFFT_COMPUTE_ACCUMULATED for trafo and adj.  Optional keys: n, x_max, acc, f0, grad_f0, f_hat0."""
+    names = []
+    seed = 500
+
+    def one(name, N, M, m, flags, c2r, single, n=None, x_max=(0.5, 0.5, 0.5), acc=False, edge=False):
+        nonlocal seed
+        seed += 1
+        ref = refdrv.get(single)
+        x, fh, f, g = inputs(N, M, seed, c2r, single)
+        rdt = np.float32 if single else np.float64
+        xm = np.array(x_max)
+        x = (x * (2 * xm)).astype(rdt)                         # nodes inside [-x_max, x_max)
+        if edge:                                               # within half a mesh width of the upper border: they fold
+            x[:6] = np.nextafter(rdt(0.5), rdt(0))
+            x[6:9, 0] = rdt(0.5) - rdt(0.2) / (2 * N[0]); x[9:12, 2] = rdt(0.5) - rdt(0.01) / (2 * N[2])
+        n_ = tuple(n) if n is not None else tuple(2 * v for v in N)
+        kw = dict(n=n_, m=m, pnfft_flags=flags, c2r=c2r, x_max=tuple(x_max))
+        extra = {}
+        if acc:
+            rng = np.random.default_rng(seed + 7000)
+            f0 = (f[::-1] * 0.5).copy(); g0 = (g[::-1] * 0.25).copy()
+            fh0 = (fh[::-1, ::-1, ::-1] * 0.125).copy()
+            rt = ref.trafo(N, x, fh, f=f0, grad_f=g0, compute_flags=3 | ACC, **kw)
+            ra = ref.adj(N, x, f=f, grad_f=g, f_hat=fh0, compute_flags=3 | ACC, **kw)
+            extra = dict(acc=True, f0=f0, grad_f0=g0, f_hat0=fh0)
+        else:
+            rt = ref.trafo(N, x, fh, compute_flags=3, **kw)
+            ra = ref.adj(N, x, f=f, grad_f=g, compute_flags=3, **kw)
+        psi, dpsi = ref.probe_tensor(x[:16], N, n=n_, m=m, x_max=tuple(x_max), pnfft_flags=flags & ~INTERLACED)
+        np.savez_compressed(os.path.join(out, name + ".npz"), N=np.array(N), n=np.array(n_), x_max=xm, m=m, flags=flags, c2r=c2r,
+                            single=single, x=x, f_hat=fh, f=f, grad_f=g, out_f=rt["f"], out_grad_f=rt["grad_f"],
+                            out_f_hat=ra["f_hat"], psi=psi, dpsi=dpsi, **extra)
+        names.append(name)
+
+    N, M = (8, 12, 10), 120
+    for win, wf in WIN.items():
+        m = 6 if win == "kaiser_bessel" else 5
+        one("t_il_%s_ad_c2c_m%d_d" % (win, m), N, M, m, wf | INTERLACED, False, False, edge=True)
+    one("t_il_kaiser_bessel_ad_c2c_m4_d", N, M, 4, INTERLACED, False, False, edge=True)
+    one("t_il_kaiser_bessel_ik_c2c_m6_d", N, M, 6, INTERLACED | DIFF_IK, False, False, edge=True)
+    one("t_il_gaussian_ik_c2c_m5_d", N, M, 5, WIN["gaussian"] | INTERLACED | DIFF_IK, False, False, edge=True)
+    one("t_il_kaiser_bessel_ad_c2r_m6_d", N, M, 6, INTERLACED, True, False, edge=True)
+    one("t_il_bspline_ad_c2r_m5_d", N, M, 5, WIN["bspline"] | INTERLACED, True, False, edge=True)
+    one("t_il_kaiser_bessel_ad_c2c_m6_f", N, M, 6, INTERLACED, False, True, edge=True)
+    one("t_il_kaiser_bessel_ad_c2r_m4_f", N, M, 4, INTERLACED, True, True, edge=True)
+    one("t_tr_kaiser_bessel_ad_c2c_m6_d", N, M, 6, TRANSPOSED, False, False)
+    one("t_tr_kaiser_bessel_ik_c2c_m6_d", N, M, 6, TRANSPOSED | DIFF_IK, False, False)
+    one("t_tr_kaiser_bessel_ad_c2r_m6_d", N, M, 6, TRANSPOSED, True, False)
+    one("t_tr_gaussian_ad_c2c_m5_f", N, M, 5, WIN["gaussian"] | TRANSPOSED, False, True)
+    one("t_tr_il_kaiser_bessel_ad_c2c_m4_d", N, M, 4, TRANSPOSED | INTERLACED, False, False, edge=True)
+    Nt, nt, xm = (24, 32, 20), (48, 64, 40), (0.3, 0.25, 0.5)
+    one("t_torus_kaiser_bessel_ad_c2c_m4_d", Nt, 300, 4, 0, False, False, n=nt, x_max=xm)
+    one("t_torus_kaiser_bessel_ik_c2c_m4_d", Nt, 300, 4, DIFF_IK, False, False, n=nt, x_max=xm)
+    one("t_torus_gaussian_ad_c2r_m4_d", Nt, 300, 4, WIN["gaussian"], True, False, n=nt, x_max=xm)
+    one("t_torus_il_kaiser_bessel_ad_c2c_m4_d", Nt, 300, 4, INTERLACED, False, False, n=nt, x_max=xm)
+    one("t_torus_tr_kaiser_bessel_ad_c2c_m4_f", Nt, 300, 4, TRANSPOSED, False, True, n=nt, x_max=xm)
+    one("t_acc_kaiser_bessel_ad_c2c_m6_d", N, M, 6, 0, False, False, acc=True)
+    one("t_acc_kaiser_bessel_ik_c2c_m6_d", N, M, 6, DIFF_IK, False, False, acc=True)
+    one("t_acc_bspline_ad_c2r_m5_d", N, M, 5, WIN["bspline"], True, False, acc=True)
+    one("t_acc_il_kaiser_bessel_ad_c2c_m4_d", N, M, 4, INTERLACED, False, False, acc=True, edge=True)
+    return names
+
+
 def main():
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
@@ -62,6 +131,7 @@ def main():
                                             single=single, x=x, f_hat=fh, f=f, grad_f=g, out_f=rt["f"], out_grad_f=rt["grad_f"],
                                             out_f_hat=ra["f_hat"], psi=psi, dpsi=dpsi)
                         cases.append(name)
+    cases += extra_cases(out)
     # integer work: layouts over process meshes, node -> rank / grid index assignment, sort keys
     ref = refdrv.get(False)
     lay = {}

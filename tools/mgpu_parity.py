@@ -38,7 +38,11 @@ def main():
     results = {}
     ok = True
     cases = [((32, 32, 32), 20000, 6, 0, False), ((32, 48, 40), 15000, 4, A.WINDOW_GAUSSIAN, False),
-             ((32, 32, 32), 20000, 6, A.DIFF_IK, False), ((32, 32, 32), 20000, 6, 0, True)]
+             ((32, 32, 32), 20000, 6, A.DIFF_IK, False), ((32, 32, 32), 20000, 6, 0, True),
+             ((32, 48, 40), 15000, 6, A.TRANSPOSED_F_HAT, False), ((32, 32, 32), 20000, 4, A.TRANSPOSED_F_HAT, True),
+             ((32, 32, 32), 20000, 6, A.INTERLACED, False), ((32, 48, 40), 15000, 4, A.INTERLACED | A.TRANSPOSED_F_HAT | A.DIFF_IK, False)]
+    if len(sys.argv) > 1:       # a larger problem: N^3 with M nodes, Kaiser-Bessel m=6 (python tools/mgpu_parity.py N M)
+        cases = [((int(sys.argv[1]),) * 3, int(sys.argv[2]), 6, 0, False)]
     for ci, (N, M, m, flags, c2r) in enumerate(cases):
         n = tuple(2 * v for v in N)
         rng = np.random.default_rng(77 + ci)
@@ -56,11 +60,11 @@ def main():
         idx = np.nonzero(mine)[0]
         xl = np.ascontiguousarray(x[idx])
         # my f_hat block: k_t = local_N_start[t] + i_t, global range [-N_t/2, N_t/2)  (c2r: k2 = 0 .. N2/2)
+        lN, lNs, lo, up = A.local_size_guru(N, n, (0.5,) * 3, m, comm, pnfft_flags=flags, c2r=c2r)
         off = [int(lNs[t] + N[t] // 2) for t in range(3)]
-        if c2r:
-            off[2] = 0
         sl = tuple(slice(off[t], off[t] + int(lN[t])) for t in range(3))
-        fh_l = np.ascontiguousarray(fh[sl])
+        tr = bool(flags & A.TRANSPOSED_F_HAT)       # the library's block is then the (k1, k2, k0) transpose of this slice
+        fh_l = np.ascontiguousarray(np.transpose(fh[sl], (1, 2, 0)) if tr else fh[sl])
         plan = A.Plan.init_guru(N, n, (0.5,) * 3, m, flags, comm, c2r=c2r)
         nodes = A.Nodes(len(idx), 0)
         ft = np.float64 if c2r else np.complex128
@@ -74,7 +78,7 @@ def main():
         plan.adj(nodes, 3)
         nodes.free(0); plan.finalize(0)
         # gather on rank 0
-        pack = (idx, f_t, g_t, sl, fhw)
+        pack = (idx, f_t, g_t, sl, np.transpose(fhw, (2, 0, 1)) if tr else fhw)
         if world > 1:
             allp = [None] * world
             dist.all_gather_object(allp, pack)
