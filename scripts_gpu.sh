@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-tools/ubench3.bin > gpurun_out/ubench3.log 2>&1
-cat gpurun_out/ubench3.log
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+tail -40 gpurun_out/pytest_gpu.log | cut -c1-220

@@ -54,8 +54,10 @@ def extra_cases(out):
         rdt = np.float32 if single else np.float64
         xm = np.array(x_max)
         x = (x * (2 * xm)).astype(rdt)                         # nodes inside [-x_max, x_max)
-        if edge:                                               # within half a mesh width of the upper border: they fold
-            x[:6] = np.nextafter(rdt(0.5), rdt(0))
+        if edge:     # within half a mesh width of the upper border: they fold in the shifted pass.  (Not one ulp below the
+            # border: there the reference's own Kaiser-Bessel derivative cancels catastrophically)
+            for t in range(3):
+                x[:6, t] = rdt(0.5) - rdt(0.3) / (2 * N[t])
             x[6:9, 0] = rdt(0.5) - rdt(0.2) / (2 * N[0]); x[9:12, 2] = rdt(0.5) - rdt(0.01) / (2 * N[2])
         n_ = tuple(n) if n is not None else tuple(2 * v for v in N)
         kw = dict(n=n_, m=m, pnfft_flags=flags, c2r=c2r, x_max=tuple(x_max))
