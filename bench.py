@@ -1,15 +1,22 @@
 #!/usr/bin/env python
 """Headline benchmark of pnfft-b200 (contract: README of the build driver).
 
-Metric (BASELINE.json): trafo+adj nonuniform points/s at N=256^3, sigma=2 (n=512^3), Kaiser-Bessel m=6, double, c2c,
-M=2^24 uniform random nodes, 1/2/4/8 B200 (process mesh 1x1 / 1x2 / 2x2 / 2x4, strong scaling: the problem is fixed).
+Default workload = BASELINE.json's metric (config C3): trafo+adj nonuniform points/s at N=256^3, sigma=2 (n=512^3),
+Kaiser-Bessel m=6, double, c2c, M=2^24 uniform random nodes, 1/2/4/8 B200 (process mesh 1x1 / 1x2 / 2x2 / 2x4, strong
+scaling: the problem is fixed).  `--config C2 | C4 | C5` runs the other BASELINE configurations through the same code
+(they are parity-test cases for the driver, measured here for the record under profiles/):
+  C2  N=128^3, M=2^21 uniform nodes, Kaiser-Bessel m=6, double, F only
+  C4  N=256^3, M=2^24 strongly clustered nodes (Gaussian blob, sigma 0.05), m=8, --window gaussian|fast_gaussian|bspline,
+      --pre-psi 0|1 (PNFFT_PRE_PSI|PRE_GRAD_PSI tables against on-the-fly window evaluation)
+  C5  N=512^3 (n=1024^3), M=2^27 uniform nodes, Kaiser-Bessel m=6, --variant c2r (real input, double) | float (c2c single)
 
-One "step" = pnfft_trafo(plan, nodes, PNFFT_COMPUTE_F|PNFFT_COMPUTE_GRAD_F) + pnfft_adj(plan, nodes, PNFFT_COMPUTE_F)
-through the C ABI of libpnfft_b200.so.
+One "step" = pnfft_trafo(plan, nodes, cf_trafo) + pnfft_adj(plan, nodes, cf_adj) through the C ABI of libpnfft_b200.so.
   value : device-resident arrays (x, f, grad_f, f_hat are CUDA pointers): M_total / step time
   e2e   : HOST (pinned) arrays handed to the same C-ABI calls: the H2D copies of x, f_hat (trafo) / x, f (adj) and the
           D2H copies of f, grad_f (trafo) / f_hat (adj) happen inside the calls and inside the timed region
   roofline : the dominant gridding kernel against max(FP64 FMA time, HBM time) (north_star)
+  parity : OUTSIDE the timed region, rank 0 compares a node subset of the last trafo and a small adjoint through the same
+           (multi-rank) plan with the CPU checker (oracle/) and prints the rel-l2 errors
   cpu_baseline : the compiled reference PNFFT (oracle/_ref) on the host cores, bounded sample (rank 0, N=1 only)
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref, else the oracle port) on the host cores.
@@ -30,30 +37,97 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 MESH = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4), 16: (4, 4)}
-METRIC = "trafo+adj nonuniform pts/s, N=256^3 m=6 double"
 UNIT = "pts/s"
+F_FAST_GAUSSIAN, F_WIN_GAUSSIAN, F_WIN_BSPLINE = 1 << 1, 1 << 13, 1 << 14
+CF_F, CF_GRAD = 1, 2
 
 
 def workload(args):
-    N = (args.N,) * 3
-    return dict(N=N, n=tuple(2 * v for v in N), m=args.m, M_total=1 << args.log2M)
+    """Everything that defines the timed work, from --config (and the overrides --N --log2M --m --flags)."""
+    c = args.config
+    w = dict(config=c, c2r=False, single=False, flags=args.flags, cf_trafo=CF_F | CF_GRAD, cf_adj=CF_F, dist="uniform",
+             pre_psi=False, window="kaiser_bessel")
+    if c == "C3":
+        Ns, l2M, m = 256, 24, 6
+        w["metric"] = "trafo+adj nonuniform pts/s, N=256^3 m=6 double"
+    elif c == "C2":
+        Ns, l2M, m = 128, 21, 6
+        w["cf_trafo"] = CF_F
+        w["metric"] = "trafo+adj nonuniform pts/s, N=128^3 m=6 double, F only (BASELINE config 2)"
+    elif c == "C4":
+        Ns, l2M, m = 256, 24, 8
+        w["dist"] = "gaussian_blob_0.05"
+        w["window"] = args.window
+        w["flags"] |= {"gaussian": F_WIN_GAUSSIAN, "fast_gaussian": F_WIN_GAUSSIAN | F_FAST_GAUSSIAN, "bspline": F_WIN_BSPLINE}[args.window]
+        w["pre_psi"] = bool(args.pre_psi)
+        w["metric"] = "trafo+adj nonuniform pts/s, N=256^3 m=8 double, clustered nodes, %s window, %s (BASELINE config 4)" % (
+            args.window, "PRE_PSI" if args.pre_psi else "on-the-fly")
+    else:
+        Ns, l2M, m = 512, 27, 6
+        w["c2r"] = args.variant == "c2r"
+        w["single"] = args.variant == "float"
+        w["metric"] = "trafo+adj nonuniform pts/s, N=512^3 m=6 %s (BASELINE config 5)" % (
+            "c2r double" if w["c2r"] else "c2c single")
+    Ns = args.N or Ns
+    l2M = args.log2M if args.log2M is not None else l2M
+    m = args.m or m
+    if (args.N or args.log2M is not None or args.m) and c == "C3":
+        w["metric"] = "trafo+adj nonuniform pts/s, N=%d^3 m=%d double" % (Ns, m)
+    w.update(N=(Ns,) * 3, n=(2 * Ns,) * 3, m=m, M_total=1 << l2M, log2M=l2M)
+    return w
 
 
-def config_dict(args, world, extra=None):
-    w = workload(args)
+def config_dict(w, world, extra=None):
+    ncomp, rb = (1 if w["c2r"] else 2), (4 if w["single"] else 8)
+    mesh = MESH[world]
+    grid_gb = np.prod([w["n"][0] / mesh[0] + 2 * w["m"], w["n"][1] / mesh[1] + 2 * w["m"], w["n"][2] + 2 * w["m"]]) * ncomp * rb / 1e9
+    node_b = rb * (3 + ncomp + (3 * ncomp if w["cf_trafo"] & CF_GRAD else 0))
     c = {
-        "workload": "C3: N=%d^3, n=%d^3 (sigma=2), M=2^%d uniform random nodes, Kaiser-Bessel m=%d, c2c double, "
-                    "step = pnfft_trafo(COMPUTE_F|COMPUTE_GRAD_F, analytic gradient) + pnfft_adj(COMPUTE_F)"
-                    % (args.N, 2 * args.N, args.log2M, args.m),
-        "N": list(w["N"]), "n": list(w["n"]), "m": args.m, "M_total": w["M_total"],
-        "process_mesh": "%dx%d" % MESH[world], "window": "kaiser_bessel", "precision": "double",
+        "workload": "%s: N=%d^3, n=%d^3 (sigma=2), M=2^%d %s nodes, %s m=%d, %s %s, step = pnfft_trafo(%s) + pnfft_adj(COMPUTE_F)%s"
+                    % (w["config"], w["N"][0], w["n"][0], w["log2M"], "uniform random" if w["dist"] == "uniform" else "clustered (Gaussian blob sigma=0.05)",
+                       w["window"], w["m"], "c2r" if w["c2r"] else "c2c", "single" if w["single"] else "double",
+                       "COMPUTE_F|COMPUTE_GRAD_F, analytic gradient" if w["cf_trafo"] & CF_GRAD else "COMPUTE_F",
+                       ", PNFFT_PRE_PSI|PRE_GRAD_PSI tables" if w["pre_psi"] else ""),
+        "N": list(w["N"]), "n": list(w["n"]), "m": w["m"], "M_total": w["M_total"],
+        "process_mesh": "%dx%d" % mesh, "window": w["window"], "precision": "single" if w["single"] else "double",
         "cache": "inputs larger than L2 (padded grid %.2f GB + nodes %.2f GB per rank vs 126 MB L2); no flush needed"
-                 % (np.prod([2 * args.N / MESH[world][0] + 2 * args.m, 2 * args.N / MESH[world][1] + 2 * args.m,
-                             2 * args.N + 2 * args.m]) * 16 / 1e9, w["M_total"] / world * 88 / 1e9),
+                 % (grid_gb, w["M_total"] / world * node_b / 1e9),
     }
     if extra:
         c.update(extra)
     return c
+
+
+def global_f_hat(w):
+    """The same global spectrum on every rank (seeded), so that any rank can hand its block to the library and rank 0 can
+    hand the whole array to the CPU checker."""
+    N = w["N"]
+    Nc = (N[0], N[1], N[2] // 2 + 1) if w["c2r"] else N
+    rng = np.random.default_rng(2000)
+    fh = np.empty(Nc, np.complex128)
+    fh.real = rng.uniform(-1, 1, Nc)
+    fh.imag = rng.uniform(-1, 1, Nc)
+    if w["c2r"]:            # planes k_t = -N_t/2 have no Hermitian partner inside [-N/2, N/2)
+        fh[0, :, :] = 0; fh[:, 0, :] = 0; fh[:, :, 0] = 0
+    return fh
+
+
+def local_nodes(w, rank, M, lo, up):
+    rng = np.random.default_rng(1000 + rank)
+    if w["dist"] == "uniform":
+        xv = rng.uniform(0.0, 1.0, (M, 3)) * (up - lo) + lo
+        return np.minimum(np.maximum(xv, lo), np.nextafter(up, -1.0))
+    # clustered: every rank draws the SAME global blob and keeps what falls into its [lo, up) (reference node ownership,
+    # kernel/ndft-parallel.c:734-775): the ranks around the origin own almost everything -- that is the point of config 4
+    out, rng = [], np.random.default_rng(4000)
+    left = w["M_total"]
+    while left > 0:
+        k = min(left, 1 << 22)
+        xg = np.mod(rng.normal(0.0, 0.05, (k, 3)) + 0.5, 1.0) - 0.5
+        xg = np.clip(xg, -0.5, np.nextafter(0.5, 0.0))
+        out.append(xg[np.all((xg >= lo) & (xg < up), axis=1)])
+        left -= k
+    return np.ascontiguousarray(np.concatenate(out))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -117,24 +191,28 @@ def cpu_mesh(cores):
     return MESH[p]
 
 
-def reference_step(args, sample_log2M, seed=0):
-    """One trafo(F|GRAD)+adj(F) of the reference on a bounded sample: the full N, n, m plan and 2^sample_log2M of the
-    2^log2M nodes.  Returns (pts/s extrapolated to the full node count, detail dict).  Extrapolation: the node loop
-    (LOOP_B timer) scales linearly with the node count, D / F / ghost cells do not depend on it."""
+def reference_step(w, sample_log2M, seed=0):
+    """One trafo+adj of the reference on a bounded sample: the full N, n, m plan and 2^sample_log2M of the nodes.
+    Returns (pts/s extrapolated to the full node count, detail dict).  Extrapolation: the node loop (LOOP_B timer)
+    scales linearly with the node count, D / F / ghost cells do not depend on it."""
     from oracle import checker
-    ref = checker.get()
-    w = workload(args)
+    ref = checker.get(w["single"])
     cores = os.cpu_count() or 1
     mesh = cpu_mesh(cores) if ref.threads else (1, 1)
     Ms = min(1 << sample_log2M, w["M_total"])
     rng = np.random.default_rng(seed)
-    x = rng.uniform(-0.5, 0.5, (Ms, 3))
+    if w["dist"] == "uniform":
+        x = rng.uniform(-0.5, 0.5, (Ms, 3))
+    else:
+        x = np.mod(rng.normal(0.0, 0.05, (Ms, 3)) + 0.5, 1.0) - 0.5
     x = np.clip(x, -0.5, np.nextafter(0.5, 0.0))
-    fh = rng.uniform(-1, 1, w["N"]) + 1j * rng.uniform(-1, 1, w["N"])
+    fh = global_f_hat(w)
+    kw = dict(n=w["n"], m=w["m"], np_mesh=mesh, pnfft_flags=w["flags"], c2r=w["c2r"],
+              precompute_flags=6 if w["pre_psi"] else 0)
     t0 = time.time()
-    rt = ref.trafo(w["N"], x, fh, n=w["n"], m=w["m"], np_mesh=mesh, compute_flags=3)
+    rt = ref.trafo(w["N"], x, fh, compute_flags=w["cf_trafo"], **kw)
     t1 = time.time()
-    ra = ref.adj(w["N"], x, f=rt["f"], n=w["n"], m=w["m"], np_mesh=mesh, compute_flags=1)
+    ra = ref.adj(w["N"], x, f=rt["f"], compute_flags=w["cf_adj"], **kw)
     t2 = time.time()
     scale = w["M_total"] / Ms
     det = {"wall_trafo_s": t1 - t0, "wall_adj_s": t2 - t1}
@@ -153,7 +231,7 @@ def reference_step(args, sample_log2M, seed=0):
     det.update(sample_s=float(sample_s), extrapolated_full_s=float(full), cores=mesh[0] * mesh[1], kind=ref.kind,
                sample="N=%d^3 n=%d^3 m=%d plan, 2^%d of 2^%d nodes, %dx%d ranks (one thread each); node loop scaled x%d, "
                       "D/F/ghost cells as measured (F by the oracle shim's host FFT, FFTW/PFFT are absent)"
-                      % (args.N, 2 * args.N, args.m, sample_log2M, args.log2M, mesh[0], mesh[1], int(scale)))
+                      % (w["N"][0], w["n"][0], w["m"], sample_log2M, w["log2M"], mesh[0], mesh[1], int(scale)))
     return w["M_total"] / full, det
 
 
@@ -162,21 +240,27 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    w = workload(args)
     steps = args.steps if args.steps is not None else 2
     warm = args.warmup if args.warmup is not None else 1
     vals, det = [], None
     t_begin = time.time()
     for it in range(warm + steps):
-        v, det = reference_step(args, args.ref_log2M, seed=it)
+        t0 = time.time()
+        v, det = reference_step(w, args.cpu_log2M, seed=it)
         if it >= warm:
-            vals.append((v, det["extrapolated_full_s"]))
-    value = len(vals) / sum(1.0 / v for v, _ in vals)       # total points / total time
-    ms = 1e3 * sum(t for _, t in vals) / len(vals)
+            vals.append((v, det["extrapolated_full_s"], time.time() - t0))
+    value = len(vals) / sum(1.0 / v for v, _, _ in vals)       # total points / total (extrapolated) time
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic (seeded uniform nodes, random f_hat)",
-        "config": config_dict(args, max(world, 1), {"process_mesh": "host: %d ranks" % det["cores"]}),
+        "impl": "reference", "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm,
+        # what one step of THIS run took on the wall (a bounded sample of the workload) ...
+        "ms_per_step": 1e3 * sum(t for _, _, t in vals) / len(vals),
+        # ... and what `value` is computed from: the node loop of the sample scaled to all 2^log2M nodes
+        "ms_per_step_full_workload_extrapolated": 1e3 * sum(t for _, t, _ in vals) / len(vals),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32" if w["single"] else "f64", "data": "synthetic (seeded nodes, random f_hat)",
+        "config": config_dict(w, max(world, 1), {"process_mesh": "host: %d ranks" % det["cores"]}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": det["cores"], "kind": det["kind"], "sample": det["sample"],
                          "stage_s_trafo": det.get("trafo"), "stage_s_adj": det.get("adj")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -213,36 +297,54 @@ def run_gpu(args):
 
     w = workload(args)
     N, n, m = w["N"], w["n"], w["m"]
+    c2r, single = w["c2r"], w["single"]
+    rdt, tdt = (np.float32, torch.float32) if single else (np.float64, torch.float64)
+    rb = 4 if single else 8
+    NC = 1 if c2r else 2
     mesh = MESH[world]
     comm = A.create_procmesh_2d(*mesh)
-    lN, lNs, lo, up = A.local_size_guru(N, n, (0.5,) * 3, m, comm)
-    M = w["M_total"] // world
-    rng = np.random.default_rng(1000 + rank)
+    lN, lNs, lo, up = A.local_size_guru(N, n, (0.5,) * 3, m, comm, pnfft_flags=w["flags"], c2r=c2r, single=single)
 
     def pinned(shape, dtype):
         return torch.empty(shape, dtype=dtype, pin_memory=True)
 
     # ---- host (pinned) arrays: what a PNFFT caller owns ----
-    hx = pinned((M, 3), torch.float64)
-    xv = rng.uniform(0.0, 1.0, (M, 3)) * (up - lo) + lo
-    xv = np.minimum(np.maximum(xv, lo), np.nextafter(up, -1.0))
-    hx.numpy()[...] = xv
+    if w["dist"] == "uniform":
+        M = w["M_total"] // world
+        xv = local_nodes(w, rank, M, lo.astype(np.float64), up.astype(np.float64))
+    else:
+        xv = local_nodes(w, rank, 0, lo.astype(np.float64), up.astype(np.float64))
+        M = xv.shape[0]
+    hx = pinned((max(M, 1), 3), tdt)[:M]
+    hx.numpy()[...] = xv.astype(rdt)
+    if single:      # float rounding may push a node onto the upper border
+        np.minimum(hx.numpy(), np.nextafter(up.astype(np.float32), np.float32(-1)), out=hx.numpy())
     del xv
-    h_fhat_in = pinned(tuple(int(v) for v in lN) + (2,), torch.float64)
-    h_fhat_in.numpy()[...] = rng.uniform(-1, 1, h_fhat_in.shape)
-    h_fhat_out = pinned(h_fhat_in.shape, torch.float64)
-    hf = pinned((M, 2), torch.float64)
-    hg = pinned((M, 3, 2), torch.float64)
+    fh_glob = global_f_hat(w)
+    off = [int(lNs[t] + N[t] // 2) for t in range(3)]
+    blk = tuple(slice(off[t], off[t] + int(lN[t])) for t in range(3))
+    transposed = bool(w["flags"] & (1 << 11))     # PNFFT_TRANSPOSED_F_HAT: the block is stored (k1, k2, k0)
+    order = (1, 2, 0) if transposed else (0, 1, 2)
+    h_fhat_in = pinned(tuple(int(lN[t]) for t in order) + (2,), tdt)
+    h_fhat_in.numpy()[...] = np.ascontiguousarray(np.transpose(fh_glob[blk], order)).view(np.float64).reshape(h_fhat_in.shape).astype(rdt)
+    if not (rank == 0 and not args.no_parity):
+        del fh_glob
+    h_fhat_out = pinned(h_fhat_in.shape, tdt)
+    fshape, gshape = ((M, NC) if NC == 2 else (M,)), ((M, 3, NC) if NC == 2 else (M, 3))
+    hf, hg = pinned(fshape, tdt), pinned(gshape, tdt)
     # ---- device-resident twins ----
     dx, d_fhat_in = hx.to(dev), h_fhat_in.to(dev)
     d_fhat_out = torch.zeros_like(d_fhat_in)
-    df = torch.zeros((M, 2), dtype=torch.float64, device=dev)
-    dg = torch.zeros((M, 3, 2), dtype=torch.float64, device=dev)
+    df = torch.zeros(fshape, dtype=tdt, device=dev)
+    dg = torch.zeros(gshape, dtype=tdt, device=dev)
 
-    plan = A.Plan.init_guru(N, n, (0.5,) * 3, m, args.flags, comm)
-    nd_dev = A.Nodes(M, 0); nd_dev.set_x(dx); nd_dev.set_f(df); nd_dev.set_grad_f(dg)
-    nd_host = A.Nodes(M, 0); nd_host.set_x(hx); nd_host.set_f(hf); nd_host.set_grad_f(hg)
-    CF_T, CF_A = A.COMPUTE_F | A.COMPUTE_GRAD_F, A.COMPUTE_F
+    plan = A.Plan.init_guru(N, n, (0.5,) * 3, m, w["flags"], comm, c2r=c2r, single=single)
+    nd_dev = A.Nodes(M, 0, single=single); nd_dev.set_x(dx); nd_dev.set_f(df); nd_dev.set_grad_f(dg)
+    nd_host = A.Nodes(M, 0, single=single); nd_host.set_x(hx); nd_host.set_f(hf); nd_host.set_grad_f(hg)
+    if w["pre_psi"]:
+        plan.precompute_psi(nd_dev, A.PRE_PSI | A.PRE_GRAD_PSI)
+        plan.precompute_psi(nd_host, A.PRE_PSI | A.PRE_GRAD_PSI)
+    CF_T, CF_A = w["cf_trafo"], w["cf_adj"]
     stream = torch.cuda.ExternalStream(plan.stream(), device=dev)
 
     def step(nodes, f_in, f_out):
@@ -290,6 +392,13 @@ def run_gpu(args):
     for _ in range(2):
         step(nd_host, h_fhat_in, h_fhat_out)
     ms_e2e, stages_e2e, _ = timed(nd_host, h_fhat_in, h_fhat_out, steps)
+    # the same end-to-end step when the caller promises unchanged coordinates (pnfft_b200_nodes_x_static): x is uploaded
+    # and binned once, not twice per step
+    nd_host.x_static(True)
+    for _ in range(2):
+        step(nd_host, h_fhat_in, h_fhat_out)
+    ms_e2e_static, _, _ = timed(nd_host, h_fhat_in, h_fhat_out, steps)
+    nd_host.x_static(False)
     clk = None
     if clocks:
         time.sleep(0.15)
@@ -300,11 +409,14 @@ def run_gpu(args):
     c3 = float((2 * m + 1) ** 3)
     t_gather = statistics.mean(s[0]["b_kernel"] for s in stages) * 1e-3
     t_scatter = statistics.mean(s[1]["b_kernel"] for s in stages) * 1e-3
+    Mmax = torch.tensor([float(M)], dtype=torch.float64, device=dev)
     red = torch.tensor([t_gather, t_scatter], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(Mmax, op=dist.ReduceOp.MAX)
     t_gather, t_scatter = float(red[0]), float(red[1])
-    fp64_peak = float(A.measure_fp64_tflops())
+    M_rf = float(Mmax.item())            # the slowest rank's kernel time belongs to the fullest rank
+    fp_peak = float(A.measure_fp64_tflops())
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -313,53 +425,71 @@ def run_gpu(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     lno = [n[0] // mesh[0], n[1] // mesh[1], n[2]]
-    grid_bytes = float(np.prod(lno)) * 16
+    grid_bytes = float(np.prod(lno)) * NC * rb
+    grad = bool(CF_T & CF_GRAD)
+    fl_g = (16 if grad else 4) * (NC / 2.0) * c3        # c2c 16 c^3 (F+grad) / 4 c^3 (F); r2r half of it
+    fl_s = 4 * (NC / 2.0) * c3
+    gname = "gather_f_grad" if grad else "gather_f"
     kern = {
-        "gather_f_grad": {"flops": 16 * c3 * M, "bytes": grid_bytes + M * (24 + 16 + 48), "ms": t_gather * 1e3},
-        "scatter_f": {"flops": 4 * c3 * M, "bytes": grid_bytes + M * (24 + 16), "ms": t_scatter * 1e3},
+        gname: {"flops": fl_g * M_rf, "bytes": grid_bytes + M_rf * rb * (3 + NC + (3 * NC if grad else 0)), "ms": t_gather * 1e3},
+        "scatter_f": {"flops": fl_s * M_rf, "bytes": grid_bytes + M_rf * rb * (3 + NC), "ms": t_scatter * 1e3},
     }
+    prec_note = ""
+    if single:
+        # the float kernels run on the FP32 FMA pipe; there is no measured FP32 peak in MEASURED_PEAKS.json, so the FP64
+        # figure stays the (conservative) denominator and the fraction can exceed what a double kernel could reach
+        prec_note = " (single-precision kernels: FP32 pipe, reported against the FP64 peak for lack of a measured FP32 figure)"
     for k in kern.values():
         k["tflops"] = k["flops"] / (k["ms"] * 1e-3) * 1e-12
         k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) * 1e-9
-        k["frac_fp64"] = k["tflops"] / fp64_peak
+        k["frac_fp64"] = k["tflops"] / fp_peak
         k["frac_hbm"] = k["gbs"] / hbm_peak
-        k["roofline_ms"] = max(k["flops"] / (fp64_peak * 1e12), k["bytes"] / (hbm_peak * 1e9)) * 1e3
+        k["roofline_ms"] = max(k["flops"] / (fp_peak * 1e12), k["bytes"] / (hbm_peak * 1e9)) * 1e3
     dom_name = max(kern, key=lambda q: kern[q]["ms"])
     dom = kern[dom_name]
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_name)
-    except Exception:
-        pass
-    bound_fp64 = dom["flops"] / (fp64_peak * 1e12) >= dom["bytes"] / (hbm_peak * 1e9)
+    if world == 1:      # ncu runs on one GPU only: the measured DRAM bytes belong to the N=1 launch of this config
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(w["config"], {}).get(dom_name)
+        except Exception:
+            pass
+    bound_fp64 = dom["flops"] / (fp_peak * 1e12) >= dom["bytes"] / (hbm_peak * 1e9)
     roofline = {
         "kernel": dom_name, "bound": "fp64" if bound_fp64 else "hbm",
-        "achieved": dom["tflops"] if bound_fp64 else dom["gbs"], "peak": fp64_peak if bound_fp64 else hbm_peak,
+        "achieved": dom["tflops"] if bound_fp64 else dom["gbs"], "peak": fp_peak if bound_fp64 else hbm_peak,
         "unit": "TFLOP/s" if bound_fp64 else "GB/s", "frac": dom["frac_fp64"] if bound_fp64 else dom["frac_hbm"],
         "traffic": traffic,
         "peak_source": "FP64 FMA: measured live (independent DFMA chains on all SMs, pnfft_b200_measure_fp64_tflops); HBM: "
-                       + hbm_src,
+                       + hbm_src + prec_note,
         "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac_hbm"]},
-        "algorithmic": "flops/node: gather F+grad 16*(2m+1)^3, scatter F 4*(2m+1)^3; bytes: grid block once + x,f[,grad_f] "
-                       "once (SURVEY.md 8d)",
+        "algorithmic": "flops/node: gather F+grad 16*(2m+1)^3, gather / scatter F 4*(2m+1)^3 (c2c; r2r half); bytes: grid "
+                       "block once + x,f[,grad_f] once (SURVEY.md 8d); the kernel time of the slowest rank against the "
+                       "node count of the fullest rank; kernel ms include the node-table kernel",
         "kernels": kern,
         "gridding_roofline_ms_per_step": sum(k["roofline_ms"] for k in kern.values()),
         "gridding_measured_ms_per_step": sum(k["ms"] for k in kern.values()),
     }
     roofline["gridding_frac"] = roofline["gridding_roofline_ms_per_step"] / roofline["gridding_measured_ms_per_step"]
 
-    h2d = hx.numel() * 8 * 2 + h_fhat_in.numel() * 8 + hf.numel() * 8           # x twice, f_hat (trafo), f (adj)
-    d2h = hf.numel() * 8 + hg.numel() * 8 + h_fhat_out.numel() * 8              # f, grad_f (trafo), f_hat (adj)
-    value = w["M_total"] / (ms_dev * 1e-3 / steps)
-    e2e = w["M_total"] / (ms_e2e * 1e-3 / steps)
+    h2d = hx.numel() * rb * 2 + h_fhat_in.numel() * rb + hf.numel() * rb           # x twice, f_hat (trafo), f (adj)
+    d2h = hf.numel() * rb + (hg.numel() * rb if grad else 0) + h_fhat_out.numel() * rb   # f, grad_f (trafo), f_hat (adj)
+    tot = torch.tensor([float(h2d), float(d2h), float(M)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    M_total = int(tot[2].item())
+    value = M_total / (ms_dev * 1e-3 / steps)
+    e2e = M_total / (ms_e2e * 1e-3 / steps)
     mean_stage = lambda idx, key, S: statistics.mean(s[idx][key] for s in S)   # noqa: E731
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic (seeded uniform nodes in each rank's [lo,up), random f_hat)",
-        "config": config_dict(args, world),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+        "dtype": "f32" if single else "f64", "data": "synthetic (seeded nodes in each rank's [lo,up), seeded random f_hat)",
+        "config": config_dict(w, world),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
                 "ms_per_step": ms_e2e / steps},
+        "e2e_x_static": {"value": M_total / (ms_e2e_static * 1e-3 / steps), "unit": UNIT, "ms_per_step": ms_e2e_static / steps,
+                         "h2d_bytes_per_step": int(tot[0].item()) - world * int(hx.numel() * rb * 2),
+                         "note": "same step with pnfft_b200_nodes_x_static(nodes, 1): coordinates uploaded and binned once"},
         "gpu_launches": int(l1 - l0), "library_calls": int(c1 - c0),
         "roofline": roofline,
         "clocks": clk,
@@ -368,14 +498,23 @@ def run_gpu(args):
                      "trafo_e2e": {k: mean_stage(0, k, stages_e2e) for k in stages_e2e[0][0]},
                      "adj_e2e": {k: mean_stage(1, k, stages_e2e) for k in stages_e2e[0][1]}},
     }
+
+    # ---- parity, outside the timed region: the last device-resident trafo on a node subset, and a small adjoint through
+    #      the same (multi-rank) plan, against the CPU checker on the global problem ----
+    if not args.no_parity:
+        try:
+            line["parity"] = parity_check(args, w, A, plan, comm, rank, world, dev, hx, h_fhat_in, blk, lN,
+                                          fh_glob if rank == 0 else None)
+        except Exception as e:   # the checker is optional equipment of the bench, never of the product
+            line["parity"] = {"error": repr(e)}
     nd_dev.free(0); nd_host.free(0); plan.finalize(0)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, det = reference_step(args, args.cpu_log2M)
+            v, det = reference_step(w, args.cpu_log2M)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": det["cores"], "kind": det["kind"], "sample": det["sample"],
                                     "stage_s_trafo": det.get("trafo"), "stage_s_adj": det.get("adj"),
                                     "sample_wall_s": det["wall_trafo_s"] + det["wall_adj_s"]}
-        except Exception as e:   # the checker is optional equipment of the bench, never of the product
+        except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -384,19 +523,94 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def parity_check(args, w, A, plan, comm, rank, world, dev, hx, h_fhat_in, blk, lN, fh_glob):
+    """rel-l2 of f, grad_f (trafo) and f_hat (adj) against the CPU checker, with KT / KA nodes per rank, through the plan
+    that was just timed (host arrays: the path a PNFFT caller uses)."""
+    import torch
+    import torch.distributed as dist
+    N, c2r, single = w["N"], w["c2r"], w["single"]
+    rdt = np.float32 if single else np.float64
+    NC = 1 if c2r else 2
+    KT, KA = args.parity_nodes, 4 * args.parity_nodes
+    M = hx.shape[0]
+    kt, ka = min(KT, M), min(KA, M)
+    x_t, x_a = np.ascontiguousarray(hx.numpy()[:kt]), np.ascontiguousarray(hx.numpy()[:ka])
+    ft = rdt if c2r else (np.complex64 if single else np.complex128)
+    # trafo on the first kt local nodes
+    nd = A.Nodes(kt, 0, single=single)
+    f_t, g_t = np.zeros(kt, ft), np.zeros((kt, 3), ft)
+    nd.set_x(x_t); nd.set_f(f_t); nd.set_grad_f(g_t)
+    plan.set_f_hat(h_fhat_in)
+    plan.trafo(nd, w["cf_trafo"])
+    nd.free(0)
+    # adjoint of the first ka local nodes
+    rng = np.random.default_rng(3000 + rank)
+    f_a = rng.uniform(-1, 1, ka).astype(rdt) if c2r else (rng.uniform(-1, 1, ka) + 1j * rng.uniform(-1, 1, ka)).astype(ft)
+    nd = A.Nodes(ka, 0, single=single)
+    fa_buf = f_a.copy()
+    nd.set_x(x_a); nd.set_f(fa_buf)
+    transposed = bool(w["flags"] & (1 << 11))
+    order = (1, 2, 0) if transposed else (0, 1, 2)
+    h_out = np.zeros(tuple(int(lN[t]) for t in order), np.complex64 if single else np.complex128)
+    plan.set_f_hat(h_out)
+    plan.adj(nd, w["cf_adj"])
+    nd.free(0)
+    if transposed:
+        h_out = np.ascontiguousarray(np.transpose(h_out, (2, 0, 1)))
+    pack = (x_t, f_t, g_t, x_a, f_a, blk, h_out)
+    if world > 1:
+        allp = [None] * world
+        dist.all_gather_object(allp, pack)
+    else:
+        allp = [pack]
+    if rank != 0:
+        return None
+    from oracle import checker
+    ref = checker.get(single)
+    cores = os.cpu_count() or 1
+    mesh = cpu_mesh(cores) if getattr(ref, "threads", False) else (1, 1)
+    kw = dict(n=w["n"], m=w["m"], pnfft_flags=w["flags"], c2r=c2r, np_mesh=mesh)
+    t0 = time.time()
+    X = np.concatenate([p[0] for p in allp]); Fo = np.concatenate([p[1] for p in allp]); Go = np.concatenate([p[2] for p in allp])
+    rt = ref.trafo(N, X, fh_glob, compute_flags=w["cf_trafo"], **kw)
+    XA = np.concatenate([p[3] for p in allp]); FA = np.concatenate([p[4] for p in allp])
+    ra = ref.adj(N, XA, f=FA, compute_flags=w["cf_adj"], **kw)
+    H = np.zeros(ra["f_hat"].shape, np.complex128)
+    for p in allp:
+        H[p[5]] = p[6]
+
+    def rl2(a, b):
+        d = np.linalg.norm(np.ravel(b))
+        return float(np.linalg.norm(np.ravel(a).astype(np.complex128) - np.ravel(b)) / (d if d > 0 else 1.0))
+    out = {"f": rl2(Fo, rt["f"]), "f_hat": rl2(H, ra["f_hat"]), "checker": ref.name, "trafo_nodes": int(X.shape[0]),
+           "adj_nodes": int(XA.shape[0]), "ranks": world, "bar": 1e-5 if single else 1e-13, "checker_wall_s": None}
+    if w["cf_trafo"] & CF_GRAD:
+        out["grad_f"] = rl2(Go, rt["grad_f"])
+    out["parity_rel_l2"] = max(v for k, v in out.items() if k in ("f", "grad_f", "f_hat"))
+    out["ok"] = bool(out["parity_rel_l2"] <= out["bar"])
+    out["checker_wall_s"] = time.time() - t0
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--N", type=int, default=256)
-    ap.add_argument("--log2M", type=int, default=24)
-    ap.add_argument("--m", type=int, default=6)
-    ap.add_argument("--flags", type=int, default=0, help="pnfft plan flags (default: Kaiser-Bessel, analytic gradient)")
-    ap.add_argument("--cpu-log2M", dest="cpu_log2M", type=int, default=20, help="node sample of the cpu_baseline leg")
-    ap.add_argument("--ref-log2M", dest="ref_log2M", type=int, default=18, help="node sample per step of --impl reference")
+    ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--window", default="gaussian", choices=["gaussian", "fast_gaussian", "bspline"], help="C4 only")
+    ap.add_argument("--pre-psi", dest="pre_psi", type=int, default=0, help="C4 only: PNFFT_PRE_PSI|PRE_GRAD_PSI tables")
+    ap.add_argument("--variant", default="c2r", choices=["c2r", "float"], help="C5 only")
+    ap.add_argument("--N", type=int, default=None)
+    ap.add_argument("--log2M", type=int, default=None)
+    ap.add_argument("--m", type=int, default=None)
+    ap.add_argument("--flags", type=int, default=0, help="extra pnfft plan flags (default: analytic gradient)")
+    ap.add_argument("--cpu-log2M", dest="cpu_log2M", type=int, default=20,
+                    help="node sample of the CPU legs (cpu_baseline and --impl reference use the same one)")
+    ap.add_argument("--parity-nodes", dest="parity_nodes", type=int, default=2048, help="trafo nodes per rank in the parity leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

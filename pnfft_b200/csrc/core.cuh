@@ -25,6 +25,8 @@ enum : unsigned {
   C_F = 1u << 0, C_GRAD_F = 1u << 1, C_HESSIAN_F = 1u << 2, C_DIRECT = 1u << 3, C_ACCUMULATED = 1u << 4,
   C_OMIT_DECONV = 1u << 5, C_OMIT_FFT = 1u << 6, C_OMIT_CONV = 1u << 7
 };
+// job lists of the peer-memory data plane (p2p.cuh)
+enum { LIST_FWD0 = 0, LIST_FWD1, LIST_FWD2, LIST_BWD2, LIST_BWD1, LIST_BWD0, LIST_FILL1, LIST_FILL0, LIST_RED0, LIST_RED1, LIST_COUNT };
 enum { T_ITER = 0, T_WHOLE, T_LOOP_B, T_SORT_NODES, T_GCELLS, T_MATRIX_B, T_MATRIX_F, T_MATRIX_D, T_SHIFT_IN, T_SHIFT_OUT };
 
 inline bool is_device_ptr(const void *p) {
@@ -363,7 +365,197 @@ template <class R> struct Core {
     upload_window_tables(p);
     make_fft_plans(p);
     PNB_CUDA(cudaStreamSynchronize(p->stream));
+    setup_peer(p, N, n, x_max, m, c2r);
     return p;
+  }
+
+  // -------------------------------------------------------------------------------------------
+  // peer-memory data plane (p2p.cuh): IPC mapping of every rank's buffers, job lists of all exchange stages
+  // -------------------------------------------------------------------------------------------
+  static void setup_peer(P *p, const INT *N, const INT *n, const R *x_max, int m, bool c2r) {
+    PeerPlane &pp = p->peer;
+    const Mesh &M = p->mesh;
+    pp.nranks = M.size; pp.rank = M.rank;
+    static const bool want = env_flag("PNFFT_B200_P2P", true);
+    if (M.size <= 1 || !want) return;
+    const int Pn = M.size;
+    if (Pn > 32) return;
+    int *my_flags = nullptr;
+    PNB_CUDA(cudaMalloc((void **)&my_flags, sizeof(int) * 64));
+    PNB_CUDA(cudaMemset(my_flags, 0, sizeof(int) * 64));
+    void *mine[6] = {p->d_work[0], p->d_work[1], p->d_work[2], p->d_grid, (void *)p->d_g1, (void *)my_flags};
+    std::vector<cudaIpcMemHandle_t> hs((size_t)6 * Pn);
+    int ok = 1;
+    for (int k = 0; k < 6; k++)
+      if (cudaIpcGetMemHandle(&hs[(size_t)6 * M.rank + k], mine[k]) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    for (int q = 0; q < Pn; q++) MPI_Bcast(&hs[(size_t)6 * q], (int)(6 * sizeof(cudaIpcMemHandle_t)), MPI_BYTE, q, p->comm);
+    for (int k = 0; k < 3; k++) pp.work[k].assign((size_t)Pn, nullptr);
+    pp.grid.assign((size_t)Pn, nullptr); pp.g1.assign((size_t)Pn, nullptr); pp.flags.assign((size_t)Pn, nullptr);
+    for (int q = 0; q < Pn && ok; q++) {
+      void *ptr[6];
+      for (int k = 0; k < 6; k++) {
+        if (q == M.rank) { ptr[k] = mine[k]; continue; }
+        ptr[k] = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr[k], hs[(size_t)6 * q + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      }
+      for (int k = 0; k < 3; k++) pp.work[k][(size_t)q] = ptr[k];
+      pp.grid[(size_t)q] = ptr[3]; pp.g1[(size_t)q] = ptr[4]; pp.flags[(size_t)q] = (int *)ptr[5];
+    }
+    // ---- job lists: every rank's layout and pipe, maps composed rank to rank ----
+    std::vector<JobList> lists((size_t)LIST_COUNT);
+    for (auto &l : lists) { l.n = 0; l.nblocks = 0; }
+    if (ok) ok = build_peer_jobs(p, N, n, x_max, m, c2r, lists) ? 1 : 0;
+    int all_ok = 0;
+    MPI_Allreduce(&ok, &all_ok, 1, MPI_INT, MPI_MIN, p->comm);
+    if (!all_ok) {
+      if (M.rank == 0) fprintf(stderr, "pnfft-b200: peer-memory exchange unavailable (CUDA IPC or map composition); using NCCL send/recv\n");
+      close_peer(p);
+      cudaFree(my_flags);
+      return;
+    }
+    for (int k = 0; k < LIST_COUNT; k++) { finish_jobs(lists[(size_t)k]); pp.nblocks[k] = lists[(size_t)k].nblocks; }
+    PNB_CUDA(cudaMalloc((void **)&pp.d_jobs, sizeof(JobList) * LIST_COUNT));
+    PNB_CUDA(cudaMemcpy(pp.d_jobs, lists.data(), sizeof(JobList) * LIST_COUNT, cudaMemcpyHostToDevice));
+    PNB_CUDA(cudaMalloc((void **)&pp.d_flag_ptrs, sizeof(int *) * Pn));
+    PNB_CUDA(cudaMemcpy(pp.d_flag_ptrs, pp.flags.data(), sizeof(int *) * Pn, cudaMemcpyHostToDevice));
+    PNB_CUDA(cudaMalloc((void **)&pp.d_error, sizeof(int)));
+    PNB_CUDA(cudaMemset(pp.d_error, 0, sizeof(int)));
+    PNB_CUDA(cudaHostAlloc((void **)&pp.h_error, sizeof(int), cudaHostAllocDefault));
+    *pp.h_error = 0;
+    pp.on = true;
+    MPI_Barrier(p->comm);       // every rank's flags are zeroed and mapped before the first epoch is released
+  }
+  static void close_peer(P *p) {
+    PeerPlane &pp = p->peer;
+    for (int q = 0; q < (int)pp.grid.size(); q++) {
+      if (q == pp.rank) continue;
+      for (int k = 0; k < 3; k++) if (pp.work[k][(size_t)q]) cudaIpcCloseMemHandle(pp.work[k][(size_t)q]);
+      if (pp.grid[(size_t)q]) cudaIpcCloseMemHandle(pp.grid[(size_t)q]);
+      if (pp.g1[(size_t)q]) cudaIpcCloseMemHandle(pp.g1[(size_t)q]);
+      if (pp.flags[(size_t)q]) cudaIpcCloseMemHandle(pp.flags[(size_t)q]);
+    }
+    for (int k = 0; k < 3; k++) pp.work[k].clear();
+    pp.grid.clear(); pp.g1.clear(); pp.flags.clear();
+    pp.on = false;
+  }
+
+  static bool build_peer_jobs(P *p, const INT *N, const INT *n, const R *x_max, int m, bool c2r, std::vector<JobList> &lists) {
+    const PeerPlane &pp = p->peer;
+    const Mesh &Mm = p->mesh;
+    const int Pn = Mm.size, me = Mm.rank;
+    std::vector<Layout> Ls((size_t)Pn);
+    std::vector<PipeGeom> pipes((size_t)Pn);
+    for (int q = 0; q < Pn; q++) {
+      Mesh mq = Mm;
+      mq.rank = q; mq.co[0] = q / Mm.np[1]; mq.co[1] = q % Mm.np[1];
+      compute_layout<R>(Ls[(size_t)q], mq, N, n, x_max, m, c2r, p->pnfft_flags);
+      pipes[(size_t)q] = build_pipe(Ls[(size_t)q], mq);
+    }
+    auto entry_for = [&](const Stage &S, int peer) -> const Transfer * {
+      for (const auto &T : S.tr) if (T.peer == peer) return &T;
+      return nullptr;
+    };
+    // work buffer that holds the destination-side / source-side array of each pipeline stage (Core::fft_forward / _backward)
+    const int dst_buf[3] = {1, 0, 1};      // L1 in W1, L3 in W0, L4 in W1
+    auto src_ptr = [&](int s, int q) -> void * { return s == 0 ? pp.g1[(size_t)q] : pp.work[dst_buf[s - 1]][(size_t)q]; };
+    const PipeGeom &G = p->pipe;
+    for (int s = 0; s < 3; s++) {
+      JobList &LF = lists[(size_t)(LIST_FWD0 + s)], &LB = lists[(size_t)(LIST_BWD0 - s)];
+      for (const auto &T : G.st[s].tr) {
+        const int q = T.peer;
+        if (q == me && !T.self_maps.empty()) {
+          for (const auto &bm : T.self_maps) {
+            if (!push_job(LF, bm, pp.work[dst_buf[s]][(size_t)me], true, src_ptr(s, me), T.send_sign, false)) return false;
+            if (!push_job(LB, bm, src_ptr(s, me), false, pp.work[dst_buf[s]][(size_t)me], T.send_sign, false)) return false;
+          }
+          continue;
+        }
+        const Transfer *Tq = entry_for(pipes[(size_t)q].st[s], me);
+        if (!Tq) return false;
+        // forward: my source array -> q's destination array  (my send map o q's receive maps)
+        if (T.send_elems > 0) {
+          if (T.send_maps.size() != 1) return false;
+          for (const auto &rm : Tq->recv_maps) {
+            BoxMap c;
+            if (!compose_self_map(T.send_maps[0], rm, &c)) return false;
+            if (!push_job(LF, c, pp.work[dst_buf[s]][(size_t)q], true, src_ptr(s, me), T.send_sign, false)) return false;
+          }
+        }
+        // backward: my destination-side array -> q's source-side array  (q's send map o my receive maps)
+        if (T.recv_elems > 0) {
+          if (Tq->send_maps.size() != 1) return false;
+          for (const auto &rm : T.recv_maps) {
+            BoxMap c;
+            if (!compose_self_map(Tq->send_maps[0], rm, &c)) return false;
+            if (!push_job(LB, c, src_ptr(s, q), false, pp.work[dst_buf[s]][(size_t)me], Tq->send_sign, false)) return false;
+          }
+        }
+      }
+    }
+    // ---- ghost cells along the split axes: fill = push my border rows into the neighbours' halos (axis 1, then axis 0,
+    //      which carries the axis-1 halos => corners); reduce = pull the neighbours' halos and add (axis 0, then axis 1) ----
+    const Layout &L = p->L;
+    for (int axis = 0; axis < 2; axis++) {
+      if (Mm.np[axis] <= 1) continue;
+      JobList &LFi = lists[(size_t)(axis == 1 ? LIST_FILL1 : LIST_FILL0)], &LR = lists[(size_t)(axis == 0 ? LIST_RED0 : LIST_RED1)];
+      int cu[2] = {Mm.co[0], Mm.co[1]}, cd[2] = {Mm.co[0], Mm.co[1]};
+      cu[axis] += 1; cd[axis] -= 1;
+      const int up = Mm.rank_of(cu[0], cu[1]), down = Mm.rank_of(cd[0], cd[1]);
+      const Layout &Lu = Ls[(size_t)up], &Ld = Ls[(size_t)down];
+      const long long gcb = L.gcb[axis], gca = L.gca[axis], lno = L.local_no[axis];
+      long long lo[3], ext[3];
+      for (int t = 0; t < 3; t++) {
+        const bool wide = t > axis;            // axes filled before this one span the padded extent (Core::halo_T)
+        lo[t] = wide ? 0 : L.gcb[t];
+        ext[t] = wide ? L.ngc[t] : L.local_no[t];
+      }
+      auto region = [&](const Layout &LL, long long start, long long width, long long *off, long long *str, long long *dims) {
+        long long s3[3] = {lo[0], lo[1], lo[2]}, d3[3] = {ext[0], ext[1], ext[2]};
+        s3[axis] = start; d3[axis] = width;
+        str[0] = (long long)LL.ngc[1] * LL.pitch2; str[1] = LL.pitch2; str[2] = 1;
+        *off = s3[0] * str[0] + s3[1] * str[1] + s3[2];
+        for (int t = 0; t < 3; t++) dims[t] = d3[t];
+      };
+      auto add_job = [&](JobList &JL, void *dst, const Layout &Ldst, long long dstart, const void *src, const Layout &Lsrc, long long sstart,
+                         long long width, bool add) -> bool {
+        if (JL.n >= kMaxJobs) return false;
+        BoxJob &J = JL.j[JL.n++];
+        long long dd[3];
+        region(Ldst, dstart, width, &J.d_off, J.d_str, J.dims);
+        region(Lsrc, sstart, width, &J.s_off, J.s_str, dd);
+        J.dst = dst; J.src = src; J.parity = 0; J.sign = 0; J.add = add ? 1 : 0; J.first_block = 0; J.bx = J.by = 1;
+        return true;
+      };
+      void *gme = pp.grid[(size_t)me];
+      // fill: my top gcb interior rows -> up's below halo; my bottom gca interior rows -> down's above halo
+      if (!add_job(LFi, pp.grid[(size_t)up], Lu, 0, gme, L, gcb + lno - gcb, gcb, false)) return false;
+      if (!add_job(LFi, pp.grid[(size_t)down], Ld, Ld.gcb[axis] + Ld.local_no[axis], gme, L, gcb, gca, false)) return false;
+      // reduce: down's above halo -> my bottom interior rows; up's below halo -> my top interior rows
+      if (!add_job(LR, gme, L, gcb, pp.grid[(size_t)down], Ld, Ld.gcb[axis] + Ld.local_no[axis], gca, true)) return false;
+      if (!add_job(LR, gme, L, gcb + lno - gcb, pp.grid[(size_t)up], Lu, 0, gcb, true)) return false;
+    }
+    return true;
+  }
+
+  static void peer_barrier(P *p) {
+    PeerPlane &pp = p->peer;
+    pp.epoch++;
+    k_peer_barrier<<<1, 32, 0, p->stream>>>(pp.d_flag_ptrs, pp.flags[(size_t)pp.rank], pp.rank, pp.nranks, pp.epoch, pp.d_error);
+    p->launches++;
+  }
+  template <class T> static void peer_jobs(P *p, int list) {
+    PeerPlane &pp = p->peer;
+    if (pp.nblocks[list] <= 0) return;
+    k_box_jobs<T><<<(unsigned)pp.nblocks[list], 256, 0, p->stream>>>(pp.d_jobs + list);
+    p->launches++;
+  }
+  // after a call: did a barrier give up waiting for a peer?
+  static void peer_check(P *p) {
+    PeerPlane &pp = p->peer;
+    if (!pp.on) return;
+    PNB_CUDA(cudaMemcpyAsync(pp.h_error, pp.d_error, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    PNB_CUDA(cudaStreamSynchronize(p->stream));
+    if (*pp.h_error) { fprintf(stderr, "pnfft-b200: rank %d: a peer did not reach exchange barrier %d (epoch now %d)\n", pp.rank, *pp.h_error, pp.epoch); abort(); }
   }
 
   static void make_fft_plans(P *p) {
@@ -384,6 +576,13 @@ template <class R> struct Core {
   static void finalize(P *p, unsigned flags) {
     if (!p) return;
     cudaStreamSynchronize(p->stream);
+    if (p->peer.on) {          // nobody unmaps or frees while a peer may still touch the buffers
+      int *my_flags = p->peer.flags[(size_t)p->peer.rank];
+      MPI_Barrier(p->comm);
+      close_peer(p);
+      MPI_Barrier(p->comm);
+      cudaFree(my_flags); cudaFree(p->peer.d_jobs); cudaFree(p->peer.d_flag_ptrs); cudaFree(p->peer.d_error); cudaFreeHost(p->peer.h_error);
+    }
     if (p->fft_x) cufftDestroy(p->fft_x);
     if (p->fft_y) cufftDestroy(p->fft_y);
     if (p->fft_z_fwd) cufftDestroy(p->fft_z_fwd);
@@ -409,11 +608,12 @@ template <class R> struct Core {
     const PipeGeom &G = p->pipe;
     cudaStream_t st = p->stream;
     C *W0 = (C *)p->d_work[0], *W1 = (C *)p->d_work[1], *PK = (C *)p->d_work[2];
-    run_stage_forward<C>(G.st[0], p->mesh, p->d_g1, W0, W1, PK, st, &p->launches);       // L1 in W1
+    const bool peer = p->peer.on;
+    if (peer) peer_stage_forward(p, 0, W1); else run_stage_forward<C>(G.st[0], p->mesh, p->d_g1, W0, W1, PK, st, &p->launches);       // L1 in W1
     if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_FORWARD); p->lib_launches++; }
-    run_stage_forward<C>(G.st[1], p->mesh, W1, W1, W0, PK, st, &p->launches);            // L3 in W0
+    if (peer) peer_stage_forward(p, 1, W0); else run_stage_forward<C>(G.st[1], p->mesh, W1, W1, W0, PK, st, &p->launches);            // L3 in W0
     if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_FORWARD); p->lib_launches++; }
-    run_stage_forward<C>(G.st[2], p->mesh, W0, W0, W1, PK, st, &p->launches);            // L4 in W1
+    if (peer) peer_stage_forward(p, 2, W1); else run_stage_forward<C>(G.st[2], p->mesh, W0, W0, W1, PK, st, &p->launches);            // L4 in W1
     const long long lno0 = L.local_no[0], lno1 = L.local_no[1];
     if (!L.c2r) {
       if (p->fft_z_fwd) { FftType<R>::exec_c2c(p->fft_z_fwd, W1, CUFFT_FORWARD); p->lib_launches++; }
@@ -449,16 +649,37 @@ template <class R> struct Core {
       box_copy<R>(st, (R *)p->d_grid, (R *)W0, bm, BOX_A2C, false, &p->launches);
       if (p->fft_z_bwd) { FftType<R>::exec_r2c(p->fft_z_bwd, (R *)W0, W1); p->lib_launches++; }
     }
+    const bool peer = p->peer.on;
     // L4 in W1 -> L3 in W0
-    if (L.no[1] < L.n[1]) stage_backward_zero(p, G.st[2], W1, W0, W0, G.L3_elems);
+    if (peer) peer_stage_backward(p, 2, W0, G.L3_elems, L.no[1] < L.n[1]);
+    else if (L.no[1] < L.n[1]) stage_backward_zero(p, G.st[2], W1, W0, W0, G.L3_elems);
     else run_stage_backward<C>(G.st[2], p->mesh, W1, W0, W0, PK, st, &p->launches);
     if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_INVERSE); p->lib_launches++; }
     // L3 in W0 -> L1 in W1
-    if (L.no[0] < L.n[0]) stage_backward_zero(p, G.st[1], W0, W1, W1, G.L1_elems);
+    if (peer) peer_stage_backward(p, 1, W1, G.L1_elems, L.no[0] < L.n[0]);
+    else if (L.no[0] < L.n[0]) stage_backward_zero(p, G.st[1], W0, W1, W1, G.L1_elems);
     else run_stage_backward<C>(G.st[1], p->mesh, W0, W1, W1, PK, st, &p->launches);
     if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_INVERSE); p->lib_launches++; }
     // L1 in W1 -> g1
-    run_stage_backward<C>(G.st[0], p->mesh, W1, W0, p->d_g1, PK, st, &p->launches);
+    if (peer) peer_stage_backward(p, 0, p->d_g1, 0, false);
+    else run_stage_backward<C>(G.st[0], p->mesh, W1, W0, p->d_g1, PK, st, &p->launches);
+  }
+
+  // One re-distribution of the pencil FFT over peer memory: zero what the stage leaves untouched, wait until every rank is
+  // ready to be written to, push my part of every rank's destination array, wait until every rank's pushes have landed.
+  static void peer_stage_forward(P *p, int s, C *dest) {
+    const Stage &S = p->pipe.st[s];
+    if (S.zero_all) PNB_CUDA(cudaMemsetAsync(dest, 0, sizeof(C) * (size_t)S.dst_elems, p->stream));
+    else if (S.zero_len > 0) PNB_CUDA(cudaMemsetAsync(dest + S.zero_off, 0, sizeof(C) * (size_t)S.zero_len, p->stream));
+    peer_barrier(p);
+    peer_jobs<C>(p, LIST_FWD0 + s);
+    peer_barrier(p);
+  }
+  static void peer_stage_backward(P *p, int s, C *out, long long out_elems, bool zero_out) {
+    if (zero_out) PNB_CUDA(cudaMemsetAsync(out, 0, sizeof(C) * (size_t)out_elems, p->stream));
+    peer_barrier(p);
+    peer_jobs<C>(p, LIST_BWD0 - s);
+    peer_barrier(p);
   }
 
   // backward stage whose source-side array has rows outside the pruned output range: they must be zero
@@ -541,6 +762,8 @@ template <class R> struct Core {
   template <class T> static void halo_T(P *p, bool reduce) {
     const Layout &L = p->L;
     const Mesh &M = p->mesh;
+    const bool peer = p->peer.on;
+    bool pushed = false, any_peer = false;     // peer stores in flight that the next step (any axis) must see
     // fill order z, y, x (later axes carry the earlier halos => corners); reduce runs backwards
     for (int k = 0; k < 3; k++) {
       const int axis = reduce ? k : 2 - k;
@@ -552,9 +775,21 @@ template <class R> struct Core {
         hi[t] = wide ? (int)L.ngc[t] : (int)(L.gcb[t] + L.local_no[t]);
       }
       const bool split = axis < 2 && M.np[axis] > 1;
-      if (split) halo_axis_nccl<T>(p, axis, reduce, lo, hi);
-      else halo_axis_local<T>(p, axis, reduce, lo, hi);
+      if (split && peer) {
+        // the neighbours must have finished whatever produced the rows this step reads or overwrites
+        peer_barrier(p);
+        if (!reduce) { peer_jobs<T>(p, axis == 1 ? LIST_FILL1 : LIST_FILL0); pushed = true; }
+        else peer_jobs<T>(p, axis == 0 ? LIST_RED0 : LIST_RED1);
+        any_peer = true;
+      } else {
+        if (pushed) { peer_barrier(p); pushed = false; }
+        if (split) halo_axis_nccl<T>(p, axis, reduce, lo, hi);
+        else halo_axis_local<T>(p, axis, reduce, lo, hi);
+      }
     }
+    // fill: the last pushes must have landed before the gather; reduce: nobody may overwrite a halo (next call) that a
+    // neighbour is still reading
+    if (any_peer) peer_barrier(p);
   }
   static void halo(P *p, bool reduce) {
     if (p->L.c2r) halo_T<R>(p, reduce); else halo_T<C>(p, reduce);
@@ -1158,6 +1393,7 @@ template <class R> struct Core {
     rec(p, 8);
     p->x_via_copy_stream = false;
     PNB_CUDA(cudaStreamSynchronize(st));
+    peer_check(p);
     finish_timers(p, false, ik);
   }
 
@@ -1252,6 +1488,7 @@ template <class R> struct Core {
     if (fh && !fh_dev) PNB_CUDA(cudaMemcpyAsync(p->f_hat, fh, sizeof(C) * nloc, cudaMemcpyDeviceToHost, st));
     rec(p, 8);
     PNB_CUDA(cudaStreamSynchronize(st));
+    peer_check(p);
     finish_timers(p, true, ik);
   }
 

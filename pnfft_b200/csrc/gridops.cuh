@@ -3,6 +3,7 @@
 // (PFFT's pfft_exchange / pfft_reduce, reference call sites kernel/ndft-parallel.c:2558,2679).
 #pragma once
 #include "fftpipe.cuh"
+#include "p2p.cuh"
 
 namespace pnb {
 

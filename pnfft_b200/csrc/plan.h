@@ -139,6 +139,23 @@ struct PipeGeom {
   long long buf_elems;                       // complex elements each work buffer needs
 };
 
+// Peer-memory data plane of a multi-rank plan (p2p.cuh): every other rank's work buffers, padded grid, g1 and flag array
+// as mapped into this process with CUDA IPC, and the device-resident job lists of the exchange stages.
+struct JobList;
+struct PeerPlane {
+  bool on = false;
+  int nranks = 1, rank = 0;
+  std::vector<void *> work[3];     // [rank] base of d_work[k] as mapped here
+  std::vector<void *> grid;        // [rank] padded grid
+  std::vector<void *> g1;          // [rank] compact FFT-input-side array
+  std::vector<int *> flags;        // [rank] flag array (nranks ints)
+  int **d_flag_ptrs = nullptr;     // device copy of flags[]
+  int *d_error = nullptr, *h_error = nullptr;
+  int epoch = 0;
+  JobList *d_jobs = nullptr;       // device job lists (LIST_* in core.cuh)
+  int nblocks[16] = {0};           // blocks of each list (0: nothing to do)
+};
+
 template <class R> struct Nodes;
 
 template <class R> struct Plan {
@@ -177,6 +194,7 @@ template <class R> struct Plan {
   C *d_g1_buffer = nullptr;      // ik differentiation buffer
 
   PipeGeom pipe;
+  PeerPlane peer;
   // FFT plans
   cufftHandle fft_x = 0, fft_y = 0, fft_z_fwd = 0, fft_z_bwd = 0;
   bool fft_ready = false;
