@@ -15,6 +15,29 @@
 
 #include <stddef.h>
 
+/* The stand-in never exports the names of a real MPI library: every entry point is compiled and called as pnb_MPI_*, so
+ * that libpnfft_b200.so can live in a process that also loaded libmpi (no interposition, no clash).  Callers built
+ * against THIS header bind to the prefixed symbols automatically.  A build of the library against a real MPI
+ * (make -C pnfft_b200/csrc REAL_MPI=1 with the MPI compiler wrappers' include path) does not use this header at all. */
+#define MPI_Init pnb_MPI_Init
+#define MPI_Initialized pnb_MPI_Initialized
+#define MPI_Finalize pnb_MPI_Finalize
+#define MPI_Abort pnb_MPI_Abort
+#define MPI_Comm_rank pnb_MPI_Comm_rank
+#define MPI_Comm_size pnb_MPI_Comm_size
+#define MPI_Comm_dup pnb_MPI_Comm_dup
+#define MPI_Comm_free pnb_MPI_Comm_free
+#define MPI_Cart_create pnb_MPI_Cart_create
+#define MPI_Cartdim_get pnb_MPI_Cartdim_get
+#define MPI_Cart_get pnb_MPI_Cart_get
+#define MPI_Cart_coords pnb_MPI_Cart_coords
+#define MPI_Cart_rank pnb_MPI_Cart_rank
+#define MPI_Barrier pnb_MPI_Barrier
+#define MPI_Bcast pnb_MPI_Bcast
+#define MPI_Reduce pnb_MPI_Reduce
+#define MPI_Allreduce pnb_MPI_Allreduce
+#define MPI_Wtime pnb_MPI_Wtime
+
 #ifdef __cplusplus
 extern "C" {
 #endif

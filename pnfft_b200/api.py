@@ -58,7 +58,7 @@ def lib():
             raise RuntimeError("libpnfft_b200.so is missing (%s): build it with `make -C pnfft_b200/csrc`; "
                                "there is no CPU fallback" % LIB_PATH)
         _lib = C.CDLL(LIB_PATH)
-        _lib.MPI_Init(None, None)
+        _lib.pnb_MPI_Init(None, None)
     return _lib
 
 
@@ -76,13 +76,13 @@ def _int3(v):
 
 def mpi_rank_size(comm=MPI_COMM_WORLD):
     r, s = C.c_int(), C.c_int()
-    lib().MPI_Comm_rank(comm, C.byref(r))
-    lib().MPI_Comm_size(comm, C.byref(s))
+    lib().pnb_MPI_Comm_rank(comm, C.byref(r))
+    lib().pnb_MPI_Comm_size(comm, C.byref(s))
     return r.value, s.value
 
 
 def mpi_barrier(comm=MPI_COMM_WORLD):
-    lib().MPI_Barrier(comm)
+    lib().pnb_MPI_Barrier(comm)
 
 
 def create_procmesh_2d(np0, np1, comm=MPI_COMM_WORLD):

@@ -12,10 +12,12 @@
 #include <netdb.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
+#include <poll.h>
 #include <sys/socket.h>
 #include <sys/time.h>
 #include <unistd.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,6 +43,12 @@ struct World {
 [[noreturn]] void die(const char *msg) {
   fprintf(stderr, "pnfft-b200 mini-MPI (rank %d): %s (%s)\n", W.rank, msg, strerror(errno));
   abort();
+}
+
+double now_s() {
+  timeval tv;
+  gettimeofday(&tv, nullptr);
+  return (double)tv.tv_sec + 1e-6 * (double)tv.tv_usec;
 }
 
 int env_int(const char *const *names, int dflt) {
@@ -98,38 +106,84 @@ void combine(void *acc, const void *in, int count, MPI_Datatype t, MPI_Op op) {
   }
 }
 
+// Rank 0 listens on MASTER_ADDR (loopback by default), never on every interface; a peer has to present the job's
+// token (PNFFT_B200_TOKEN, else derived from the launcher's run id / port / world size) before its rank is believed, and
+// neither accept nor the handshake waits for ever.
+uint64_t job_token() {
+  const char *src[] = {getenv("PNFFT_B200_TOKEN"), getenv("TORCHELASTIC_RUN_ID"), getenv("MASTER_PORT"), getenv("WORLD_SIZE")};
+  uint64_t h = 1469598103934665603ull;     // FNV-1a
+  for (const char *s : src) {
+    if (!s) s = "-";
+    for (; *s; s++) { h ^= (unsigned char)*s; h *= 1099511628211ull; }
+    h ^= 0xff; h *= 1099511628211ull;
+  }
+  return h;
+}
+struct Hello { uint32_t magic; int32_t rank; uint64_t token; };
+constexpr uint32_t kMagic = 0x32424e50u;   // "PNB2"
+
+bool recv_timed(int fd, void *buf, size_t n, int timeout_ms) {
+  char *p = (char *)buf;
+  while (n) {
+    pollfd pf{fd, POLLIN, 0};
+    const int r = poll(&pf, 1, timeout_ms);
+    if (r == 0) return false;
+    if (r < 0) { if (errno == EINTR) continue; return false; }
+    ssize_t k = ::recv(fd, p, n, 0);
+    if (k <= 0) { if (k < 0 && errno == EINTR) continue; return false; }
+    p += k; n -= (size_t)k;
+  }
+  return true;
+}
+
 void rendezvous() {
   static const char *port_names[] = {"MASTER_PORT", nullptr};
   static const char *off_names[] = {"PNFFT_B200_PORT_OFFSET", nullptr};
+  static const char *to_names[] = {"PNFFT_B200_RENDEZVOUS_TIMEOUT_S", nullptr};
   const int port = env_int(port_names, 29500) + env_int(off_names, 1007);
+  const int timeout_s = env_int(to_names, 300);
   const char *addr = getenv("MASTER_ADDR");
   if (!addr || !*addr) addr = "127.0.0.1";
   const int one = 1;
+  const uint64_t token = job_token();
+  addrinfo hints{}, *res = nullptr;
+  hints.ai_family = AF_INET; hints.ai_socktype = SOCK_STREAM;
+  char ps[16]; snprintf(ps, sizeof ps, "%d", port);
+  if (getaddrinfo(addr, ps, &hints, &res) != 0 || !res) die("cannot resolve MASTER_ADDR");
   if (W.rank == 0) {
     W.listen_fd = socket(AF_INET, SOCK_STREAM, 0);
     if (W.listen_fd < 0) die("socket");
     setsockopt(W.listen_fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
-    sockaddr_in sa{};
-    sa.sin_family = AF_INET; sa.sin_addr.s_addr = htonl(INADDR_ANY); sa.sin_port = htons((uint16_t)port);
-    if (bind(W.listen_fd, (sockaddr *)&sa, sizeof sa) < 0) die("bind (set PNFFT_B200_PORT_OFFSET to move the rendezvous port)");
-    if (listen(W.listen_fd, W.size) < 0) die("listen");
+    if (bind(W.listen_fd, res->ai_addr, res->ai_addrlen) < 0) {
+      // MASTER_ADDR is not an address of this host (a name that resolves elsewhere): loopback is the safe default
+      sockaddr_in sa{};
+      sa.sin_family = AF_INET; sa.sin_addr.s_addr = htonl(INADDR_LOOPBACK); sa.sin_port = htons((uint16_t)port);
+      if (bind(W.listen_fd, (sockaddr *)&sa, sizeof sa) < 0) die("bind (set PNFFT_B200_PORT_OFFSET to move the rendezvous port)");
+    }
+    freeaddrinfo(res);
+    if (listen(W.listen_fd, W.size + 8) < 0) die("listen");
     W.peer.assign((size_t)W.size, -1);
-    for (int i = 1; i < W.size; i++) {
+    const double t_end = now_s() + timeout_s;
+    for (int have = 1; have < W.size;) {
+      pollfd pf{W.listen_fd, POLLIN, 0};
+      const double left = t_end - now_s();
+      if (left <= 0) die("rendezvous timed out waiting for the other ranks (PNFFT_B200_RENDEZVOUS_TIMEOUT_S)");
+      const int pr = poll(&pf, 1, (int)(left * 1000) + 1);
+      if (pr < 0 && errno == EINTR) continue;
+      if (pr <= 0) continue;
       int fd = accept(W.listen_fd, nullptr, nullptr);
-      if (fd < 0) die("accept");
+      if (fd < 0) continue;
       setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
-      int r = -1;
-      recv_all(fd, &r, sizeof r);
-      if (r <= 0 || r >= W.size || W.peer[(size_t)r] != -1) die("bad rank in rendezvous");
-      W.peer[(size_t)r] = fd;
+      Hello h{};
+      // a stray or foreign connection is dropped, it cannot claim a rank or stall the job
+      if (!recv_timed(fd, &h, sizeof h, 10000) || h.magic != kMagic || h.token != token || h.rank <= 0 || h.rank >= W.size ||
+          W.peer[(size_t)h.rank] != -1) { close(fd); continue; }
+      W.peer[(size_t)h.rank] = fd;
+      have++;
     }
   } else {
-    addrinfo hints{}, *res = nullptr;
-    hints.ai_family = AF_INET; hints.ai_socktype = SOCK_STREAM;
-    char ps[16]; snprintf(ps, sizeof ps, "%d", port);
-    if (getaddrinfo(addr, ps, &hints, &res) != 0 || !res) die("cannot resolve MASTER_ADDR");
     int fd = -1;
-    for (int attempt = 0; attempt < 3000; attempt++) {   // up to ~5 min
+    for (int attempt = 0; attempt < timeout_s * 10; attempt++) {
       fd = socket(AF_INET, SOCK_STREAM, 0);
       if (fd < 0) die("socket");
       if (connect(fd, res->ai_addr, res->ai_addrlen) == 0) break;
@@ -139,7 +193,8 @@ void rendezvous() {
     freeaddrinfo(res);
     if (fd < 0) die("cannot reach rank 0");
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
-    send_all(fd, &W.rank, sizeof W.rank);
+    Hello h{kMagic, (int32_t)W.rank, token};
+    send_all(fd, &h, sizeof h);
     W.peer.assign(1, fd);
   }
 }

@@ -21,7 +21,8 @@ def declared_symbols():
     names = set(re.findall(r"PNX\((\w+)\)\s*\(", body))
     names -= {"plan_s", "nodes_s"}
     plain = set(re.findall(r"^\w[\w\s\*]*?\b(pnfft_b200_\w+)\s*\(", src, flags=re.M))
-    mpi = set(re.findall(r"\b(MPI_\w+)\s*\(", open(os.path.join(ROOT, "include", "mpi.h")).read()))
+    # the stand-in MPI is exported under pnb_MPI_* only (include/mpi.h renames every entry point), never as MPI_*
+    mpi = set("pnb_" + n for n in re.findall(r"^\w[\w\s\*]*?\b(MPI_\w+)\s*\(", open(os.path.join(ROOT, "include", "mpi.h")).read(), flags=re.M))
     mpi |= set(re.findall(r"\b(pfftf?_\w+)\s*\(", open(os.path.join(ROOT, "include", "pfft.h")).read()))
     return names, plain, mpi
 
@@ -33,6 +34,11 @@ def test_library_loads_and_exports_every_declared_symbol():
     missing = [p + n for n in sorted(names) for p in ("pnfft_", "pnfftf_") if not hasattr(lib, p + n)]
     missing += [n for n in sorted(plain | mpi) if not hasattr(lib, n)]
     assert not missing, missing
+    assert len([n for n in mpi if n.startswith("pnb_MPI_")]) >= 18
+    # no name of a real MPI library is exported: the .so can share a process with libmpi
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", A.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert not re.findall(r" T (MPI_\w+)", out)
 
 
 def test_flag_values_match_reference_header():
@@ -59,6 +65,19 @@ def test_single_rank_layout_matches_golden_reference():
         cfg = L[key + "_cfg"]
         N, n, m, c2r = tuple(cfg[0:3]), tuple(cfg[3:6]), int(cfg[6]), bool(cfg[7])
         lN, lNs, lo, up = A.local_size_guru(N, n, tuple(L[key + "_xmax"]), m, comm, c2r=c2r)
+        assert np.array_equal(lN, L[key + "_local_N"][0]) and np.array_equal(lNs, L[key + "_local_N_start"][0])
+        assert np.array_equal(lo, L[key + "_lo"][0]) and np.array_equal(up, L[key + "_up"][0])
+
+
+def test_single_rank_layout_transposed_interlaced():
+    L = np.load(os.path.join(GOLD, "layouts_r2.npz"))
+    comm = A.create_procmesh_2d(1, 1)
+    keys = sorted(k[:-4] for k in L.files if k.endswith("_1x1_c2c_cfg") or k.endswith("_1x1_c2r_cfg"))
+    assert len(keys) == 6
+    for key in keys:
+        cfg = L[key + "_cfg"]
+        N, n, m, c2r, fl = tuple(cfg[0:3]), tuple(cfg[3:6]), int(cfg[6]), bool(cfg[7]), int(cfg[10])
+        lN, lNs, lo, up = A.local_size_guru(N, n, tuple(L[key + "_xmax"]), m, comm, pnfft_flags=fl, c2r=c2r)
         assert np.array_equal(lN, L[key + "_local_N"][0]) and np.array_equal(lNs, L[key + "_local_N_start"][0])
         assert np.array_equal(lo, L[key + "_lo"][0]) and np.array_equal(up, L[key + "_up"][0])
 

@@ -38,12 +38,12 @@ def _worker(rank, world, mesh, port, q):
         # host collectives of the control plane (reference kernel/timer.c:79-86 uses MPI_Reduce(MAX))
         v = (C.c_double * 2)(float(rank + 1), float(-rank))
         o = (C.c_double * 2)()
-        lib.MPI_Allreduce(v, o, 2, 6, 1, comm)      # MPI_DOUBLE, MPI_SUM
+        lib.pnb_MPI_Allreduce(v, o, 2, 6, 1, comm)      # MPI_DOUBLE, MPI_SUM
         assert o[0] == world * (world + 1) / 2 and o[1] == -world * (world - 1) / 2
-        lib.MPI_Allreduce(v, o, 2, 6, 2, comm)      # MPI_MAX
+        lib.pnb_MPI_Allreduce(v, o, 2, 6, 2, comm)      # MPI_MAX
         assert o[0] == world and o[1] == 0
         b = (C.c_int * 1)(1234 if rank == 0 else 0)
-        lib.MPI_Bcast(b, 1, 2, 0, comm)
+        lib.pnb_MPI_Bcast(b, 1, 2, 0, comm)
         assert b[0] == 1234
         L = np.load(os.path.join(GOLD, "layouts.npz"))
         res = []
@@ -56,6 +56,16 @@ def _worker(rank, world, mesh, port, q):
                 ok = (np.array_equal(lN, L[key + "_local_N"][rank]) and np.array_equal(lNs, L[key + "_local_N_start"][rank])
                       and np.array_equal(lo, L[key + "_lo"][rank]) and np.array_equal(up, L[key + "_up"][rank]))
                 res.append(int(ok))
+        L2 = np.load(os.path.join(GOLD, "layouts_r2.npz"))     # PNFFT_TRANSPOSED_F_HAT / PNFFT_INTERLACED blocks
+        for tag in ("tr_even", "tr_ragged", "tr_il_torus"):
+            for c2r in (False, True):
+                key = "%s_%dx%d_%s" % (tag, mesh[0], mesh[1], "c2r" if c2r else "c2c")
+                cfg = L2[key + "_cfg"]
+                N, n, m, fl = tuple(cfg[0:3]), tuple(cfg[3:6]), int(cfg[6]), int(cfg[10])
+                lN, lNs, lo, up = A.local_size_guru(N, n, tuple(L2[key + "_xmax"]), m, comm, pnfft_flags=fl, c2r=c2r)
+                ok = (np.array_equal(lN, L2[key + "_local_N"][rank]) and np.array_equal(lNs, L2[key + "_local_N_start"][rank])
+                      and np.array_equal(lo, L2[key + "_lo"][rank]) and np.array_equal(up, L2[key + "_up"][rank]))
+                res.append(int(ok))
         t = torch.tensor(res, dtype=torch.int32)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         A.mpi_barrier(comm)
@@ -65,7 +75,7 @@ def _worker(rank, world, mesh, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mesh", [(1, 2), (2, 2)])
+@pytest.mark.parametrize("mesh", [(1, 2), (2, 2), (2, 4)])
 def test_layout_and_control_plane_over_ranks(mesh):
     import torch.multiprocessing as mp
     world = mesh[0] * mesh[1]

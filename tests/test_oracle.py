@@ -69,6 +69,22 @@ def test_layout_golden():
             assert np.array_equal(r["lo"], L[key + "_lo"]) and np.array_equal(r["up"], L[key + "_up"]), (name, key)
 
 
+def test_layout_golden_transposed_interlaced():
+    """Round 2: PNFFT_TRANSPOSED_F_HAT blocks (k1 over mesh dim 0, k2 over mesh dim 1, k0 whole) and PNFFT_INTERLACED on a
+    truncated torus, 1x1 .. 2x4 meshes: integers identical, borders bit-identical."""
+    L = np.load(os.path.join(GOLD, "layouts_r2.npz"))
+    keys = sorted(k[:-4] for k in L.files if k.endswith("_cfg"))
+    assert len(keys) == 24
+    for key in keys:
+        cfg = L[key + "_cfg"]
+        N, n, m, c2r, mesh, fl = tuple(cfg[0:3]), tuple(cfg[3:6]), int(cfg[6]), bool(cfg[7]), (int(cfg[8]), int(cfg[9])), int(cfg[10])
+        for name, impl in _impls(False):
+            r = impl.layout(N, n, m=m, np_mesh=mesh, x_max=tuple(L[key + "_xmax"]), c2r=c2r, pnfft_flags=fl)
+            for k in ("local_N", "local_N_start", "local_no", "local_no_start"):
+                assert np.array_equal(r[k], L[key + "_" + k]), (name, key, k)
+            assert np.array_equal(r["lo"], L[key + "_lo"]) and np.array_equal(r["up"], L[key + "_up"]), (name, key)
+
+
 def test_node_index_golden():
     """node -> rank ownership, local grid index u_j and plain index m0, and the sort key: bit-exact."""
     g = np.load(os.path.join(GOLD, "node_index.npz"))

@@ -150,6 +150,21 @@ def main():
                     lay[key + "_" + k] = L[k]
                 lay[key + "_no"] = np.array(L["no"])
     np.savez_compressed(os.path.join(out, "layouts.npz"), **lay)
+    # round 2: the same with PNFFT_TRANSPOSED_F_HAT and PNFFT_INTERLACED (one more ghost cell above does not move a border)
+    lay = {}
+    for mesh in [(1, 1), (1, 2), (2, 2), (2, 4)]:
+        for tag, N, n, xm, fl in [("tr_even", (16, 16, 16), (32, 32, 32), (0.5, 0.5, 0.5), TRANSPOSED),
+                                  ("tr_ragged", (20, 12, 16), (48, 26, 32), (0.5, 0.5, 0.5), TRANSPOSED),
+                                  ("tr_il_torus", (16, 16, 16), (32, 32, 32), (0.3, 0.25, 0.5), TRANSPOSED | INTERLACED)]:
+            for c2r in (False, True):
+                L = ref.layout(N, n, m=4, np_mesh=mesh, x_max=xm, c2r=c2r, pnfft_flags=fl)
+                key = "%s_%dx%d_%s" % (tag, mesh[0], mesh[1], "c2r" if c2r else "c2c")
+                lay[key + "_cfg"] = np.array(list(N) + list(n) + [4, int(c2r)] + list(mesh) + [fl], np.int64)
+                lay[key + "_xmax"] = np.array(xm)
+                for k in ("local_N", "local_N_start", "local_no", "local_no_start", "lo", "up"):
+                    lay[key + "_" + k] = L[k]
+                lay[key + "_no"] = np.array(L["no"])
+    np.savez_compressed(os.path.join(out, "layouts_r2.npz"), **lay)
     rng = np.random.default_rng(7)
     N, M = (16, 16, 16), 4000
     x = np.clip(rng.uniform(-0.5, 0.5, (M, 3)), -0.5, np.nextafter(0.5, 0))
