@@ -459,7 +459,7 @@ void PNX(b200_window_tensor)(PNX(plan) ths, PNX(nodes) nodes, RT *psi, RT *dpsi)
 
 // variant bit 0: generic global-memory kernels; bit 1: exact window evaluation instead of the fitted polynomials;
 // 8: z-march v1 (CTA-synchronous) instead of the warp-autonomous v2
-void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant) { AS_PLAN(ths)->kernel_variant = variant & 9; AS_PLAN(ths)->use_poly = (variant & 2) ? 0 : 1; }
+void PNX(b200_set_kernel_variant)(PNX(plan) ths, int variant) { AS_PLAN(ths)->kernel_variant = variant & 13; AS_PLAN(ths)->use_poly = (variant & 2) ? 0 : 1; }
 // "the node coordinates will not change until I call pnfft_set_x again": the upload of x and its binning are reused by
 // every following pnfft_trafo / pnfft_adj on these nodes (the reference re-reads x every call, api/api-basic.c:199-244)
 void PNX(b200_nodes_x_static)(PNX(nodes) nodes, int on) {

@@ -6,7 +6,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "zmarch2.cuh"
+#include "zmarch3.cuh"
 #include "gridops.cuh"
 
 namespace pnb {
@@ -854,6 +854,12 @@ template <class R> struct Core {
     if (kv == 8 || m == 8) return 0;
     return 2;
   }
+  // family 2 in double runs its node loops on the FP64 tensor cores (zmarch3.cuh) unless variant bit 4 or
+  // PNFFT_B200_NO_MMA=1 asks for the DFMA loops of zmarch2.cuh (kept for single precision and for comparison)
+  template <int M_> static bool use_mma(const P *p) {
+    static const bool off = getenv("PNFFT_B200_NO_MMA") && atoi(getenv("PNFFT_B200_NO_MMA")) != 0;
+    return sizeof(R) == 8 && Zm3Ok<M_>::value && !off && !(p->kernel_variant & 4);
+  }
   static TileGeom tile_geom(const P *p, bool *tiled_ok) {
     TileGeom tg;
     const int m = p->L.m;
@@ -974,7 +980,10 @@ template <class R> struct Core {
       const TileGeom tg = tile_geom(p, nullptr);
       const GridGeom<R> g = geom(p);
       typedef typename CellT<R, CPLX>::type Cell;
-      const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::XW, 16, Cfg::ZB, zm2_swizzle_mode<Cell, Cfg::ZB>());
+      // double, cutoffs with a whole-k-step window: the tensor-core node loops (zmarch3.cuh); their staging boxes are
+      // read / written 256 contiguous bytes per n-block, so the tensor map needs no swizzle
+      const bool mma = use_mma<M_>(p);
+      const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::XW, 16, Cfg::ZB, mma ? 0 : zm2_swizzle_mode<Cell, Cfg::ZB>());
       Zm2Geom zg;
       zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2];
       // whole columns per work item when there are enough columns to fill the GPU, else split along z
@@ -1036,9 +1045,21 @@ template <class R> struct Core {
           if (p->b_phase & 2) {
             GatherOut<R> out;
             out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
-            auto kern = k_gather_zm2<R, CPLX, M_, GRAD>;
-            PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
-            kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
+            bool done = false;
+            if constexpr (sizeof(R) == 8 && Zm3Ok<M_>::value) {
+              if (mma) {
+                typedef Zm3Smem<CPLX, M_, GRAD> Sm3;
+                auto kern = k_gather_mma<CPLX, M_, GRAD>;
+                PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm3::gather));
+                kern<<<nblk, (Cfg::NCW + 2) * 32, Sm3::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
+                done = true;
+              }
+            }
+            if (!done) {
+              auto kern = k_gather_zm2<R, CPLX, M_, GRAD>;
+              PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
+              kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
+            }
             p->launches++;
           }
         } else {
@@ -1046,9 +1067,21 @@ template <class R> struct Core {
           const size_t tsm = (size_t)kZm2TabNodes * RowS::ROWBYTES + psm;
           PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
           kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, nb_args, tab, first);
-          auto kern = k_scatter_zm2<R, CPLX, M_, GRAD>;
-          PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
-          kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::scatter, p->stream>>>(tm, zg, tab, nd->d_tile_start);
+          bool done = false;
+          if constexpr (sizeof(R) == 8 && Zm3Ok<M_>::value) {
+            if (mma) {
+              typedef Zm3Smem<CPLX, M_, GRAD> Sm3;
+              auto kern = k_scatter_mma<CPLX, M_, GRAD>;
+              PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm3::scatter));
+              kern<<<nblk, (Cfg::NCW + 1) * 32, Sm3::scatter, p->stream>>>(tm, zg, tab, nd->d_tile_start);
+              done = true;
+            }
+          }
+          if (!done) {
+            auto kern = k_scatter_zm2<R, CPLX, M_, GRAD>;
+            PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
+            kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::scatter, p->stream>>>(tm, zg, tab, nd->d_tile_start);
+          }
           p->launches += 2;
         }
       }
