@@ -1051,7 +1051,7 @@ template <class R> struct Core {
                 typedef Zm3Smem<CPLX, M_, GRAD> Sm3;
                 auto kern = k_gather_mma<CPLX, M_, GRAD>;
                 PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm3::gather));
-                kern<<<nblk, (Cfg::NCW + 2) * 32, Sm3::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
+                kern<<<nblk, (Cfg::NCW + 1) * 32, Sm3::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
                 done = true;
               }
             }

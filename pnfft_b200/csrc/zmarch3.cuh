@@ -27,8 +27,25 @@ namespace pnb {
 
 template <int M_> struct Zm3Ok { static constexpr bool value = (M_ == 6); };
 
+#ifdef ZM3_DBG_NOEPI      // timing experiment only (wrong results): the MMAs stay, the x-y contraction goes
+#define ZM3_ASM asm volatile
+#else
+#define ZM3_ASM asm
+#endif
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+  ZM3_ASM("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// non-blocking phase test (the service warp polls two pipelines)
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned phase) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  return __any_sync(0xffffffffu, ok != 0);
 }
 
 template <bool CPLX, int M_, bool GRAD> struct Zm3Smem {
@@ -40,7 +57,16 @@ template <bool CPLX, int M_, bool GRAD> struct Zm3Smem {
   static constexpr int WARP_BOX = Cfg::XW * 16 * Cfg::ZS * CELLB;          // bytes one warp stages per window advance
   static constexpr int NVAL = NCOMP * (GRAD ? 4 : 1);                      // output values per node
   // gather: one staging box per warp, ring of S stages of GB nodes, P stages of per-warp partial outputs
-  static constexpr int GS = 4, GP = 3, GGB = 32;
+#ifndef ZM3_GP
+#define ZM3_GP 3
+#endif
+#ifndef ZM3_GS
+#define ZM3_GS 4
+#endif
+#ifndef ZM3_GGB
+#define ZM3_GGB 32
+#endif
+  static constexpr int GS = ZM3_GS, GP = ZM3_GP, GGB = ZM3_GGB;
   static constexpr int g_stage = kZm2HdrBytes + GGB * RowG::ROWBYTES;
   static constexpr int g_off_ring = Cfg::NCW * WARP_BOX;
   static constexpr int g_off_part = g_off_ring + GS * g_stage;
@@ -66,7 +92,7 @@ template <bool CPLX, int M_, bool GRAD> struct Zm3Smem {
 // A fragment of slot s: z weight 4 q + t of node g of the batch, q = (s - cur) mod KS the chunk's place in the window.
 // C fragment: node g, columns 2t, 2t+1 of the n-block = one complex partial sum (two real ones) per lane.
 template <bool CPLX, int M_, bool GRAD>
-__global__ void __launch_bounds__((Zm2Cfg<M_>::NCW + 2) * 32, 1)
+__global__ void __launch_bounds__((Zm2Cfg<M_>::NCW + 1) * 32, 1)
 k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double *__restrict__ tab, const int *__restrict__ bin_start,
              GatherOut<double> out) {
   typedef Zm2Cfg<M_> Cfg;
@@ -105,39 +131,79 @@ k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double 
   __syncthreads();
 
   if (warp == NCW) {
-    zm2_produce<T0, Cfg::SUB, S, GB, ROWBYTES, STAGE, 1>(ring, full, empty, reinterpret_cast<const unsigned char *>(tab), bs, tz0, tz1, lane);
-    return;
-  }
-
-  if (warp == NCW + 1) {
-    // ---- reducer warp: sums the partial outputs of the warps that met a node, in warp order, and writes the node out ----
-    constexpr int NPP = 32 / NVAL;                 // nodes per pass
+    // ---- service warp: feeds the node ring (zm2_produce as a resumable state machine) and, between two stages, sums the
+    // partial outputs of the stages the consumers have finished: per node the warps that met it, in warp order ----
+    constexpr int NPP = 32 / NVAL;                 // nodes per reduction pass
     const int sub = lane / NVAL, v = lane - sub * NVAL;
-    for (int kb = 0;; kb++) {
-      const int st = kb % S, ps = kb % P;
-      mbar_wait_park(&full[st], ((unsigned)(kb / S)) & 1u);
-      const unsigned char *sp = ring + (size_t)st * STAGE;
-      const int *h = reinterpret_cast<const int *>(sp);
-      if (h[0] == INT_MAX) break;
-      const int cnt = h[1];
-      mbar_wait_park(&pfull[ps], ((unsigned)(kb / P)) & 1u, 100u);
-      const double *pp = part + (size_t)ps * (Sm::g_part_stage / 8);
-      for (int i0 = 0; i0 < cnt; i0 += NPP) {
-        const int i = i0 + sub;
-        if (i < cnt) {
-          const int *hd = reinterpret_cast<const int *>(sp + kZm2HdrBytes + (size_t)i * ROWBYTES);
-          const int dx = hd[3], j = hd[4];
-          const int wlo = dx / XW, whi = min(NCW - 1, (dx + C - 1) / XW);
-          double s = 0;
-          for (int w = wlo; w <= whi; w++) s += pp[((size_t)w * GB + i) * NVAL + v];
-          double *o = nullptr;
-          if (v < NCOMP) { if (out.f) o = out.f + ((size_t)j * out.f_stride + out.f_off) * NCOMP + v; }
-          else if (GRAD) o = out.grad + (size_t)j * 3 * NCOMP + (v - NCOMP);
-          if (o) *o = out.accumulate ? *o + s : s;
+    const unsigned char *tabb = reinterpret_cast<const unsigned char *>(tab);
+    int ptz = tz0 - 1, c0 = 0, e = 0, kbp = 0, kbr = 0, nreal = 0, gs = 0;
+    int gs_next = (lane <= T0) ? bs[(size_t)tz0 * Cfg::SUB + lane] : 0;
+    bool at_end = false, pdone = false;
+    for (;;) {
+      bool did = false;
+      if (!pdone) {
+        while (!at_end && c0 >= e) {               // next z sub-chunk with nodes
+          ptz++;
+          if (ptz >= tz1) { at_end = true; break; }
+          gs = gs_next;
+          if (ptz + 1 < tz1) gs_next = (lane <= T0) ? bs[(size_t)(ptz + 1) * Cfg::SUB + lane] : 0;
+          c0 = __shfl_sync(0xffffffffu, gs, 0);
+          e = __shfl_sync(0xffffffffu, gs, T0);
+        }
+        const int st = kbp % S;
+        if (mbar_test(&empty[st], (((unsigned)(kbp / S)) & 1u) ^ 1u)) {
+          unsigned char *sp = ring + (size_t)st * STAGE;
+          int *h = reinterpret_cast<int *>(sp);
+          if (at_end) {
+            if (lane == 0) { h[0] = INT_MAX; h[1] = 0; mbar_arrive(&full[st]); }
+            pdone = true;
+          } else {
+            const int cnt = min(GB, e - c0);
+            if (lane <= T0) h[4 + lane] = min(max(gs - c0, 0), cnt);
+            if (lane == 0) { h[0] = ptz; h[1] = cnt; h[2] = c0; h[3] = 0; }
+            __syncwarp();
+            if (lane == 0) {
+              const unsigned bytes = (unsigned)(cnt * ROWBYTES);
+              mbar_expect_tx(&full[st], bytes);
+              bulk_load_1d(sp + kZm2HdrBytes, tabb + (size_t)c0 * ROWBYTES, bytes, &full[st]);
+            }
+            c0 += GB;
+            nreal++;
+          }
+          kbp++;
+          did = true;
+          __syncwarp();
         }
       }
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(&pempty[ps]); mbar_arrive(&empty[st]); }
+      if (kbr < nreal) {
+        const int st = kbr % S, ps = kbr % P;
+        if (mbar_test(&pfull[ps], ((unsigned)(kbr / P)) & 1u)) {
+          mbar_wait(&full[st], ((unsigned)(kbr / S)) & 1u);     // passed long ago: orders my reads behind the bulk copy
+          const unsigned char *sp = ring + (size_t)st * STAGE;
+          const int cnt = reinterpret_cast<const int *>(sp)[1];
+          const double *pp = part + (size_t)ps * (Sm::g_part_stage / 8);
+          for (int i0 = 0; i0 < cnt; i0 += NPP) {
+            const int i = i0 + sub;
+            if (i < cnt) {
+              const int *hd = reinterpret_cast<const int *>(sp + kZm2HdrBytes + (size_t)i * ROWBYTES);
+              const int dx = hd[3], j = hd[4];
+              const int wlo = dx / XW, whi = min(NCW - 1, (dx + C - 1) / XW);
+              double sum = 0;
+              for (int w = wlo; w <= whi; w++) sum += pp[((size_t)w * GB + i) * NVAL + v];
+              double *o = nullptr;
+              if (v < NCOMP) { if (out.f) o = out.f + ((size_t)j * out.f_stride + out.f_off) * NCOMP + v; }
+              else if (GRAD) o = out.grad + (size_t)j * 3 * NCOMP + (v - NCOMP);
+              if (o) *o = out.accumulate ? *o + sum : sum;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&pempty[ps]); mbar_arrive(&empty[st]); }
+          kbr++;
+          did = true;
+        }
+      }
+      if (pdone && kbr == nreal) break;
+      if (!did) __nanosleep(64);
     }
     return;
   }
@@ -205,33 +271,50 @@ k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double 
     issue(cur + KS);
   };
 
+#ifdef ZM2_TIMING
+  long long tq[6] = {0, 0, 0, 0, 0, 0}, tc = clock64(), tit = 0, itsum = 0, itn = 0, itmin = 1LL << 40;
+#endif
   for (int kb = 0;; kb++) {
     const int st = kb % S, ps = kb % P;
+    ZM2_T(5);
     mbar_wait_park(&full[st], ((unsigned)(kb / S)) & 1u);
+    ZM2_T(0);
     const unsigned char *sp = ring + (size_t)st * STAGE;
     const int *h = reinterpret_cast<const int *>(sp);
     const int tz = h[0];
     if (tz == INT_MAX) break;
     const int lo = h[4 + dxlo], hi = h[4 + dxhi1];
     mbar_wait_park(&pempty[ps], (((unsigned)(kb / P)) & 1u) ^ 1u);
+    ZM2_T(1);
     if (hi > lo) {
       if (tz != cur) {
         if (pending && tz == cur + 1) advance1();
         else if (pending && tz == cur + 2) { advance1(); advance1(); }
         else reload(tz);
       }
+      ZM2_T(2);
       double *pw = part + (size_t)ps * (Sm::g_part_stage / 8) + (size_t)warp * GB * NVAL;
-      for (int b0 = lo; b0 < hi; b0 += 8) {
+      // A fragments (z weights of node g of the batch) are fetched one batch ahead
+      auto load_a = [&](int b0, const unsigned char *&row, int4 &hd, double (&az)[KS], double (&adz)[KS]) {
         const int i = min(b0 + g, hi - 1);
-        const unsigned char *row = sp + kZm2HdrBytes + (size_t)i * ROWBYTES;
-        const int4 hd = *reinterpret_cast<const int4 *>(row);       // {-dx*8, -dy*8, dz, dx}
-        double az[KS], adz[KS];
+        row = sp + kZm2HdrBytes + (size_t)i * ROWBYTES;
+        hd = *reinterpret_cast<const int4 *>(row);       // {-dx*8, -dy*8, dz, dx}
 #pragma unroll
         for (int s = 0; s < KS; s++) {
           const int q = (s - rot + KS) % KS;
           az[s] = *reinterpret_cast<const double *>(row + (Row::oZ + 4 * q + t) * 8);
           if (GRAD) adz[s] = *reinterpret_cast<const double *>(row + (Row::oDZ + 4 * q + t) * 8);
         }
+      };
+      const unsigned char *row, *row_n;
+      int4 hd, hd_n;
+      double az[KS], adz[KS], az_n[KS], adz_n[KS];
+      load_a(lo, row, hd, az, adz);
+      for (int b0 = lo; b0 < hi; b0 += 8) {
+#ifdef ZM2_TIMING
+        { const long long now_ = clock64(); if (b0 > lo) { const long long d_ = now_ - tit; itsum += d_; itn++; if (d_ < itmin) itmin = d_; } tit = now_; }
+#endif
+        load_a(b0 + 8, row_n, hd_n, az_n, adz_n);
         double wx[XW], dwx[XW], wy[4], dwy[4];
 #pragma unroll
         for (int e = 0; e < XW; e++) {
@@ -261,6 +344,10 @@ k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double 
               dmma884(cp, az[s], win[nb][s]);
               if (GRAD) dmma884(cd, adz[s], win[nb][s]);
             }
+#ifdef ZM3_DBG_NOEPI
+            a[0] += cp[0];
+            if (false)
+#endif
             if constexpr (CPLX) {
               a[0] = fma(wy[jy], cp[0], a[0]); a[1] = fma(wy[jy], cp[1], a[1]);
               if (GRAD) {
@@ -317,11 +404,24 @@ k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double 
           k += shfl_xor(k, 1);
           if (b0 + g < hi && t == 0) pw[(size_t)(b0 + g) * NVAL] = k;
         }
+        row = row_n; hd = hd_n;
+#pragma unroll
+        for (int s = 0; s < KS; s++) { az[s] = az_n[s]; if (GRAD) adz[s] = adz_n[s]; }
       }
     }
+    ZM2_T(3);
     __syncwarp();
     if (lane == 0) { mbar_arrive(&pfull[ps]); mbar_arrive(&empty[st]); }
+    ZM2_T(4);
   }
+#ifdef ZM2_TIMING
+  if (lane == 0 && g_zm2_timing) {
+    for (int i = 0; i < 6; i++) atomicAdd((unsigned long long *)&g_zm2_timing[warp * 6 + i], (unsigned long long)tq[i]);
+    atomicAdd((unsigned long long *)&g_zm2_timing[72 + warp * 2], (unsigned long long)itsum);
+    atomicAdd((unsigned long long *)&g_zm2_timing[72 + warp * 2 + 1], (unsigned long long)itn);
+    atomicMin((long long *)&g_zm2_timing[96 + warp], itmin);
+  }
+#endif
   drop_pending();    // no TMA write may still be in flight when the CTA retires
 }
 
@@ -438,12 +538,12 @@ k_scatter_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
       int offA[NZB];
 #pragma unroll
       for (int zb = 0; zb < NZB; zb++) offA[zb] = (Row::oZ + ((8 * zb + g - cur * ZS) & (W - 1))) * 8;
-      for (int b0 = lo; b0 < hi; b0 += 4) {
+      // operands of one batch: z weight fragments and the amplitude of node t in each of my columns
+      auto prep = [&](int b0, double (&az)[NZB], double (&adz)[NZB], double (&bA)[NB], double (&bB)[NB]) {
         const bool valid = b0 + t < hi;
         const int i = min(b0 + t, hi - 1);
         const unsigned char *row = sp + kZm2HdrBytes + (size_t)i * ROWBYTES;
         const int4 hd = *reinterpret_cast<const int4 *>(row);       // {-dx*8, -dy*8, dz, dx}
-        double az[NZB], adz[NZB];
 #pragma unroll
         for (int zb = 0; zb < NZB; zb++) {
           az[zb] = *reinterpret_cast<const double *>(row + offA[zb]);
@@ -480,17 +580,28 @@ k_scatter_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
 #pragma unroll
           for (int x = 0; x < XW; x++) {
             const int nb = x * NYB + jy;
-            double bA = w1 * ax[x];
-            if (GRAD) bA = fma(dw1, bx[x], bA);
-#pragma unroll
-            for (int zb = 0; zb < NZB; zb++) dmma884(acc[nb][zb], az[zb], bA);
-            if (GRAD) {
-              const double bB = w1 * cxw[x];
-#pragma unroll
-              for (int zb = 0; zb < NZB; zb++) dmma884(acc[nb][zb], adz[zb], bB);
-            }
+            bA[nb] = w1 * ax[x];
+            if (GRAD) { bA[nb] = fma(dw1, bx[x], bA[nb]); bB[nb] = w1 * cxw[x]; }
           }
         }
+      };
+      double az[NZB], adz[NZB], bA[NB], bB[NB], az_n[NZB], adz_n[NZB], bA_n[NB], bB_n[NB];
+      prep(lo, az, adz, bA, bB);
+      for (int b0 = lo; b0 < hi; b0 += 4) {
+        prep(b0 + 4, az_n, adz_n, bA_n, bB_n);        // the next batch's operands build while this batch's MMAs run
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) {
+#pragma unroll
+          for (int zb = 0; zb < NZB; zb++) dmma884(acc[nb][zb], az[zb], bA[nb]);
+          if (GRAD) {
+#pragma unroll
+            for (int zb = 0; zb < NZB; zb++) dmma884(acc[nb][zb], adz[zb], bB[nb]);
+          }
+        }
+#pragma unroll
+        for (int zb = 0; zb < NZB; zb++) { az[zb] = az_n[zb]; if (GRAD) adz[zb] = adz_n[zb]; }
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) { bA[nb] = bA_n[nb]; if (GRAD) bB[nb] = bB_n[nb]; }
       }
       dirty = Cfg::NFL;
     }
