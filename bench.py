@@ -92,6 +92,9 @@ def config_dict(w, world, extra=None):
         "process_mesh": "%dx%d" % mesh, "window": w["window"], "precision": "single" if w["single"] else "double",
         "cache": "inputs larger than L2 (padded grid %.2f GB + nodes %.2f GB per rank vs 126 MB L2); no flush needed"
                  % (grid_gb, w["M_total"] / world * node_b / 1e9),
+        "nodes_per_step": ("fixed (PNFFT_PRE_PSI tables belong to one set of coordinates)" if w["pre_psi"] else
+                           "new coordinates every step (two node sets alternate, pnfft_set_x per step): upload, binning and "
+                           "window table are redone in every pnfft_trafo; pnfft_adj of the same step reuses them"),
     }
     if extra:
         c.update(extra)
@@ -332,8 +335,14 @@ def run_gpu(args):
     h_fhat_out = pinned(h_fhat_in.shape, tdt)
     fshape, gshape = ((M, NC) if NC == 2 else (M,)), ((M, 3, NC) if NC == 2 else (M, 3))
     hf, hg = pinned(fshape, tdt), pinned(gshape, tdt)
+    # a second set of coordinates (the same nodes in reverse order): the timed loops alternate between the two, so that
+    # every step meets coordinates the library has not seen in the previous call (nothing derived from x - upload, bins,
+    # window table - survives from step to step; pnfft_adj may reuse what pnfft_trafo of the SAME step derived)
+    hx2 = pinned((max(M, 1), 3), tdt)[:M]
+    hx2.numpy()[...] = hx.numpy()[::-1]
     # ---- device-resident twins ----
     dx, d_fhat_in = hx.to(dev), h_fhat_in.to(dev)
+    dx2 = hx2.to(dev)
     d_fhat_out = torch.zeros_like(d_fhat_in)
     df = torch.zeros(fshape, dtype=tdt, device=dev)
     dg = torch.zeros(gshape, dtype=tdt, device=dev)
@@ -347,7 +356,9 @@ def run_gpu(args):
     CF_T, CF_A = w["cf_trafo"], w["cf_adj"]
     stream = torch.cuda.ExternalStream(plan.stream(), device=dev)
 
-    def step(nodes, f_in, f_out):
+    def step(nodes, f_in, f_out, x=None):
+        if x is not None:
+            nodes.set_x(x)
         plan.set_f_hat(f_in)
         plan.trafo(nodes, CF_T)
         st_t = plan.stage_ms(False)
@@ -361,14 +372,14 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nodes, f_in, f_out, k):
+    def timed(nodes, f_in, f_out, k, xs=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stages = []
         barrier()
         t0 = time.time()
         e0.record(stream)
-        for _ in range(k):
-            stages.append(step(nodes, f_in, f_out))
+        for i in range(k):
+            stages.append(step(nodes, f_in, f_out, None if xs is None else xs[i % 2]))
         e1.record(stream)
         barrier()
         t1 = time.time()
@@ -384,16 +395,25 @@ def run_gpu(args):
         pass
     clocks = Clocks(uuid) if rank == 0 else None
 
-    for _ in range(warm):
-        step(nd_dev, d_fhat_in, d_fhat_out)
+    pre = bool(w["pre_psi"])       # PNFFT_PRE_PSI tables belong to ONE set of coordinates: those runs keep x fixed
+    for i in range(warm):
+        step(nd_dev, d_fhat_in, d_fhat_out, None if pre else (dx, dx2)[i % 2])
     l0, c0 = plan.kernel_launches(), plan.library_calls()
-    ms_dev, stages, win = timed(nd_dev, d_fhat_in, d_fhat_out, steps)
+    ms_dev, stages, win = timed(nd_dev, d_fhat_in, d_fhat_out, steps, None if pre else (dx, dx2))
     l1, c1 = plan.kernel_launches(), plan.library_calls()
+    # the same loop on unchanged coordinates (an iterative solver): bins and window table of the first call serve all others
+    if not pre:
+        nd_dev.set_x(dx)
     for _ in range(2):
-        step(nd_host, h_fhat_in, h_fhat_out)
-    ms_e2e, stages_e2e, _ = timed(nd_host, h_fhat_in, h_fhat_out, steps)
+        step(nd_dev, d_fhat_in, d_fhat_out)
+    ms_dev_static, _, _ = timed(nd_dev, d_fhat_in, d_fhat_out, steps)
+    for i in range(2):
+        step(nd_host, h_fhat_in, h_fhat_out, None if pre else (hx, hx2)[i % 2])
+    ms_e2e, stages_e2e, _ = timed(nd_host, h_fhat_in, h_fhat_out, steps, None if pre else (hx, hx2))
     # the same end-to-end step when the caller promises unchanged coordinates (pnfft_b200_nodes_x_static): x is uploaded
     # and binned once, not twice per step
+    if not pre:
+        nd_host.set_x(hx)
     nd_host.x_static(True)
     for _ in range(2):
         step(nd_host, h_fhat_in, h_fhat_out)
@@ -464,7 +484,8 @@ def run_gpu(args):
         "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac_hbm"]},
         "algorithmic": "flops/node: gather F+grad 16*(2m+1)^3, gather / scatter F 4*(2m+1)^3 (c2c; r2r half); bytes: grid "
                        "block once + x,f[,grad_f] once (SURVEY.md 8d); the kernel time of the slowest rank against the "
-                       "node count of the fullest rank; kernel ms include the node-table kernel",
+                       "node count of the fullest rank; kernel ms include the node-table kernel of the call "
+                       "(new coordinates every step: pnfft_trafo builds the table, pnfft_adj of the same step reuses it)",
         "kernels": kern,
         "gridding_roofline_ms_per_step": sum(k["roofline_ms"] for k in kern.values()),
         "gridding_measured_ms_per_step": sum(k["ms"] for k in kern.values()),
@@ -487,6 +508,9 @@ def run_gpu(args):
         "config": config_dict(w, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
                 "ms_per_step": ms_e2e / steps},
+        "value_x_static": {"value": M_total / (ms_dev_static * 1e-3 / steps), "unit": UNIT, "ms_per_step": ms_dev_static / steps,
+                           "note": "device-resident loop on UNCHANGED coordinates (content hash): bins and window table of the "
+                                   "first call serve every later trafo / adj"},
         "e2e_x_static": {"value": M_total / (ms_e2e_static * 1e-3 / steps), "unit": UNIT, "ms_per_step": ms_e2e_static / steps,
                          "h2d_bytes_per_step": int(tot[0].item()) - world * int(hx.numel() * rb * 2),
                          "note": "same step with pnfft_b200_nodes_x_static(nodes, 1): coordinates uploaded and binned once"},

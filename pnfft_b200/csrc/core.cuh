@@ -337,7 +337,7 @@ template <class R> struct Core {
     for (int i = 0; i < 16; i++) PNB_CUDA(cudaEventCreate(&p->ev[i]));
     PNB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     PNB_CUDA(cudaStreamCreateWithFlags(&p->node_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) PNB_CUDA(cudaEventCreateWithFlags(&p->ev_copy[i], cudaEventDisableTiming));
+    for (int i = 0; i < 3; i++) PNB_CUDA(cudaEventCreateWithFlags(&p->ev_copy[i], cudaEventDisableTiming));
     memset(p->timer_trafo, 0, sizeof p->timer_trafo);
     memset(p->timer_adj, 0, sizeof p->timer_adj);
     memset(p->stage_ms, 0, sizeof p->stage_ms);
@@ -595,7 +595,7 @@ template <class R> struct Core {
     cudaStreamDestroy(p->stream);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->node_stream) cudaStreamDestroy(p->node_stream);
-    for (int i = 0; i < 2; i++) if (p->ev_copy[i]) cudaEventDestroy(p->ev_copy[i]);
+    for (int i = 0; i < 3; i++) if (p->ev_copy[i]) cudaEventDestroy(p->ev_copy[i]);
     MPI_Comm_free(&p->comm);
     delete p;
   }
@@ -817,11 +817,11 @@ template <class R> struct Core {
     if ((flags & N_MALLOC_F) && nd->f) { if (is_device_ptr(nd->f)) cudaFree(nd->f); else cudaFreeHost(nd->f); }
     if ((flags & N_MALLOC_GRAD_F) && nd->grad_f) { if (is_device_ptr(nd->grad_f)) cudaFree(nd->grad_f); else cudaFreeHost(nd->grad_f); }
     if ((flags & N_MALLOC_HESSIAN_F) && nd->hessian_f) cudaFreeHost(nd->hessian_f);
-    cudaFree(nd->d_x); cudaFree(nd->d_f); cudaFree(nd->d_grad_f); cudaFree(nd->d_wtab);
+    cudaFree(nd->d_x); cudaFree(nd->d_f); cudaFree(nd->d_grad_f); cudaFree(nd->d_wtab); cudaFree(nd->d_vals);
     for (int k = 0; k < 2; k++) {
       BinState<R> &b = k ? nd->il : *static_cast<BinState<R> *>(nd);
       cudaFree(b.d_tile); cudaFree(b.d_tile_sorted); cudaFree(b.d_perm); cudaFree(b.d_idx);
-      cudaFree(b.d_tile_count); cudaFree(b.d_tile_start); cudaFree(b.d_pre_psi); cudaFree(b.d_pre_dpsi);
+      cudaFree(b.d_tile_count); cudaFree(b.d_tile_start); cudaFree(b.d_pre_psi); cudaFree(b.d_pre_dpsi); cudaFree(b.d_rows);
       if (b.h_maxcol) { cudaFreeHost(b.h_maxcol); cudaFree(b.d_maxcol); }
     }
     if (nd->h_hash) { cudaFreeHost(nd->h_hash); cudaFree(nd->d_hash); }
@@ -980,10 +980,7 @@ template <class R> struct Core {
       const TileGeom tg = tile_geom(p, nullptr);
       const GridGeom<R> g = geom(p);
       typedef typename CellT<R, CPLX>::type Cell;
-      // double, cutoffs with a whole-k-step window: the tensor-core node loops (zmarch3.cuh); their staging boxes are
-      // read / written 256 contiguous bytes per n-block, so the tensor map needs no swizzle
-      const bool mma = use_mma<M_>(p);
-      const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::XW, 16, Cfg::ZB, mma ? 0 : zm2_swizzle_mode<Cell, Cfg::ZB>());
+      const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::XW, 16, Cfg::ZB, zm2_swizzle_mode<Cell, Cfg::ZB>());
       Zm2Geom zg;
       zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2];
       // whole columns per work item when there are enough columns to fill the GPU, else split along z
@@ -1045,21 +1042,9 @@ template <class R> struct Core {
           if (p->b_phase & 2) {
             GatherOut<R> out;
             out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
-            bool done = false;
-            if constexpr (sizeof(R) == 8 && Zm3Ok<M_>::value) {
-              if (mma) {
-                typedef Zm3Smem<CPLX, M_, GRAD> Sm3;
-                auto kern = k_gather_mma<CPLX, M_, GRAD>;
-                PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm3::gather));
-                kern<<<nblk, (Cfg::NCW + 1) * 32, Sm3::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
-                done = true;
-              }
-            }
-            if (!done) {
-              auto kern = k_gather_zm2<R, CPLX, M_, GRAD>;
-              PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
-              kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
-            }
+            auto kern = k_gather_zm2<R, CPLX, M_, GRAD>;
+            PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
+            kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
             p->launches++;
           }
         } else {
@@ -1067,22 +1052,135 @@ template <class R> struct Core {
           const size_t tsm = (size_t)kZm2TabNodes * RowS::ROWBYTES + psm;
           PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
           kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, nb_args, tab, first);
-          bool done = false;
-          if constexpr (sizeof(R) == 8 && Zm3Ok<M_>::value) {
-            if (mma) {
-              typedef Zm3Smem<CPLX, M_, GRAD> Sm3;
-              auto kern = k_scatter_mma<CPLX, M_, GRAD>;
-              PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm3::scatter));
-              kern<<<nblk, (Cfg::NCW + 1) * 32, Sm3::scatter, p->stream>>>(tm, zg, tab, nd->d_tile_start);
-              done = true;
-            }
-          }
-          if (!done) {
-            auto kern = k_scatter_zm2<R, CPLX, M_, GRAD>;
-            PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
-            kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::scatter, p->stream>>>(tm, zg, tab, nd->d_tile_start);
-          }
+          auto kern = k_scatter_zm2<R, CPLX, M_, GRAD>;
+          PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
+          kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::scatter, p->stream>>>(tm, zg, tab, nd->d_tile_start);
           p->launches += 2;
+        }
+      }
+      PNB_CUDA(cudaGetLastError());
+    }
+  }
+
+  // work items of the family-2 geometry: whole columns when there are enough of them to fill the GPU, else split along z;
+  // clustered node sets (hint from the previous binning) get smaller items
+  static Zm2Geom zm2_work_items(const TileGeom &tg, const Nd *nd, int M) {
+    Zm2Geom zg;
+    zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2]; zg.col0 = 0;
+    const int ncol = tg.nt[0] * tg.nt[1];
+    int nseg = 1;
+    while (ncol * nseg < 8 * 148 && nseg * 2 <= tg.nt[2]) nseg *= 2;
+    static const int nseg_env = getenv("PNFFT_B200_NSEG") ? atoi(getenv("PNFFT_B200_NSEG")) : 0;
+    int nseg_min = nseg_env;
+    if (!nseg_env && nd->h_maxcol) {
+      const long long maxcol = *(volatile int *)nd->h_maxcol;      // from the previous binning of this node set
+      if (maxcol * ncol > 4LL * M) nseg_min = 4;
+      if (maxcol * ncol > 32LL * M) nseg_min = 8;
+    }
+    while (nseg < nseg_min && nseg * 2 <= tg.nt[2]) nseg *= 2;
+    zg.zseg = (tg.nt[2] + nseg - 1) / nseg;
+    zg.nseg = (tg.nt[2] + zg.zseg - 1) / zg.zseg;
+    return zg;
+  }
+
+  // z-march v3 (zmarch3.cuh, double only): node-table rows WITHOUT node values, kept across calls while the binning they
+  // were made from stays valid (device-resident x with an unchanged content hash, x declared static, PNFFT_PRE_PSI); a
+  // table with derivative sections serves F-only calls too.  PNFFT_B200_ROW_CACHE=0 rebuilds the rows in every call.
+  template <bool CPLX, int M_, bool GRAD, bool RG>
+  static void launch_zm3_kernels(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter, const Zm2Geom &zg, unsigned nblk, const R *tab) {
+    if constexpr (sizeof(R) == 8 && Zm3Ok<M_>::value) {
+      typedef Zm2Cfg<M_> Cfg;
+      typedef Zm3Smem<CPLX, M_, GRAD, RG> Sm;
+      const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::XW, 16, Cfg::ZB, 0);   // boxes are read 256 contiguous bytes per n-block: no swizzle
+      if (!scatter) {
+        GatherOut<R> out;
+        out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
+        auto kern = k_gather_mma<CPLX, M_, GRAD, RG>;
+        PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
+        kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, tab, nd->d_tile_start, out);
+      } else {
+        auto kern = k_scatter_mma<CPLX, M_, GRAD, RG>;
+        PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::scatter));
+        kern<<<nblk, (Cfg::NCW + 1) * 32, Sm::scatter, p->stream>>>(tm, zg, tab, nd->d_vals, nd->d_tile_start);
+      }
+      p->launches++;
+    }
+  }
+  template <bool CPLX, int M_, bool RG>
+  static void launch_zm3_table(P *p, const GridGeom<R> &g, const NodeArgs<R> &na_upto, R *tab, int first) {
+    if constexpr (sizeof(R) == 8 && Zm3Ok<M_>::value) {
+      typedef Zm2Row<R, M_, RG, false, CPLX> Row;
+      const size_t psm = g.poly ? sizeof(R) * (size_t)2 * (g.poly_deg + 1) * 3 * Zm2Cfg<M_>::C : 0;
+      const unsigned ntb = (unsigned)((na_upto.M - first + kZm2TabNodes - 1) / kZm2TabNodes);
+      auto kt = k_node_table2<R, M_, RG, false, CPLX>;
+      const size_t tsm = (size_t)kZm2TabNodes * Row::ROWBYTES + psm;
+      PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+      kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, na_upto, tab, first);
+      p->launches++;
+    }
+  }
+  template <bool CPLX, int M_, bool GRAD>
+  static void launch_zm3(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
+    if constexpr (sizeof(R) == 8 && Zm3Ok<M_>::value) {
+      typedef Zm2Cfg<M_> Cfg;
+      const TileGeom tg = tile_geom(p, nullptr);
+      const GridGeom<R> g = geom(p);
+      Zm2Geom zg = zm2_work_items(tg, nd, na.M);
+      const int ncol = tg.nt[0] * tg.nt[1];
+      if (scatter && (p->b_phase & 2)) {       // node values in sorted order
+        constexpr int NVP = Zm3Smem<CPLX, M_, GRAD, GRAD>::NVP;
+        ensure(&nd->d_vals, &nd->cap_vals, (size_t)na.M * NVP + 64);
+        const long long n = (long long)na.M * NVP;
+        k_pack_vals<CPLX, GRAD><<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(na, nd->d_vals);
+        p->launches++;
+      }
+      const size_t len_g = Zm2Row<R, M_, true, false, CPLX>::ROWLEN, len_f = Zm2Row<R, M_, false, false, CPLX>::ROWLEN;
+      static const double cap_gb = getenv("PNFFT_B200_TABLE_GB") ? atof(getenv("PNFFT_B200_TABLE_GB")) : 24.0;
+      const char *rc = getenv("PNFFT_B200_ROW_CACHE");
+      const bool cache_on = !(rc && atoi(rc) == 0);
+      const double need_gb = (double)na.M * (GRAD ? len_g : len_f) * sizeof(R) / 1073741824.0;
+      if (need_gb <= cap_gb || p->b_phase != 3) {
+        // one table for the whole node set, in the binning's own buffer
+        const bool reuse = cache_on && nd->binned && nd->rows_plan == (const void *)p && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
+        int flavor = reuse ? nd->rows_flavor : (GRAD ? 1 : 0);
+        if (!reuse && (p->b_phase & 1)) {
+          ensure(&nd->d_rows, &nd->cap_rows, (size_t)na.M * (flavor ? len_g : len_f) + 64);
+          if (flavor) launch_zm3_table<CPLX, M_, true>(p, g, na, nd->d_rows, 0);
+          else launch_zm3_table<CPLX, M_, false>(p, g, na, nd->d_rows, 0);
+          nd->rows_flavor = flavor; nd->rows_plan = p;
+        } else if (!reuse) {
+          flavor = nd->rows_flavor;      // the table phase of this call ran earlier (side stream)
+        }
+        if (p->b_phase & 2) {
+          const unsigned nblk = (unsigned)(ncol * zg.nseg);
+          if (flavor) launch_zm3_kernels<CPLX, M_, GRAD, true>(p, nd, na, scatter, zg, nblk, nd->d_rows);
+          else if constexpr (!GRAD) launch_zm3_kernels<CPLX, M_, false, false>(p, nd, na, scatter, zg, nblk, nd->d_rows);
+        }
+      } else {
+        // the table would not fit the budget: built and consumed in column batches, nothing kept
+        const size_t rowlen = GRAD ? len_g : len_f;
+        const int nbatch = std::min(ncol, (int)std::ceil(2.0 * need_gb / cap_gb));
+        std::vector<int> cb((size_t)nbatch + 1), nb((size_t)nbatch + 1);
+        for (int k = 0; k <= nbatch; k++) cb[(size_t)k] = (int)((long long)ncol * k / nbatch);
+        nb[0] = 0; nb[(size_t)nbatch] = na.M;
+        const size_t per_col = (size_t)tg.nt[2] * Cfg::SUB;
+        for (int k = 1; k < nbatch; k++)
+          PNB_CUDA(cudaMemcpyAsync(&nb[(size_t)k], nd->d_tile_start + (size_t)cb[(size_t)k] * per_col, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        PNB_CUDA(cudaStreamSynchronize(p->stream));
+        size_t max_rows = 0;
+        for (int k = 0; k < nbatch; k++) max_rows = std::max(max_rows, (size_t)(nb[(size_t)k + 1] - nb[(size_t)k]));
+        ensure(&nd->d_wtab, &nd->cap_wtab, max_rows * rowlen + 64);
+        nd->rows_flavor = -1;
+        for (int k = 0; k < nbatch; k++) {
+          const int first = nb[(size_t)k], last = nb[(size_t)k + 1];
+          if (last <= first) continue;
+          NodeArgs<R> nb_args = na;
+          nb_args.M = last;
+          R *tab = nd->d_wtab - (size_t)first * rowlen;        // rows are addressed by their absolute sorted position
+          zg.col0 = cb[(size_t)k];
+          const unsigned nblk = (unsigned)((cb[(size_t)k + 1] - cb[(size_t)k]) * zg.nseg);
+          launch_zm3_table<CPLX, M_, GRAD>(p, g, nb_args, tab, first);
+          launch_zm3_kernels<CPLX, M_, GRAD, GRAD>(p, nd, na, scatter, zg, nblk, tab);
         }
       }
       PNB_CUDA(cudaGetLastError());
@@ -1091,8 +1189,10 @@ template <class R> struct Core {
 
   template <bool CPLX, int M_, bool GRAD>
   static void launch_zmarch(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
-    if (kernel_family(p) == 2) launch_zm2<CPLX, M_, GRAD>(p, nd, na, scatter);
-    else launch_zm<CPLX, M_, GRAD>(p, nd, na, scatter);
+    if (kernel_family(p) == 2) {
+      if (use_mma<M_>(p)) launch_zm3<CPLX, M_, GRAD>(p, nd, na, scatter);
+      else launch_zm2<CPLX, M_, GRAD>(p, nd, na, scatter);
+    } else launch_zm<CPLX, M_, GRAD>(p, nd, na, scatter);
   }
 
   template <bool CPLX> static void launch_B(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
@@ -1133,11 +1233,16 @@ template <class R> struct Core {
     const char *e = getenv(name);
     return e ? atoi(e) != 0 : dflt;
   }
-  static unsigned long long hash_device_x(P *p, Nd *nd, const R *dx) {
+  // `after`: stream the coordinates were just written on (an upload), nullptr if they have been resident all along
+  static unsigned long long hash_device_x(P *p, Nd *nd, const R *dx, cudaStream_t after = nullptr) {
     const size_t n = 3 * (size_t)nd->local_M;
     if (!nd->h_hash) {
       PNB_CUDA(cudaHostAlloc((void **)&nd->h_hash, sizeof(unsigned long long), cudaHostAllocDefault));
       PNB_CUDA(cudaMalloc((void **)&nd->d_hash, sizeof(unsigned long long)));
+    }
+    if (after && after != p->copy_stream) {
+      PNB_CUDA(cudaEventRecord(p->ev_copy[2], after));
+      PNB_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_copy[2], 0));
     }
     PNB_CUDA(cudaMemsetAsync(nd->d_hash, 0, sizeof(unsigned long long), p->copy_stream));
     if (n) k_hash_words<R><<<148 * 8, 256, 0, p->copy_stream>>>(dx, (long long)n, nd->d_hash);
@@ -1151,6 +1256,7 @@ template <class R> struct Core {
     const size_t M = (size_t)nd->local_M;
     static const bool env_static = env_flag("PNFFT_B200_X_STATIC", false);
     static const bool use_hash = env_flag("PNFFT_B200_X_HASH", true);
+    static const bool hash_up = env_flag("PNFFT_B200_X_HASH_UPLOADS", true);
     const bool is_static = nd->x_static || env_static;
     const bool pinned = (nd->precompute_flags & P_PRE_PSI) != 0;
     const int fam = kernel_family(p);
@@ -1172,14 +1278,22 @@ template <class R> struct Core {
       PNB_CUDA(cudaStreamWaitEvent(p->stream, p->ev_copy[1], 0));
       dx = nd->d_x;
       nd->x_uploaded = true;
+      // the uploaded coordinates may be the ones the bins and the window table were made from (trafo then adj of one
+      // step): one streaming pass over them tells, and saves the binning and the table
+      if (use_hash && hash_up && !pinned) h = hash_device_x(p, nd, dx, p->copy_stream);
     } else {
       dx = dev_in(p, nd->x, &nd->d_x, &nd->cap_x, 3 * M, true);
       nd->x_uploaded = true;
+      if (use_hash && hash_up && !pinned && M && nd->x && !is_device_ptr(nd->x)) h = hash_device_x(p, nd, dx, p->stream);
     }
     if (ev_after_copy >= 0) PNB_CUDA(cudaEventRecord(p->ev[ev_after_copy], p->stream));
     bool valid = nd->binned && nd->bin_plan == (const void *)p && nd->bin_family == fam && nd->d_x_bound == dx;
     if (valid && !pinned && !is_static) valid = h != 0 && nd->bin_hash == h;     // device x: same content as last time?
+    static const bool dbg = env_flag("PNFFT_B200_DEBUG_BIN", false);
+    if (dbg) fprintf(stderr, "prepare_nodes: valid=%d binned=%d plan=%d fam=%d/%d bound=%p dx=%p h=%llx bin_hash=%llx static=%d pinned=%d\n", (int)valid, (int)nd->binned,
+                     (int)(nd->bin_plan == (const void *)p), nd->bin_family, fam, (const void *)nd->d_x_bound, (const void *)dx, h, nd->bin_hash, (int)is_static, (int)pinned);
     if (!valid) {
+      nd->rows_flavor = -1;          // the cached node-table rows belong to the old bins
       bin_nodes(p, nd, dx);
       nd->bin_plan = p; nd->bin_family = fam; nd->d_x_bound = dx; nd->bin_hash = h;
       nd->binned = pinned || is_static || h != 0;

@@ -175,7 +175,7 @@ template <class R> struct Plan {
   // device state
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // second H2D queue: node coordinates travel while D and F run (Core::trafo)
-  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
   cudaStream_t node_stream = nullptr;   // trafo: binning + node table run here while D, F and the halo exchange run on `stream`
   int b_phase = 3;                      // what launch_B does: bit 0 = node table, bit 1 = gridding kernel (z-march v2 only)
   bool side_nodes = false;              // the current trafo ran its node side on node_stream (stage timers: ev[9..12])
@@ -234,6 +234,12 @@ template <class R> struct BinState {
   int *d_maxcol = nullptr;
   // PNFFT_PRE_PSI tables in sorted order (reference kernel/ndft-parallel.c:1184-1240)
   R *d_pre_psi = nullptr, *d_pre_dpsi = nullptr;
+  // node-table rows of the tensor-core gridding kernels (zmarch3.cuh), kept while this binning stays valid: the window
+  // factors depend on x alone, so trafo and adj (and every further call on the same coordinates) share one table
+  R *d_rows = nullptr;
+  size_t cap_rows = 0;
+  int rows_flavor = -1;            // -1: none, 0: psi sections only, 1: with the derivative sections
+  const void *rows_plan = nullptr;
 };
 
 template <class R> struct Nodes : BinState<R> {
@@ -263,6 +269,9 @@ template <class R> struct Nodes : BinState<R> {
   // per-call node table of the z-marching kernels (zmarch.cuh: ZmTab), grown on demand
   R *d_wtab = nullptr;
   size_t cap_wtab = 0;
+  // node values in sorted order for the tensor-core scatter (k_pack_vals)
+  R *d_vals = nullptr;
+  size_t cap_vals = 0;
 };
 
 }  // namespace pnb

@@ -48,15 +48,18 @@ __device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned phas
   return __any_sync(0xffffffffu, ok != 0);
 }
 
-template <bool CPLX, int M_, bool GRAD> struct Zm3Smem {
+// RG: the node-table rows carry the derivative sections (a table built for a gradient transform also serves F-only
+// gathers and scatters of the same node set: Core keeps the rows while the binning they belong to stays valid).  The rows
+// never hold node values; the scatter streams f / grad_f as a second, small section of every ring stage (k_pack_vals).
+template <bool CPLX, int M_, bool GRAD, bool RG> struct Zm3Smem {
+  static_assert(RG || !GRAD, "a gradient kernel needs rows with derivative sections");
   typedef Zm2Cfg<M_> Cfg;
-  typedef Zm2Row<double, M_, GRAD, true, CPLX> RowS;
-  typedef Zm2Row<double, M_, GRAD, false, CPLX> RowG;
+  typedef Zm2Row<double, M_, RG, false, CPLX> Row;
   static constexpr int NCOMP = CPLX ? 2 : 1;
   static constexpr int CELLB = 8 * NCOMP;
   static constexpr int WARP_BOX = Cfg::XW * 16 * Cfg::ZS * CELLB;          // bytes one warp stages per window advance
-  static constexpr int NVAL = NCOMP * (GRAD ? 4 : 1);                      // output values per node
-  // gather: one staging box per warp, ring of S stages of GB nodes, P stages of per-warp partial outputs
+  static constexpr int NVAL = NCOMP * (GRAD ? 4 : 1);                      // values per node (f, grad_f)
+  static constexpr int NVP = (NVAL + 1) / 2 * 2;                           // ... padded to 16-byte granules
 #ifndef ZM3_GP
 #define ZM3_GP 3
 #endif
@@ -66,22 +69,37 @@ template <bool CPLX, int M_, bool GRAD> struct Zm3Smem {
 #ifndef ZM3_GGB
 #define ZM3_GGB 32
 #endif
+  // gather: one staging box per warp, ring of S stages of GB nodes, P stages of per-warp partial outputs
   static constexpr int GS = ZM3_GS, GP = ZM3_GP, GGB = ZM3_GGB;
-  static constexpr int g_stage = kZm2HdrBytes + GGB * RowG::ROWBYTES;
+  static constexpr int g_stage = kZm2HdrBytes + GGB * Row::ROWBYTES;
   static constexpr int g_off_ring = Cfg::NCW * WARP_BOX;
   static constexpr int g_off_part = g_off_ring + GS * g_stage;
   static constexpr int g_part_stage = Cfg::NCW * GGB * NVAL * 8;
   static constexpr int g_off_bar = g_off_part + GP * g_part_stage;
   static constexpr int gather = g_off_bar + (2 * GS + 2 * GP + Cfg::NCW) * 8;
-  // scatter: two staging boxes per warp, ring
+  // scatter: two staging boxes per warp, ring of stages {header, GB rows, GB value rows}
   static constexpr int SS = 4, SGB = 32;
-  static constexpr int s_stage = kZm2HdrBytes + SGB * RowS::ROWBYTES;
+  static constexpr int s_off_vals = kZm2HdrBytes + SGB * Row::ROWBYTES;
+  static constexpr int s_stage = s_off_vals + SGB * NVP * 8;
   static constexpr int s_off_ring = Cfg::NCW * 2 * WARP_BOX;
   static constexpr int s_off_bar = s_off_ring + SS * s_stage;
   static constexpr int scatter = s_off_bar + 2 * SS * 8;
-  static_assert(g_stage % 16 == 0 && s_stage % 16 == 0 && g_off_ring % 128 == 0 && s_off_ring % 128 == 0 && WARP_BOX % 256 == 0, "alignment");
+  static_assert(g_stage % 16 == 0 && s_stage % 16 == 0 && s_off_vals % 16 == 0 && g_off_ring % 128 == 0 && s_off_ring % 128 == 0 && WARP_BOX % 256 == 0, "alignment");
   static_assert(scatter <= 232448 && gather <= 232448, "shared-memory budget of one CTA exceeded");
 };
+
+// node values in sorted order for the scatter: vals[p] = {f, grad_f[0..3)} of node perm[p], NVP reals per node
+template <bool CPLX, bool GRAD> __global__ void __launch_bounds__(256) k_pack_vals(NodeArgs<double> na, double *__restrict__ vals) {
+  constexpr int NCOMP = CPLX ? 2 : 1, NVAL = NCOMP * (GRAD ? 4 : 1), NVP = (NVAL + 1) / 2 * 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)na.M * NVP) return;
+  const int p = (int)(i / NVP), c = (int)(i - (long long)p * NVP);
+  const int j = na.perm ? na.perm[p] : p;
+  double v = 0;
+  if (c < NCOMP) { if (na.f) v = na.f[((size_t)j * na.f_stride + na.f_off) * NCOMP + c]; }
+  else if (GRAD && c < NVAL) v = na.grad[(size_t)j * 3 * NCOMP + (c - NCOMP)];
+  vals[i] = v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // gather (trafo B)
@@ -91,13 +109,13 @@ template <bool CPLX, int M_, bool GRAD> struct Zm3Smem {
 // real grids: column c is row c.  Row r of the warp is x row r / 16, y row r % 16 of its [XW][16] footprint slice.
 // A fragment of slot s: z weight 4 q + t of node g of the batch, q = (s - cur) mod KS the chunk's place in the window.
 // C fragment: node g, columns 2t, 2t+1 of the n-block = one complex partial sum (two real ones) per lane.
-template <bool CPLX, int M_, bool GRAD>
+template <bool CPLX, int M_, bool GRAD, bool RG>
 __global__ void __launch_bounds__((Zm2Cfg<M_>::NCW + 1) * 32, 1)
 k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double *__restrict__ tab, const int *__restrict__ bin_start,
              GatherOut<double> out) {
   typedef Zm2Cfg<M_> Cfg;
-  typedef Zm3Smem<CPLX, M_, GRAD> Sm;
-  typedef typename Sm::RowG Row;
+  typedef Zm3Smem<CPLX, M_, GRAD, RG> Sm;
+  typedef typename Sm::Row Row;
   constexpr int C = Cfg::C, T0 = Cfg::T0, T1 = Cfg::T1, ZS = Cfg::ZS, W = Cfg::W, NCW = Cfg::NCW, XW = Cfg::XW;
   constexpr int NCOMP = Sm::NCOMP, S = Sm::GS, P = Sm::GP, GB = Sm::GGB, ROWBYTES = Row::ROWBYTES, STAGE = Sm::g_stage, NVAL = Sm::NVAL;
   constexpr int KS = W / 4;                       // k-steps = chunks in the window
@@ -221,7 +239,7 @@ k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double 
   // weights of the rows my C fragments hold: y rows 4 jy + t (complex) or 8 jy + 2 t + e (real)
   const int aX = (Row::oX + Cfg::XLEAD + XW * warp) * 8;
   const int aY = (Row::oY + T1 - 1 + (CPLX ? t : 2 * t)) * 8;
-  constexpr int dOff = (Row::oDX - Row::oX) * 8;
+  constexpr int dOff = RG ? (Row::oDX - Row::oX) * 8 : 0;
 
   double win[NB][KS];
   int cur = INT_MIN / 2;       // sub-chunk whose cells [cur*ZS, cur*ZS + W) are in the window
@@ -303,7 +321,7 @@ k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double 
         for (int s = 0; s < KS; s++) {
           const int q = (s - rot + KS) % KS;
           az[s] = *reinterpret_cast<const double *>(row + (Row::oZ + 4 * q + t) * 8);
-          if (GRAD) adz[s] = *reinterpret_cast<const double *>(row + (Row::oDZ + 4 * q + t) * 8);
+          if (GRAD) adz[s] = *reinterpret_cast<const double *>(row + (Row::oZ + 4 * q + t) * 8 + dOff);
         }
       };
       const unsigned char *row, *row_n;
@@ -433,14 +451,15 @@ k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double 
 // the chunk that leaves at an advance is the four slots (4 cur) mod 16 .. +3: half the lanes of one cell block store them
 // to the staging box (TMA reduce-add) and clear them.  A fragment: z weight ((8 zb + g) - 4 cur) mod 16 of node t of the
 // batch; B fragment: amplitude of node t in column 8 nb + g = psi_x psi_y f (+ gradient terms), built per lane.
-template <bool CPLX, int M_, bool GRAD>
+template <bool CPLX, int M_, bool GRAD, bool RG>
 __global__ void __launch_bounds__((Zm2Cfg<M_>::NCW + 1) * 32, 1)
-k_scatter_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double *__restrict__ tab, const int *__restrict__ bin_start) {
+k_scatter_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double *__restrict__ tab, const double *__restrict__ vals,
+              const int *__restrict__ bin_start) {
   typedef Zm2Cfg<M_> Cfg;
-  typedef Zm3Smem<CPLX, M_, GRAD> Sm;
-  typedef typename Sm::RowS Row;
+  typedef Zm3Smem<CPLX, M_, GRAD, RG> Sm;
+  typedef typename Sm::Row Row;
   constexpr int C = Cfg::C, T0 = Cfg::T0, T1 = Cfg::T1, ZS = Cfg::ZS, W = Cfg::W, NCW = Cfg::NCW, XW = Cfg::XW;
-  constexpr int NCOMP = Sm::NCOMP, S = Sm::SS, GB = Sm::SGB, ROWBYTES = Row::ROWBYTES, STAGE = Sm::s_stage;
+  constexpr int NCOMP = Sm::NCOMP, S = Sm::SS, GB = Sm::SGB, ROWBYTES = Row::ROWBYTES, STAGE = Sm::s_stage, NVP = Sm::NVP;
   constexpr int NYB = 16 * NCOMP / 8, NB = XW * NYB, NZB = W / 8;
   static_assert(W == 16 && ZS == 4 && Cfg::ZB == 4 && Cfg::RPT == 1, "accumulator window = two cell blocks of eight slots");
   static_assert(GB % 4 == 0, "ring stages hold whole node batches");
@@ -463,7 +482,38 @@ k_scatter_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
   __syncthreads();
 
   if (warp == NCW) {
-    zm2_produce<T0, Cfg::SUB, S, GB, ROWBYTES, STAGE, 1>(ring, full, empty, reinterpret_cast<const unsigned char *>(tab), bs, tz0, tz1, lane);
+    // producer: zm2_produce with a second bulk copy per stage, the node values
+    const unsigned char *tabb = reinterpret_cast<const unsigned char *>(tab);
+    int kb = 0;
+    int gs_next = (lane <= T0) ? bs[(size_t)tz0 * Cfg::SUB + lane] : 0;
+    for (int tz = tz0; tz < tz1; tz++) {
+      const int gs = gs_next;
+      if (tz + 1 < tz1) gs_next = (lane <= T0) ? bs[(size_t)(tz + 1) * Cfg::SUB + lane] : 0;
+      const int s0 = __shfl_sync(0xffffffffu, gs, 0), e = __shfl_sync(0xffffffffu, gs, T0);
+      for (int c0 = s0; c0 < e; c0 += GB, kb++) {
+        const int st = kb % S;
+        mbar_wait_park(&empty[st], (((unsigned)(kb / S)) & 1u) ^ 1u);
+        const int cnt = min(GB, e - c0);
+        unsigned char *sp = ring + (size_t)st * STAGE;
+        int *h = reinterpret_cast<int *>(sp);
+        if (lane <= T0) h[4 + lane] = min(max(gs - c0, 0), cnt);
+        if (lane == 0) { h[0] = tz; h[1] = cnt; h[2] = c0; h[3] = 0; }
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned rb = (unsigned)(cnt * ROWBYTES), vb = (unsigned)(cnt * NVP * 8);
+          mbar_expect_tx(&full[st], rb + vb);
+          bulk_load_1d(sp + kZm2HdrBytes, tabb + (size_t)c0 * ROWBYTES, rb, &full[st]);
+          bulk_load_1d(sp + Sm::s_off_vals, vals + (size_t)c0 * NVP, vb, &full[st]);
+        }
+      }
+    }
+    const int st = kb % S;
+    mbar_wait_park(&empty[st], (((unsigned)(kb / S)) & 1u) ^ 1u);
+    if (lane == 0) {
+      int *h = reinterpret_cast<int *>(ring + (size_t)st * STAGE);
+      h[0] = INT_MAX; h[1] = 0;
+      mbar_arrive(&full[st]);
+    }
     return;
   }
 
@@ -475,8 +525,8 @@ k_scatter_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
   // B fragment: column 8 nb + g is component g & 1 of row 4 nb + (g >> 1) (complex) or row 8 nb + g (real)
   const int aX = (Row::oX + Cfg::XLEAD + XW * warp) * 8;
   const int aY = (Row::oY + T1 - 1 + (CPLX ? (g >> 1) : g)) * 8;
-  const int aV = (Row::oV + (CPLX ? (g & 1) : 0)) * 8;
-  constexpr int dOff = (Row::oDX - Row::oX) * 8;
+  const int aV = CPLX ? (g & 1) * 8 : 0;          // my component of the node's values (second section of the stage)
+  constexpr int dOff = RG ? (Row::oDX - Row::oX) * 8 : 0;
   // C fragment -> staging box [XW][16][4]: cell z = g & 3 of row 4 nb + t (complex), rows 8 nb + 2t, 2t + 1 (real)
   const int stg_off = CPLX ? (t * 64 + (g & 3) * 16) : (2 * t * 32 + (g & 3) * 8);
 
@@ -547,15 +597,16 @@ k_scatter_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
 #pragma unroll
         for (int zb = 0; zb < NZB; zb++) {
           az[zb] = *reinterpret_cast<const double *>(row + offA[zb]);
-          if (GRAD) adz[zb] = *reinterpret_cast<const double *>(row + offA[zb] + (Row::oDZ - Row::oZ) * 8);
+          if (GRAD) adz[zb] = *reinterpret_cast<const double *>(row + offA[zb] + dOff);
         }
-        double f = *reinterpret_cast<const double *>(row + aV);
+        const unsigned char *vrow = sp + Sm::s_off_vals + (size_t)i * NVP * 8 + aV;
+        double f = *reinterpret_cast<const double *>(vrow);
         if (!valid) f = 0;
         double g0 = 0, g1 = 0, g2 = 0;
         if (GRAD) {
-          g0 = *reinterpret_cast<const double *>(row + aV + NCOMP * 8);
-          g1 = *reinterpret_cast<const double *>(row + aV + 2 * NCOMP * 8);
-          g2 = *reinterpret_cast<const double *>(row + aV + 3 * NCOMP * 8);
+          g0 = *reinterpret_cast<const double *>(vrow + NCOMP * 8);
+          g1 = *reinterpret_cast<const double *>(vrow + 2 * NCOMP * 8);
+          g2 = *reinterpret_cast<const double *>(vrow + 3 * NCOMP * 8);
           if (!valid) { g0 = 0; g1 = 0; g2 = 0; }
         }
         // amplitudes: A = psi_x (psi_y f + dpsi_y g1) + dpsi_x psi_y g0, B = psi_x psi_y g2 (paired with dpsi_z)
