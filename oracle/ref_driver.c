@@ -50,6 +50,7 @@ typedef struct {
   INT *node_index;       /* optional out [M][4]: u_j[0..2] in the padded local array, m0 */
   INT *sort_perm;        /* optional out [M]: global node index in the rank's processing order */
   double b_out[3];       /* out: window shape parameters */
+  R *hessian_f;          /* optional out [M][6] complex interleaved or real (PNFFT_COMPUTE_HESSIAN_F) */
 } DRV(job);
 
 typedef struct {
@@ -134,7 +135,8 @@ static void rank_main(int rank, void *arg)
   }
 
   if (J->op != OP_LAYOUT) {
-    PNX(nodes) nodes = PNX(init_nodes)(local_M, PNFFT_MALLOC_X | PNFFT_MALLOC_F | PNFFT_MALLOC_GRAD_F);
+    PNX(nodes) nodes = PNX(init_nodes)(local_M, PNFFT_MALLOC_X | PNFFT_MALLOC_F | PNFFT_MALLOC_GRAD_F
+                                                 | (J->hessian_f ? PNFFT_MALLOC_HESSIAN_F : 0u));
     for (INT p = 0; p < local_M; p++)
       for (int t = 0; t < 3; t++) nodes->x[3 * p + t] = J->x[3 * mine[p] + t];
 
@@ -179,6 +181,9 @@ static void rank_main(int rank, void *arg)
       if (J->grad_f && (J->compute_flags & PNFFT_COMPUTE_GRAD_F))
         for (INT p = 0; p < local_M; p++)
           for (int c = 0; c < 3 * tup; c++) J->grad_f[3 * tup * mine[p] + c] = nodes->grad_f[3 * tup * p + c];
+      if (J->hessian_f && (J->compute_flags & PNFFT_COMPUTE_HESSIAN_F))
+        for (INT p = 0; p < local_M; p++)
+          for (int c = 0; c < 6 * tup; c++) J->hessian_f[6 * tup * mine[p] + c] = nodes->hessian_f[6 * tup * p + c];
       if (J->get_g1 && J->g1) copy_fhat(J, local_N, local_N_start, J->g1, ths->g1, 0);
       if (J->get_grid && J->grid) copy_grid(J, ths->no, ths->local_no, ths->local_no_start, J->grid, ths->g2, 0);
     } else {
@@ -203,7 +208,7 @@ static void rank_main(int rank, void *arg)
       double *T = J->timers + 2 * PNFFT_TIMER_LENGTH * rank;
       for (int t = 0; t < PNFFT_TIMER_LENGTH; t++) { T[t] = ths->timer_trafo[t]; T[PNFFT_TIMER_LENGTH + t] = ths->timer_adj[t]; }
     }
-    PNX(free_nodes)(nodes, PNFFT_FREE_X | PNFFT_FREE_F | PNFFT_FREE_GRAD_F);
+    PNX(free_nodes)(nodes, PNFFT_FREE_X | PNFFT_FREE_F | PNFFT_FREE_GRAD_F | (J->hessian_f ? PNFFT_FREE_HESSIAN_F : 0u));
   }
 
   free(mine);

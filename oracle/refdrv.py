@@ -29,6 +29,7 @@ PRE_PSI = 1 << 1
 PRE_GRAD_PSI = 1 << 2
 COMPUTE_F = 1 << 0
 COMPUTE_GRAD_F = 1 << 1
+COMPUTE_HESSIAN_F = 1 << 2
 COMPUTE_DIRECT = 1 << 3
 COMPUTE_ACCUMULATED = 1 << 4
 OMIT_DECONV = 1 << 5
@@ -64,6 +65,7 @@ def _job_struct(real):
             ("node_index", C.POINTER(INT)),
             ("sort_perm", C.POINTER(INT)),
             ("b_out", C.c_double * 3),
+            ("hessian_f", RP),
         ]
 
     class Probe(C.Structure):
@@ -139,6 +141,10 @@ class RefLib:
             go = np.zeros((M, 3), ftype) if grad_f is None else np.ascontiguousarray(grad_f, dtype=ftype).copy()
         J.f_hat, J.f, J.grad_f = self._rp(fh), self._rp(fo), self._rp(go)
         keep.update(fh=fh, fo=fo, go=go)
+        ho = None
+        if op == OP_TRAFO and (compute_flags & COMPUTE_HESSIAN_F):
+            ho = np.zeros((M, 6), ftype)
+            J.hessian_f = self._rp(ho)
 
         gtype = self.rdt if c2r else self.cdt
         grid_a = None
@@ -173,7 +179,7 @@ class RefLib:
         rc = self._run(C.byref(J))
         if rc:
             raise RuntimeError("reference driver failed (process mesh does not match)")
-        return dict(f_hat=fh, f=fo, grad_f=go, grid=grid_a, g1=g1_a, owner=owner,
+        return dict(f_hat=fh, f=fo, grad_f=go, hessian_f=ho, grid=grid_a, g1=g1_a, owner=owner,
                     local_N=layout[:, 0:3], local_N_start=layout[:, 3:6], local_no=layout[:, 6:9],
                     local_no_start=layout[:, 9:12], no=tuple(int(v) for v in layout[0, 12:15]),
                     lo=borders[:, 0:3], up=borders[:, 3:6], timers=timers, node_index=node_index,

@@ -166,6 +166,11 @@ class Nodes:
         self._keep["g"] = g
         self.P.fn("set_grad_f", None, [C.c_void_p, C.c_void_p])(_ptr(g), self.h)
 
+    def set_hessian_f(self, h):
+        """6 values per node (xx, xy, xz, yy, yz, zz; complex for c2c plans), written by trafo(COMPUTE_HESSIAN_F)"""
+        self._keep["h"] = h
+        self.P.fn("set_hessian_f", None, [C.c_void_p, C.c_void_p])(_ptr(h), self.h)
+
     def x_static(self, on=True):
         """pnfft_b200_nodes_x_static: promise that x stays unchanged until the next set_x (upload and binning are reused)."""
         self.P.fn("b200_nodes_x_static", None, [C.c_void_p, C.c_int])(self.h, int(bool(on)))

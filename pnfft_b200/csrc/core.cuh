@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "fftown.cuh"
 #include "zmarch3.cuh"
 #include "gridops.cuh"
 
@@ -561,10 +562,22 @@ template <class R> struct Core {
   static void make_fft_plans(P *p) {
     const Layout &L = p->L;
     const PipeGeom &G = p->pipe;
-    p->fft_x = make_plan_1d(L.n[0], G.S1, 1, G.S1, FftType<R>::c2c, 0, p->stream);
-    p->fft_y = make_plan_1d(L.n[1], G.S3, 1, G.S3, FftType<R>::c2c, 0, p->stream);
+    // complex passes of power-of-two length can run on the library's own kernels (fftown.cuh): PNFFT_B200_OWN_FFT=1.
+    // Measured on B200 (n = 512^3, profiles/r2_fft_own.md): cuFFT's kernels are faster than this first version, so cuFFT
+    // stays the default.
+    const bool force_cufft = !(getenv("PNFFT_B200_OWN_FFT") && atoi(getenv("PNFFT_B200_OWN_FFT")) != 0);    // read per plan
+    for (int t = 0; t < 3; t++) {
+      p->own_fft[t] = !force_cufft && fft_own_ok(L.n[t]) && !(t == 2 && L.c2r);
+      if (p->own_fft[t]) {
+        for (int u = 0; u < t; u++) if (p->own_fft[u] && L.n[u] == L.n[t]) p->d_tw[t] = p->d_tw[u];
+        if (!p->d_tw[t]) { C *tw = nullptr; fft_make_twiddles<C>((int)L.n[t], &tw); p->d_tw[t] = tw; }
+      }
+    }
+    if (!p->own_fft[0]) p->fft_x = make_plan_1d(L.n[0], G.S1, 1, G.S1, FftType<R>::c2c, 0, p->stream);
+    if (!p->own_fft[1]) p->fft_y = make_plan_1d(L.n[1], G.S3, 1, G.S3, FftType<R>::c2c, 0, p->stream);
     const long long nb = (long long)L.local_no[0] * L.local_no[1];
-    if (!L.c2r) {
+    if (p->own_fft[2]) {
+    } else if (!L.c2r) {
       p->fft_z_fwd = make_plan_1d(L.n[2], 1, L.n[2], nb, FftType<R>::c2c, 0, p->stream);
       p->fft_z_bwd = p->fft_z_fwd;
     } else {
@@ -591,6 +604,11 @@ template <class R> struct Core {
     cudaFree(p->d_f_hat); cudaFree(p->d_g1); cudaFree(p->d_g1_buffer); cudaFree(p->d_grid);
     cudaFree(p->d_work[0]); cudaFree(p->d_work[1]); cudaFree(p->d_work[2]); cudaFree(p->d_exp_const); cudaFree(p->d_sort_tmp); cudaFree(p->d_poly);
     for (int t = 0; t < 3; t++) cudaFree(p->d_invphi[t]);
+    for (int t = 0; t < 3; t++) {
+      bool shared = false;
+      for (int u = 0; u < t; u++) if (p->d_tw[u] == p->d_tw[t]) shared = true;
+      if (!shared) cudaFree(p->d_tw[t]);
+    }
     for (int i = 0; i < 16; i++) cudaEventDestroy(p->ev[i]);
     cudaStreamDestroy(p->stream);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -610,12 +628,18 @@ template <class R> struct Core {
     C *W0 = (C *)p->d_work[0], *W1 = (C *)p->d_work[1], *PK = (C *)p->d_work[2];
     const bool peer = p->peer.on;
     if (peer) peer_stage_forward(p, 0, W1); else run_stage_forward<C>(G.st[0], p->mesh, p->d_g1, W0, W1, PK, st, &p->launches);       // L1 in W1
-    if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_FORWARD); p->lib_launches++; }
+    if (p->own_fft[0]) { fft_strided_launch<C>(W1, (int)L.n[0], G.S1, G.S1, -1, (const C *)p->d_tw[0], st); p->launches++; }
+    else if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_FORWARD); p->lib_launches++; }
     if (peer) peer_stage_forward(p, 1, W0); else run_stage_forward<C>(G.st[1], p->mesh, W1, W1, W0, PK, st, &p->launches);            // L3 in W0
-    if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_FORWARD); p->lib_launches++; }
+    if (p->own_fft[1]) { fft_strided_launch<C>(W0, (int)L.n[1], G.S3, G.S3, -1, (const C *)p->d_tw[1], st); p->launches++; }
+    else if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_FORWARD); p->lib_launches++; }
     if (peer) peer_stage_forward(p, 2, W1); else run_stage_forward<C>(G.st[2], p->mesh, W0, W0, W1, PK, st, &p->launches);            // L4 in W1
     const long long lno0 = L.local_no[0], lno1 = L.local_no[1];
-    if (!L.c2r) {
+    if (p->own_fft[2]) {
+      // z pass fused with the crop / embed into the padded grid
+      fft_z_grid_launch<C>(W1, (C *)p->d_grid, (int)L.n[2], grid_map(p), -1, (const C *)p->d_tw[2], st);
+      p->launches++;
+    } else if (!L.c2r) {
       if (p->fft_z_fwd) { FftType<R>::exec_c2c(p->fft_z_fwd, W1, CUFFT_FORWARD); p->lib_launches++; }
       // crop l2 in [o_off2, o_off2+no2) and embed into the padded grid
       BoxMap bm = dense_map(lno0, lno1, L.no[2], L.ngc[1], L.pitch2, L.gcb[0], L.gcb[1], L.gcb[2], L.o_off[2]);
@@ -629,6 +653,15 @@ template <class R> struct Core {
     }
   }
 
+  static FftGridMap grid_map(const P *p) {
+    const Layout &L = p->L;
+    FftGridMap gm;
+    gm.rows = (long long)L.local_no[0] * L.local_no[1]; gm.rows1 = L.local_no[1];
+    gm.ngc1 = L.ngc[1]; gm.pitch2 = L.pitch2;
+    gm.gcb0 = (int)L.gcb[0]; gm.gcb1 = (int)L.gcb[1]; gm.gcb2 = (int)L.gcb[2]; gm.o_off = (int)L.o_off[2]; gm.no = (int)L.no[2];
+    return gm;
+  }
+
   static void fft_backward(P *p) {
     const Layout &L = p->L;
     const PipeGeom &G = p->pipe;
@@ -636,7 +669,10 @@ template <class R> struct Core {
     C *W0 = (C *)p->d_work[0], *W1 = (C *)p->d_work[1], *PK = (C *)p->d_work[2];
     const long long lno0 = L.local_no[0], lno1 = L.local_no[1];
     const bool pruned2 = L.no[2] < L.n[2];
-    if (!L.c2r) {
+    if (p->own_fft[2]) {
+      fft_z_grid_launch<C>(W1, (C *)p->d_grid, (int)L.n[2], grid_map(p), 1, (const C *)p->d_tw[2], st);
+      p->launches++;
+    } else if (!L.c2r) {
       if (pruned2) PNB_CUDA(cudaMemsetAsync(W1, 0, sizeof(C) * (size_t)G.L4_elems, st));
       BoxMap bm = dense_map(lno0, lno1, L.no[2], L.ngc[1], L.pitch2, L.gcb[0], L.gcb[1], L.gcb[2], L.o_off[2]);
       bm.c_str[0] = lno1 * L.n[2]; bm.c_str[1] = L.n[2];
@@ -654,12 +690,14 @@ template <class R> struct Core {
     if (peer) peer_stage_backward(p, 2, W0, G.L3_elems, L.no[1] < L.n[1]);
     else if (L.no[1] < L.n[1]) stage_backward_zero(p, G.st[2], W1, W0, W0, G.L3_elems);
     else run_stage_backward<C>(G.st[2], p->mesh, W1, W0, W0, PK, st, &p->launches);
-    if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_INVERSE); p->lib_launches++; }
+    if (p->own_fft[1]) { fft_strided_launch<C>(W0, (int)L.n[1], G.S3, G.S3, 1, (const C *)p->d_tw[1], st); p->launches++; }
+    else if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_INVERSE); p->lib_launches++; }
     // L3 in W0 -> L1 in W1
     if (peer) peer_stage_backward(p, 1, W1, G.L1_elems, L.no[0] < L.n[0]);
     else if (L.no[0] < L.n[0]) stage_backward_zero(p, G.st[1], W0, W1, W1, G.L1_elems);
     else run_stage_backward<C>(G.st[1], p->mesh, W0, W1, W1, PK, st, &p->launches);
-    if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_INVERSE); p->lib_launches++; }
+    if (p->own_fft[0]) { fft_strided_launch<C>(W1, (int)L.n[0], G.S1, G.S1, 1, (const C *)p->d_tw[0], st); p->launches++; }
+    else if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_INVERSE); p->lib_launches++; }
     // L1 in W1 -> g1
     if (peer) peer_stage_backward(p, 0, p->d_g1, 0, false);
     else run_stage_backward<C>(G.st[0], p->mesh, W1, W0, p->d_g1, PK, st, &p->launches);
@@ -817,7 +855,7 @@ template <class R> struct Core {
     if ((flags & N_MALLOC_F) && nd->f) { if (is_device_ptr(nd->f)) cudaFree(nd->f); else cudaFreeHost(nd->f); }
     if ((flags & N_MALLOC_GRAD_F) && nd->grad_f) { if (is_device_ptr(nd->grad_f)) cudaFree(nd->grad_f); else cudaFreeHost(nd->grad_f); }
     if ((flags & N_MALLOC_HESSIAN_F) && nd->hessian_f) cudaFreeHost(nd->hessian_f);
-    cudaFree(nd->d_x); cudaFree(nd->d_f); cudaFree(nd->d_grad_f); cudaFree(nd->d_wtab); cudaFree(nd->d_vals);
+    cudaFree(nd->d_x); cudaFree(nd->d_f); cudaFree(nd->d_grad_f); cudaFree(nd->d_hess); cudaFree(nd->d_wtab); cudaFree(nd->d_vals);
     for (int k = 0; k < 2; k++) {
       BinState<R> &b = k ? nd->il : *static_cast<BinState<R> *>(nd);
       cudaFree(b.d_tile); cudaFree(b.d_tile_sorted); cudaFree(b.d_perm); cudaFree(b.d_idx);
@@ -1389,6 +1427,30 @@ template <class R> struct Core {
     p->launches++;
   }
 
+  static void run_ik2(P *p, const C *in, C *out, int comp) {
+    static const int t1[6] = {0, 0, 0, 1, 1, 2}, t2[6] = {0, 1, 2, 1, 2, 2};
+    const FhatGeom fg = fhat_geom(p, 0);
+    if (fg.l[0] <= 0 || fg.l[1] <= 0 || fg.l[2] <= 0) return;
+    int ax[3], a = 0, b = 0;
+    fhat_axes(p, ax);
+    for (int k = 0; k < 3; k++) { if (ax[k] == t1[comp]) a = k; if (ax[k] == t2[comp]) b = k; }
+    const int bs = fg.l[2] >= 128 ? 128 : 32;
+    k_ik_scale2<R, C><<<grid3(fg.l[0], fg.l[1], fg.l[2], bs), bs, 0, p->stream>>>(in, out, a, b, fg);
+    p->launches++;
+  }
+  // Hessian with analytic window derivatives: one generic pass over the padded grid the gather just read
+  static void launch_hessian(P *p, const NodeArgs<R> &na, R *dh) {
+    if (na.M == 0 || !dh) return;
+    const GridGeom<R> g = geom(p);
+    const int wpb = 8;
+    const size_t smem = (size_t)wpb * 9 * g.cutoff * sizeof(R);
+    const int nblk = (na.M + wpb - 1) / wpb;
+    if (p->L.c2r) k_hessian_generic<R, false><<<nblk, wpb * 32, smem, p->stream>>>(g, (const R *)p->d_grid, na, dh);
+    else k_hessian_generic<R, true><<<nblk, wpb * 32, smem, p->stream>>>(g, (const R *)p->d_grid, na, dh);
+    PNB_CUDA(cudaGetLastError());
+    p->launches++;
+  }
+
   static void rec(P *p, int i) { PNB_CUDA(cudaEventRecord(p->ev[i], p->stream)); }
   static double ms(P *p, int a, int b) { float t = 0; cudaEventElapsedTime(&t, p->ev[a], p->ev[b]); return (double)t; }
 
@@ -1420,7 +1482,11 @@ template <class R> struct Core {
     const int NC = L.c2r ? 1 : 2;
     const bool ik = (p->pnfft_flags & F_DIFF_IK) != 0;
     const int npass = (p->pnfft_flags & F_INTERLACED) ? 2 : 1;   // reference api-basic.c:233-240
-    hessian_unsupported(p, nd, cf);
+    const bool want_h = (cf & C_HESSIAN_F) && nd && nd->hessian_f;      // reference api-basic.c:148-166 (ik), assign.c:881 (AD)
+    if ((cf & C_HESSIAN_F) && nd && !nd->hessian_f && !p->warned_hessian) {
+      fprintf(stderr, "pnfft-b200: PNFFT_COMPUTE_HESSIAN_F without hessian_f (PNFFT_MALLOC_HESSIAN_F / pnfft_set_hessian_f)\n");
+      p->warned_hessian = true;
+    }
     rec(p, 0);
     // ---- f_hat on the device ----
     const C *fh = nullptr;
@@ -1436,7 +1502,7 @@ template <class R> struct Core {
     PNB_CUDA(cudaEventRecord(p->ev_copy[0], st));
     p->x_via_copy_stream = !no_prefetch;
 
-    R *df = nullptr, *dg = nullptr;
+    R *df = nullptr, *dg = nullptr, *dh = nullptr;
     const R *dx = nullptr;
     const bool conv = !(cf & C_OMIT_CONV);
     const bool acc = (cf & C_ACCUMULATED) != 0;
@@ -1454,6 +1520,7 @@ template <class R> struct Core {
         if (pass == 0) {
           if (cf & C_F) df = dev_in(p, nd->f, &nd->d_f, &nd->cap_f, (size_t)NC * M, acc);
           if (cf & C_GRAD_F) dg = dev_in(p, nd->grad_f, &nd->d_grad_f, &nd->cap_grad, (size_t)3 * NC * M, acc);
+          if (want_h) dh = dev_in(p, nd->hessian_f, &nd->d_hess, &nd->cap_hess, (size_t)6 * NC * M, acc);
         }
       };
       auto base_args = [&]() {
@@ -1500,6 +1567,7 @@ template <class R> struct Core {
           p->b_phase = 2;
           if (df || dg) launch_B_any(p, nd, na_side, false);
           p->b_phase = 3;
+          if (dh) launch_hessian(p, na_side, dh);
           rec(p, 7);
         } else if (conv) {
           node_setup();
@@ -1509,11 +1577,12 @@ template <class R> struct Core {
           na.f = df; na.grad = dg;
           if (na.grad && na.pre_psi && !na.pre_dpsi) na.pre_psi = nullptr;   // no dpsi table: evaluate on the fly
           if (df || dg) launch_B_any(p, nd, na, false);
+          if (dh) launch_hessian(p, na, dh);
           rec(p, 7);
         } else { rec(p, 4); rec(p, 5); rec(p, 6); rec(p, 7); }
       } else {
         // ik differentiation: 1 (f) + 3 (grad) passes of F and B (reference api-basic.c:100-167)
-        if ((cf & C_GRAD_F) && !(cf & C_OMIT_DECONV))
+        if (((cf & C_GRAD_F) || want_h) && !(cf & C_OMIT_DECONV))
           PNB_CUDA(cudaMemcpyAsync(p->d_g1_buffer, p->d_g1, sizeof(C) * nloc, cudaMemcpyDeviceToDevice, st));
         rec(p, 3);
         if (conv) node_setup(); else { rec(p, 4); rec(p, 5); }
@@ -1527,6 +1596,12 @@ template <class R> struct Core {
             if (!(cf & C_OMIT_FFT)) fft_forward(p);
             if (conv) { halo(p, false); NodeArgs<R> na = base_args(); na.f = dg; na.f_stride = 3; na.f_off = dim; launch_B_any(p, nd, na, false); }
           }
+        if (want_h)
+          for (int comp = 0; comp < 6; comp++) {
+            if (!(cf & C_OMIT_DECONV)) run_ik2(p, p->d_g1_buffer, p->d_g1, comp);
+            if (!(cf & C_OMIT_FFT)) fft_forward(p);
+            if (conv) { halo(p, false); NodeArgs<R> na = base_args(); na.f = dh; na.f_stride = 6; na.f_off = comp; launch_B_any(p, nd, na, false); }
+          }
         rec(p, 6); rec(p, 7);
       }
       if (pass) nd->swap_il();
@@ -1536,6 +1611,7 @@ template <class R> struct Core {
     if (conv) {
       if (df && !is_device_ptr(nd->f)) PNB_CUDA(cudaMemcpyAsync(nd->f, df, sizeof(R) * NC * M, cudaMemcpyDeviceToHost, st));
       if (dg && !is_device_ptr(nd->grad_f)) PNB_CUDA(cudaMemcpyAsync(nd->grad_f, dg, sizeof(R) * 3 * NC * M, cudaMemcpyDeviceToHost, st));
+      if (dh && !is_device_ptr(nd->hessian_f)) PNB_CUDA(cudaMemcpyAsync(nd->hessian_f, dh, sizeof(R) * 6 * NC * M, cudaMemcpyDeviceToHost, st));
     }
     rec(p, 8);
     p->x_via_copy_stream = false;

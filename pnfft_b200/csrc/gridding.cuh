@@ -321,6 +321,71 @@ __global__ void __launch_bounds__(256) k_gather_generic(GridGeom<R> g, const R *
   }
 }
 
+// Hessian of the trafo at the nodes with analytic window derivatives (reference kernel/assign.c:881-1027 with the tables
+// of kernel/ndft-parallel.c:1956-2105): one warp per node, any cutoff, padded grid in global memory.  Components in the
+// reference's order xx, xy, xz, yy, yz, zz.  The windows are always evaluated on the fly (exact formulas).
+template <class R, bool CPLX>
+__global__ void __launch_bounds__(256) k_hessian_generic(GridGeom<R> g, const R *__restrict__ grid, NodeArgs<R> na, R *__restrict__ hess) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R *scratch = reinterpret_cast<R *>(smem_raw);
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (p >= na.M) return;
+  const int c = g.cutoff;
+  R *psi_s = scratch + (size_t)wib * 9 * c, *dpsi_s = psi_s + 3 * c, *ddpsi_s = psi_s + 6 * c;
+  const int j = na.perm ? na.perm[p] : p;
+  R xs[3] = {na.x[3 * (size_t)j], na.x[3 * (size_t)j + 1], na.x[3 * (size_t)j + 2]}, nx[3], fl[3];
+  int cell[3];
+  project_node(g, xs, nx, fl, cell);
+  bool inside = true;
+  for (int t = 0; t < 3; t++) inside = inside && cell[t] >= 0 && cell[t] < g.lno[t] + g.il_on;
+  warp_window_eval(g, nx, fl, lane, psi_s, dpsi_s, true);
+  __syncwarp();
+  for (int v = lane; v < 3 * c; v += 32) {
+    const int t = v / c, s = v - t * c;
+    const R y = fl[t] - nx[t] - (R)g.m + (R)s;
+    ddpsi_s[v] = window_ddtap<R>(g.kind, y, g.n[t], g.b[t], g.m, psi_s[v], dpsi_s[v]);
+  }
+  __syncwarp();
+  if (g.wscale != (R)1) for (int v = lane; v < c; v += 32) { psi_s[v] *= g.wscale; dpsi_s[v] *= g.wscale; ddpsi_s[v] *= g.wscale; }
+  __syncwarp();
+  constexpr int NC = CPLX ? 2 : 1;
+  R h[6][2];
+  for (int q = 0; q < 6; q++) { h[q][0] = 0; h[q][1] = 0; }
+  if (inside) {
+    const long long base = (long long)cell[0] * g.pitch0 + (long long)cell[1] * g.pitch1 + cell[2];
+    for (int q = lane; q < c * c; q += 32) {
+      const int l1 = q / c, l2 = q - l1 * c;
+      R s0[2] = {0, 0}, s1[2] = {0, 0}, s2[2] = {0, 0};     // sums over x with psi, dpsi, ddpsi
+      const long long off = base + (long long)l1 * g.pitch1 + l2;
+      for (int l0 = 0; l0 < c; l0++) {
+        const long long i = off + (long long)l0 * g.pitch0;
+        R v0, v1 = 0;
+        if (CPLX) { v0 = grid[2 * i]; v1 = grid[2 * i + 1]; } else { v0 = grid[i]; }
+        const R w = psi_s[l0], dw = dpsi_s[l0], ddw = ddpsi_s[l0];
+        s0[0] += w * v0; s0[1] += w * v1; s1[0] += dw * v0; s1[1] += dw * v1; s2[0] += ddw * v0; s2[1] += ddw * v1;
+      }
+      const R w1 = psi_s[c + l1], d1 = dpsi_s[c + l1], dd1 = ddpsi_s[c + l1];
+      const R w2 = psi_s[2 * c + l2], d2 = dpsi_s[2 * c + l2], dd2 = ddpsi_s[2 * c + l2];
+      for (int k = 0; k < NC; k++) {
+        h[0][k] += w1 * w2 * s2[k];      // xx
+        h[1][k] += d1 * w2 * s1[k];      // xy
+        h[2][k] += w1 * d2 * s1[k];      // xz
+        h[3][k] += dd1 * w2 * s0[k];     // yy
+        h[4][k] += d1 * d2 * s0[k];      // yz
+        h[5][k] += w1 * dd2 * s0[k];     // zz
+      }
+    }
+  }
+  for (int q = 0; q < 6; q++)
+    for (int k = 0; k < NC; k++) h[q][k] = warp_sum(h[q][k]);
+  if (lane == 0) {
+    R *o = hess + (size_t)j * 6 * NC;
+    for (int q = 0; q < 6; q++)
+      for (int k = 0; k < NC; k++) o[q * NC + k] = na.accumulate ? o[q * NC + k] + h[q][k] : h[q][k];
+  }
+}
+
 template <class R, bool CPLX>
 __global__ void __launch_bounds__(256) k_scatter_generic(GridGeom<R> g, R *__restrict__ grid, NodeArgs<R> na) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

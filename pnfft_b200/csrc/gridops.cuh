@@ -95,6 +95,24 @@ __global__ void k_ik_scale(const C *__restrict__ in, C *__restrict__ out, int mo
     }
 }
 
+// Hessian by ik differentiation (reference kernel/ndft-parallel.c:3056-3087): out = -4 pi^2 k_a k_b in, a / b the MEMORY
+// axes that carry the two differentiated dimensions
+template <class R, class C>
+__global__ void k_ik_scale2(const C *__restrict__ in, C *__restrict__ out, int axis_a, int axis_b, FhatGeom fg) {
+  const int iC = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iC >= fg.l[2]) return;
+  const R m4pi2 = (R)(-4.0 * 3.14159265358979323846 * 3.14159265358979323846);
+  for (int iA = blockIdx.z; iA < fg.l[0]; iA += gridDim.z)
+    for (int iB = blockIdx.y; iB < fg.l[1]; iB += gridDim.y) {
+      const size_t i = ((size_t)iA * fg.l[1] + iB) * fg.l[2] + iC;
+      const int k[3] = {fg.s[0] + iA, fg.s[1] + iB, fg.s[2] + iC};
+      const R w = m4pi2 * (R)k[axis_a] * (R)k[axis_b];
+      const C v = in[i];
+      C o; o.x = w * v.x; o.y = w * v.y;
+      out[i] = o;
+    }
+}
+
 inline dim3 grid3(int l0, int l1, int l2, int bs) {
   return dim3((unsigned)((l2 + bs - 1) / bs), (unsigned)(l1 < 65535 ? l1 : 65535), (unsigned)(l0 < 1024 ? l0 : 1024));
 }

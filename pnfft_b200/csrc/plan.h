@@ -198,6 +198,9 @@ template <class R> struct Plan {
   // FFT plans
   cufftHandle fft_x = 0, fft_y = 0, fft_z_fwd = 0, fft_z_bwd = 0;
   bool fft_ready = false;
+  // own FFT kernels (fftown.cuh) per axis: power-of-two complex lengths; the twiddle tables exp(-2 pi i q / n)
+  bool own_fft[3] = {false, false, false};
+  void *d_tw[3] = {nullptr, nullptr, nullptr};
 
   // timers (seconds), reference slots api/pnfft.h:407-418
   double timer_trafo[10], timer_adj[10];
@@ -249,12 +252,12 @@ template <class R> struct Nodes : BinState<R> {
   R *x = nullptr;
   R *f = nullptr;          // C[M] (c2c) or R[M] (c2r), user pointer (host or device)
   R *grad_f = nullptr;     // 3 per node
-  R *hessian_f = nullptr;  // accepted, never computed
+  R *hessian_f = nullptr;  // 6 per node (xx, xy, xz, yy, yz, zz), trafo only
   unsigned precompute_flags = 0;
 
   // device mirrors (allocated when the user arrays live on the host)
-  R *d_x = nullptr, *d_f = nullptr, *d_grad_f = nullptr;
-  size_t cap_x = 0, cap_f = 0, cap_grad = 0;
+  R *d_x = nullptr, *d_f = nullptr, *d_grad_f = nullptr, *d_hess = nullptr;
+  size_t cap_x = 0, cap_f = 0, cap_grad = 0, cap_hess = 0;
 
   BinState<R> il;          // the same for the shifted nodes of the second interlacing pass
   void swap_il() { BinState<R> t = *static_cast<BinState<R> *>(this); *static_cast<BinState<R> *>(this) = il; il = t; }

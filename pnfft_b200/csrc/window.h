@@ -250,6 +250,43 @@ template <class R> PNB_HD void window_tap(int kind, R y, R n, R b, int m, bool w
   if (want_d) *dpsi_out = dpsi;
 }
 
+// second derivative of the window with respect to x (reference kernel/ndft-parallel.c:2010-2105, 2220-2285), from the
+// tap's value and first derivative; y as in window_tap (z = -y = n x - l)
+template <class R> PNB_HD R window_ddtap(int kind, R y, R n, R b, int m, R psi, R dpsi) {
+  const R pi = m_pi<R>();
+  const R z = -y;
+  switch (kind) {
+    case WIN_GAUSSIAN:
+      return (R)2 * n * n / b * ((R)2 / b * z * z - (R)1) * psi;
+    case WIN_SINC_POWER: {
+      const R w = pi * z / b, c = pi * n / b;
+      if (m_fabs(w) > m_eps<R>()) {
+        const R ct = (R)1 / m_tan(w);
+        return (R)2 * (R)m * c * (ct - (R)1 / w) * dpsi + (R)2 * (R)m * c * c * ((R)1 / (w * w) - (R)1 - ct * ct) * psi;
+      }
+      return (R)(-2.0) * (R)m * c * c / ((R)3 * b);
+    }
+    case WIN_BSPLINE:
+      return n * n * (bspline<R>(2 * m - 2, y + (R)m) - (R)2 * bspline<R>(2 * m - 2, y + (R)m - (R)1) + bspline<R>(2 * m - 2, y + (R)m - (R)2));
+    case WIN_BESSEL_I0: {
+      const R d = (R)m * (R)m - z * z;
+      if (d < 0) return (R)0;
+      if (d > 0) {
+        const R r = m_sqrt(d), yy = z * z;
+        return (R)0.5 * b * n * n / d * (b * yy * bessel_i<R>(0, b * r) - bessel_i<R>(1, b * r) / r * (yy + (R)m * (R)m));
+      }
+      return (b * b * (R)m * n) * (b * b * (R)m * n) / (R)16 - (b * n) * (b * n) / (R)4;
+    }
+    default: {   // Kaiser-Bessel
+      const R d = (R)m * (R)m - z * z;
+      const R r = m_sqrt(m_fabs(d));
+      if (d < 0) return (R)3 * n * z * dpsi / d + n * n * psi / d * ((R)1 + (b * z) * (b * z)) - b * n * n / (pi * d) * m_cos(b * r);
+      if (d > 0) return (R)3 * n * z * dpsi / d + n * n * psi / d * ((R)1 + (b * z) * (b * z)) - b * n * n / (pi * d) * m_cosh(b * r);
+      return b * (b * n) * (b * n) / ((R)15 * pi) * ((b * (R)m) * (b * (R)m) - (R)5);
+    }
+  }
+}
+
 // ---- Fourier coefficients of the window (host only in practice: 3 tables per plan) ----
 template <class R> inline R phi_hat_any(int kind, long k, long n, R b, int m, bool inverse) {
   const R pi = m_pi<R>();

@@ -43,6 +43,66 @@ def test_golden_fixture(case, variant):
     assert rel_l2(fh, g["out_f_hat"]) <= gtol
 
 
+@pytest.mark.parametrize("single", [False, True])
+@pytest.mark.parametrize("N", [(16, 16, 16), (32, 8, 64)])
+def test_own_fft_kernels(N, single, monkeypatch):
+    """PNFFT_B200_OWN_FFT=1: the x / y / z passes on the library's own radix-8/4/2 shared-memory kernels (fftown.cuh, the z
+    pass fused with the embed into / extract from the padded grid) give the transform cuFFT gives."""
+    M = 3000
+    x, fh, f, g = make_inputs(N, M, 33, c2r=False, single=single)
+    res = []
+    for own in ("0", "1"):
+        monkeypatch.setenv("PNFFT_B200_OWN_FFT", own)
+        run = Run1(N, x, m=4, single=single)
+        fo, go = run.trafo(fh, F | G)
+        fho = run.adj(f, g, F | G)
+        run.close()
+        res.append((fo, go, fho))
+    tol = 2e-5 if single else 1e-13
+    for a, b in zip(res[0], res[1]):
+        assert rel_l2(a, b) <= tol
+
+
+HCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "h_*.npz")))
+
+
+@pytest.mark.parametrize("case", HCASES)
+def test_hessian_golden(case):
+    """PNFFT_COMPUTE_HESSIAN_F (reference api/api-basic.c:148-166, kernel/assign.c:881-1027): analytic second derivatives
+    of every window and ik differentiation, c2c / c2r, against fixtures from the unmodified reference; f and grad_f of the
+    same call must not change."""
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    single, c2r = bool(g["single"]), bool(g["c2r"])
+    tol = 1e-5 if single else 1e-13
+    # float: the analytic second derivative of sinc-power / Kaiser-Bessel amplifies the rounding of psi, dpsi (see the
+    # gradient note in tests/test_oracle.py); the double fixtures pin the formulas
+    htol = 2e-4 if single else 1e-13
+    if "sinc_power" in case and "_ad_" in case and not single:
+        # the reference's own formula (kernel/ndft-parallel.c:2048-2052) takes 1/y^2 - 1 - cot(y)^2 with y = pi (u - s) / b:
+        # for a node close to a grid line (here |y| ~ 1e-3) six digits cancel, so two correct evaluations of it differ by
+        # ~1e-10 (one ulp of tan() is enough).  Conditioning of the reference formula, not of the kernel: the other windows hold 1e-13.
+        htol = 1e-8
+    run = Run1(tuple(g["N"]), g["x"], m=int(g["m"]), flags=int(g["flags"]), c2r=c2r, single=single)
+    f, gr, h = run.trafo_hessian(g["f_hat"], F | G | A.COMPUTE_HESSIAN_F)
+    run.close()
+    assert rel_l2(f, g["out_f"]) <= tol
+    assert rel_l2(gr, g["out_grad_f"]) <= (1e-4 if (single and "sinc_power" in case) else tol)
+    assert rel_l2(h, g["out_hessian_f"]) <= htol
+
+
+def test_hessian_only_and_accumulated():
+    """COMPUTE_HESSIAN_F alone (no f / grad_f requested) and with PNFFT_COMPUTE_ACCUMULATED: h0 + H."""
+    g = np.load(os.path.join(GOLD, "h_kaiser_bessel_ad_c2c_m6_d.npz"))
+    run = Run1(tuple(g["N"]), g["x"], m=6, flags=int(g["flags"]))
+    _, _, h = run.trafo_hessian(g["f_hat"], A.COMPUTE_HESSIAN_F)
+    assert rel_l2(h, g["out_hessian_f"]) <= 1e-13
+    run.h[...] = 1.0 + 2.0j
+    run.put_f_hat(g["f_hat"])
+    run.plan.trafo(run.nodes, A.COMPUTE_HESSIAN_F | A.COMPUTE_ACCUMULATED)
+    assert rel_l2(run.h - (1.0 + 2.0j), g["out_hessian_f"]) <= 1e-13
+    run.close()
+
+
 @pytest.mark.parametrize("m", [4, 6])
 @pytest.mark.parametrize("single", [False, True])
 @pytest.mark.parametrize("c2r", [False, True])

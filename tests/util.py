@@ -79,6 +79,15 @@ class Run1:
         self.plan.trafo(self.nodes, cf)
         return self.f.copy(), self.g.copy()
 
+    def trafo_hessian(self, f_hat, cf):
+        """trafo with PNFFT_COMPUTE_HESSIAN_F among cf: returns f, grad_f, hessian_f [M, 6]"""
+        ft = self.rdt if self.c2r else self.cdt
+        self.h = np.zeros((self.M, 6), ft)
+        self.nodes.set_hessian_f(self.h)
+        self.put_f_hat(f_hat)
+        self.plan.trafo(self.nodes, cf)
+        return self.f.copy(), self.g.copy(), self.h.copy()
+
     def adj(self, f, g, cf, f_hat0=None):
         if f is not None:
             self.f[...] = f

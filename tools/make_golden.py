@@ -181,5 +181,37 @@ def main():
     print("wrote %d transform cases + layouts.npz + node_index.npz to %s" % (len(cases), out))
 
 
+def hessian_cases(out):
+    """PNFFT_COMPUTE_HESSIAN_F (trafo only): analytic window second derivatives for every window, ik differentiation,
+    c2c and c2r, double and float; the six components in the reference's order xx, xy, xz, yy, yz, zz."""
+    names = []
+    seed = 900
+    for single in (False, True):
+        ref = refdrv.get(single)
+        for win, wf in WIN.items():
+            for ik in (0, DIFF_IK):
+                for c2r in (False, True):
+                    if c2r and ik:
+                        continue
+                    if single and (win not in ("kaiser_bessel", "gaussian") or c2r):
+                        continue
+                    m = 6 if win == "kaiser_bessel" else 5
+                    N, M = (8, 12, 10), 100
+                    seed += 1
+                    x, fh, _, _ = inputs(N, M, seed, c2r, single)
+                    flags = wf | ik
+                    rt = ref.trafo(N, x, fh, m=m, pnfft_flags=flags, compute_flags=7, c2r=c2r)
+                    name = "h_%s_%s_%s_m%d_%s" % (win, "ik" if ik else "ad", "c2r" if c2r else "c2c", m, "f" if single else "d")
+                    np.savez_compressed(os.path.join(out, name + ".npz"), N=np.array(N), m=m, flags=flags, c2r=c2r, single=single,
+                                        x=x, f_hat=fh, out_f=rt["f"], out_grad_f=rt["grad_f"], out_hessian_f=rt["hessian_f"])
+                    names.append(name)
+    print("wrote %d Hessian cases" % len(names))
+    return names
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--hessian":       # round-2 addition: leaves the other fixtures untouched
+        hessian_cases(os.path.join(ROOT, "tests", "golden"))
+    else:
+        main()
+        hessian_cases(os.path.join(ROOT, "tests", "golden"))
