@@ -163,7 +163,9 @@ template <class R> struct Core {
     g.pitch1 = p->L.pitch2;
     g.pitch0 = (long long)p->L.ngc[1] * p->L.pitch2;
     g.exp_const = p->d_exp_const;
-    g.poly = (p->use_poly && p->poly_deg >= 0) ? p->d_poly : nullptr;
+    g.poly = (p->use_poly && p->poly_deg >= 0 && p->intpol_order < 0) ? p->d_poly : nullptr;
+    g.intpol_order = p->intpol_order; g.intpol_num = p->intpol_num;
+    for (int q = 0; q < 9; q++) g.intpol_tab[q] = p->d_intpol[q];
     g.poly_deg = p->poly_deg;
     g.poly_deg_psi = p->poly_deg_psi;
     const bool il = (p->pnfft_flags & F_INTERLACED) != 0;
@@ -195,6 +197,40 @@ template <class R> struct Core {
       PNB_CUDA(cudaMemcpy(p->d_exp_const, h.data(), sizeof(R) * h.size(), cudaMemcpyHostToDevice));
     }
     fit_window_polys(p);
+    build_intpol_tables(p);
+  }
+
+  // PNFFT_PRE_{CONST,LIN,QUAD,CUB}_PSI tables (reference init_intpol_table_psi kernel/ndft-parallel.c:321-353, sizes
+  // :1088-1122): entry [k][c][i] = psi((m + (k + i) / num - c) / n), i = -order/2 .. (order+1)/2, for psi, dpsi, ddpsi
+  static void build_intpol_tables(P *p) {
+    if (p->intpol_order < 0) return;
+    const Layout &L = p->L;
+    const int c = L.cutoff, m = L.m, o = p->intpol_order;
+    p->intpol_num = (int)std::ceil((2.0 * 15.0 + 1.0) / c) * 2048;
+    const size_t len = (size_t)p->intpol_num * c * (o + 1);
+    std::vector<R> h(len);
+    for (int q = 0; q < 3; q++)
+      for (int t = 0; t < 3; t++) {
+        const R n = (R)L.n[t], b = p->b[t];
+        size_t ind = 0;
+        for (int k = 0; k < p->intpol_num; k++)
+          for (int cc = 0; cc < c; cc++)
+            for (int i = -o / 2; i <= (o + 1) / 2; i++, ind++) {
+              const R x = ((R)m + (R)(k + i) / (R)p->intpol_num - (R)cc) / n;      // the reference's argument, its arithmetic
+              const R z = n * x;
+              R psi = 0, d = 0;
+              if (p->kind == WIN_BSPLINE) {
+                psi = bspline<R>(2 * m, z + (R)m);
+                d = n * (bspline<R>(2 * m - 1, z + (R)m) - bspline<R>(2 * m - 1, z + (R)m - (R)1));
+              } else {
+                window_tap<R>(p->kind, -z, n, b, m, true, &psi, &d);
+              }
+              h[ind] = q == 0 ? psi : (q == 1 ? d : window_ddtap<R>(p->kind, -z, n, b, m, psi, d));
+            }
+        R *&dst = p->d_intpol[3 * q + t];
+        if (!dst) PNB_CUDA(cudaMalloc((void **)&dst, sizeof(R) * len));
+        PNB_CUDA(cudaMemcpy(dst, h.data(), sizeof(R) * len, cudaMemcpyHostToDevice));
+      }
   }
 
 
@@ -310,6 +346,14 @@ template <class R> struct Core {
     MPI_Comm_dup(comm_cart, &p->comm);
     p->pnfft_flags = pnfft_flags; p->pfft_flags = pfft_flags;
     p->kind = window_kind(pnfft_flags);
+    {
+      // interpolation order, with the reference's precedence (kernel/ndft-parallel.c:997-1006) AND its flag promotion
+      // (api/api-guru.c:152-155 tests the plan flags against precompute-namespace constants: PNFFT_PRE_LIN_PSI (1 << 3)
+      // turns PNFFT_PRE_CONST_PSI (1 << 2) on, so "linear" interpolates with order 0 there; a drop-in does the same)
+      unsigned fl = pnfft_flags;
+      if (fl & (1u << 3)) fl |= 1u << 2;
+      p->intpol_order = (fl & (1u << 2)) ? 0 : ((fl & (1u << 3)) ? 1 : ((fl & (1u << 4)) ? 2 : ((fl & (1u << 5)) ? 3 : -1)));
+    }
     compute_layout<R>(p->L, mesh, N, n, x_max, m, c2r, pnfft_flags);
     Layout &L = p->L;
     for (int t = 0; t < 3; t++) {
@@ -604,6 +648,7 @@ template <class R> struct Core {
     cudaFree(p->d_f_hat); cudaFree(p->d_g1); cudaFree(p->d_g1_buffer); cudaFree(p->d_grid);
     cudaFree(p->d_work[0]); cudaFree(p->d_work[1]); cudaFree(p->d_work[2]); cudaFree(p->d_exp_const); cudaFree(p->d_sort_tmp); cudaFree(p->d_poly);
     for (int t = 0; t < 3; t++) cudaFree(p->d_invphi[t]);
+    for (int q = 0; q < 9; q++) cudaFree(p->d_intpol[q]);
     for (int t = 0; t < 3; t++) {
       bool shared = false;
       for (int u = 0; u < t; u++) if (p->d_tw[u] == p->d_tw[t]) shared = true;

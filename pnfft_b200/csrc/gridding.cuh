@@ -53,12 +53,37 @@ template <class R> __device__ __forceinline__ void warp_scale_x(const GridGeom<R
   for (int v = lane; v < g.cutoff; v += 32) { psi_s[v] *= g.wscale; if (want_d) dpsi_s[v] *= g.wscale; }
 }
 
+// PNFFT_PRE_*_PSI: tap s of an axis from its interpolation table (reference pre_tensor_intpol, kernel/ndft-parallel.c:1586-1617,
+// stencils kernel/ipnfft.h:450-495); dist = n x - floor(n x) in [0, 1)
+template <class R> __device__ __forceinline__ R intpol_tap(const GridGeom<R> &g, const R *__restrict__ tab, int s, R dist) {
+  const R dn = dist * (R)g.intpol_num;
+  const long long k0 = (long long)m_floor(dn);
+  const R d = dn - (R)k0;
+  const int o1 = g.intpol_order + 1;
+  const R *f = tab + (k0 * g.cutoff + s) * o1;
+  switch (g.intpol_order) {
+    case 0: return f[0];
+    case 1: return f[0] * ((R)1 - d) + f[1] * d;
+    case 2: { const R c0 = d + (R)1, c1 = d, c2 = d - (R)1; return (R)0.5 * f[0] * c1 * c2 - c0 * f[1] * c2 + (R)0.5 * c0 * c1 * f[2]; }
+    default: {
+      const R c0 = d + (R)1, c1 = d, c2 = d - (R)1, c3 = d - (R)2;
+      return (-f[0] * c1 * c2 * c3 + (R)3 * c0 * f[1] * c2 * c3 - (R)3 * c0 * c1 * f[2] * c3 + c0 * c1 * c2 * f[3]) / (R)6;
+    }
+  }
+}
+
 // 3*(2m+1) window values (and AD-gradient weights) of one node, computed by one warp into psi_s/dpsi_s.
 template <class R>
 __device__ __forceinline__ void warp_window_eval(const GridGeom<R> &g, const R *nx, const R *fl, int lane,
                                                  R *psi_s, R *dpsi_s, bool want_d) {
   const int c = g.cutoff;
-  if (g.kind == WIN_BSPLINE) {
+  if (g.intpol_order >= 0) {
+    for (int v = lane; v < 3 * c; v += 32) {
+      const int t = v / c, s = v - t * c;
+      psi_s[v] = intpol_tap(g, g.intpol_tab[t], s, nx[t] - fl[t]);
+      if (want_d) dpsi_s[v] = intpol_tap(g, g.intpol_tab[3 + t], s, nx[t] - fl[t]);
+    }
+  } else if (g.kind == WIN_BSPLINE) {
     if (lane < 3) bspline_taps<R>(g.m, nx[lane] - fl[lane], g.n[lane], psi_s + lane * c, want_d ? dpsi_s + lane * c : nullptr);
   } else if (g.kind == WIN_GAUSSIAN && g.fast_gauss) {
     // reference kernel/ndft-parallel.c:1694-1714: exp(-d^2/b) * exp(2d/b)^s * exp_const[s], d = n x - (floor - m)
@@ -344,7 +369,8 @@ __global__ void __launch_bounds__(256) k_hessian_generic(GridGeom<R> g, const R 
   for (int v = lane; v < 3 * c; v += 32) {
     const int t = v / c, s = v - t * c;
     const R y = fl[t] - nx[t] - (R)g.m + (R)s;
-    ddpsi_s[v] = window_ddtap<R>(g.kind, y, g.n[t], g.b[t], g.m, psi_s[v], dpsi_s[v]);
+    if (g.intpol_order >= 0) ddpsi_s[v] = intpol_tap(g, g.intpol_tab[6 + t], s, nx[t] - fl[t]);
+    else ddpsi_s[v] = window_ddtap<R>(g.kind, y, g.n[t], g.b[t], g.m, psi_s[v], dpsi_s[v]);
   }
   __syncwarp();
   if (g.wscale != (R)1) for (int v = lane; v < c; v += 32) { psi_s[v] *= g.wscale; dpsi_s[v] *= g.wscale; ddpsi_s[v] *= g.wscale; }

@@ -98,6 +98,12 @@ template <class R> struct GridGeom {
   // PNFFT_INTERLACED (reference kernel/ndft-parallel.c:2732-2753): in the second pass every node is shifted by half a mesh
   // width, x_t += 0.5 / n_t, and folded back into [-0.5, 0.5) AFTER its grid index was taken; both passes weigh by 0.5
   // (kernel/assign.c:481,689), which the kernels fold into the x-axis window factors (a power of two: exact)
+  // PNFFT_PRE_{CONST,LIN,QUAD,CUB}_PSI (reference kernel/ndft-parallel.c:321-353, 1586-1617): window values looked up in
+  // tables of intpol_num nodes per grid interval and interpolated with order intpol_order (-1: direct evaluation);
+  // table of axis t, derivative q: intpol_tab[3 * q + t], laid out [node k][tap c][stencil point i]
+  int intpol_order;
+  int intpol_num;
+  const R *intpol_tab[9];
   int il_on;               // this pass shifts the nodes
   double il[3];            // 0.5 / n_t
   R wscale;                // 1, or 0.5 for the two passes of an interlaced plan
@@ -185,6 +191,9 @@ template <class R> struct Plan {
   R *d_invphi_plain[3] = {nullptr, nullptr, nullptr};  // without the sign (for OMIT_FFT paths)
   R *d_exp_const = nullptr;      // [3][cutoff] for FAST_GAUSSIAN
   R *d_poly = nullptr;           // window polynomials (see GridGeom::poly)
+  int intpol_order = -1;         // PNFFT_PRE_*_PSI interpolation order, -1: none
+  int intpol_num = 0;
+  R *d_intpol[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int poly_deg = -1, poly_deg_psi = -1;
   int use_poly = 1;
   void *d_grid = nullptr;        // padded grid [ngc0][ngc1][pitch2] of C (c2c) or R (c2r)

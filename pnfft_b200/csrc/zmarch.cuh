@@ -97,6 +97,11 @@ k_node_table(GridGeom<R> g, NodeArgs<R> na, int ncomp, int with_vals, R *__restr
       rp[s] = na.pre_psi[(size_t)p * 3 * C + t * C + s];
       if (GRAD) rd[s] = na.pre_dpsi[(size_t)p * 3 * C + t * C + s];
     }
+  } else if (g.intpol_order >= 0) {
+    for (int s = 0; s < C; s++) {
+      rp[s] = intpol_tap(g, g.intpol_tab[t], s, fr);
+      if (GRAD) rd[s] = intpol_tap(g, g.intpol_tab[3 + t], s, fr);
+    }
   } else if (g.poly && fr != (R)0) {
     // per-tap polynomials in u = 2 frac - 1 (Core::fit_window_polys); all taps advance together (Horner)
     R psi[C], dpsi[GRAD ? C : 1];

@@ -134,6 +134,15 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab, int first) {
         psi[s] = na.pre_psi[(size_t)p * 3 * C + t * C + s];
         if (GRAD) dpsi[s] = na.pre_dpsi[(size_t)p * 3 * C + t * C + s];
       }
+    } else if (g.intpol_order >= 0) {
+      // (statically indexed like every other branch: psi / dpsi must stay in registers)
+      const R *tp0 = t == 0 ? g.intpol_tab[0] : (t == 1 ? g.intpol_tab[1] : g.intpol_tab[2]);
+      const R *tp1 = t == 0 ? g.intpol_tab[3] : (t == 1 ? g.intpol_tab[4] : g.intpol_tab[5]);
+#pragma unroll
+      for (int s = 0; s < C; s++) {
+        psi[s] = intpol_tap(g, tp0, s, fr);
+        if (GRAD) dpsi[s] = intpol_tap(g, tp1, s, fr);
+      }
     } else if (g.poly && fr != (R)0 && (!GRAD || g.poly_deg <= 16)) {
       // per-tap polynomials in u = 2 frac - 1 (Core::fit_window_polys); all taps advance together (Horner).  With the
       // gradient the exact formulas are cheaper than two degree > 16 Horner chains per tap (measured).

@@ -90,6 +90,46 @@ def test_hessian_golden(case):
     assert rel_l2(h, g["out_hessian_f"]) <= htol
 
 
+ICASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "i_*.npz")))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("case", ICASES)
+def test_intpol_golden(case, variant):
+    """PNFFT_PRE_{CONST,LIN,QUAD,CUB}_PSI (reference kernel/ndft-parallel.c:321-353, 1586-1617): window values, first and
+    second derivatives from interpolation tables.  The fixtures come from the unmodified reference, including its flag
+    promotion that makes PNFFT_PRE_LIN_PSI interpolate with order 0 (api/api-guru.c:152-155)."""
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    c2r = bool(g["c2r"])
+    run = Run1(tuple(g["N"]), g["x"], m=int(g["m"]), flags=int(g["flags"]), c2r=c2r, variant=variant)
+    f, gr, h = run.trafo_hessian(g["f_hat"], F | G | A.COMPUTE_HESSIAN_F)
+    fh = run.adj(g["f"], g["grad_f"], F | G)
+    run.close()
+    assert rel_l2(f, g["out_f"]) <= 1e-13
+    assert rel_l2(gr, g["out_grad_f"]) <= 1e-13
+    assert rel_l2(h, g["out_hessian_f"]) <= 1e-12
+    assert rel_l2(fh, g["out_f_hat"]) <= 1e-13
+
+
+@pytest.mark.parametrize("win", ["kaiser_bessel", "gaussian"])
+def test_intpol_quadratic_vs_direct(win):
+    """PNFFT_PRE_QUAD_PSI has no usable reference output (its flag bit doubles as PNFFT_REAL_F inside the reference's node
+    loop, kernel/ndft-parallel.c:2804-2838): the quadratic tables are checked against direct window evaluation instead; with
+    6144 table nodes per grid interval the interpolation error is far below 1e-8."""
+    N, M = (16, 16, 16), 2000
+    x, fh, f, g = make_inputs(N, M, 77)
+    flags = A.WINDOW_GAUSSIAN if win == "gaussian" else 0
+    res = []
+    for fl in (flags, flags | (1 << 4)):
+        run = Run1(N, x, m=6, flags=fl)
+        fo, go = run.trafo(fh, F | G)
+        fho = run.adj(f, g, F | G)
+        run.close()
+        res.append((fo, go, fho))
+    for a, b in zip(res[0], res[1]):
+        assert 0 < rel_l2(a, b) <= 1e-8
+
+
 def test_hessian_only_and_accumulated():
     """COMPUTE_HESSIAN_F alone (no f / grad_f requested) and with PNFFT_COMPUTE_ACCUMULATED: h0 + H."""
     g = np.load(os.path.join(GOLD, "h_kaiser_bessel_ad_c2c_m6_d.npz"))

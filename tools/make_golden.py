@@ -209,9 +209,42 @@ def hessian_cases(out):
     return names
 
 
+def intpol_cases(out):
+    """PNFFT_PRE_{CONST,LIN,QUAD,CUB}_PSI: window values (and their first / second derivatives) interpolated from the
+    reference's lookup tables; trafo with f, grad_f and hessian_f, adjoint with f and grad_f."""
+    names = []
+    seed = 1200
+    ref = refdrv.get(False)
+    # (no PNFFT_PRE_QUAD_PSI fixtures: bit 4 of the plan flags is also read as the node flag PNFFT_REAL_F inside the
+    # reference's node loop, kernel/ndft-parallel.c:2804-2838, so its quadratic runs drop the imaginary parts / return NaN)
+    for order, fl in (("const", 1 << 2), ("lin", 1 << 3), ("cub", 1 << 5)):
+        for win in ("kaiser_bessel", "gaussian", "bspline"):
+            for c2r in (False, True):
+                if c2r and win != "kaiser_bessel":
+                    continue
+                m = 6 if win == "kaiser_bessel" else 4
+                N, M = (8, 12, 10), 100
+                seed += 1
+                x, fh, f, g = inputs(N, M, seed, c2r, False)
+                flags = WIN[win] | fl
+                rt = ref.trafo(N, x, fh, m=m, pnfft_flags=flags, compute_flags=7, c2r=c2r)
+                ra = ref.adj(N, x, f=f, grad_f=g, m=m, pnfft_flags=flags, compute_flags=3, c2r=c2r)
+                name = "i_%s_%s_%s_m%d_d" % (order, win, "c2r" if c2r else "c2c", m)
+                np.savez_compressed(os.path.join(out, name + ".npz"), N=np.array(N), m=m, flags=flags, c2r=c2r, single=False,
+                                    x=x, f_hat=fh, f=f, grad_f=g, out_f=rt["f"], out_grad_f=rt["grad_f"],
+                                    out_hessian_f=rt["hessian_f"], out_f_hat=ra["f_hat"])
+                names.append(name)
+    print("wrote %d interpolation cases" % len(names))
+    return names
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "--hessian":       # round-2 addition: leaves the other fixtures untouched
-        hessian_cases(os.path.join(ROOT, "tests", "golden"))
+    gold = os.path.join(ROOT, "tests", "golden")
+    if len(sys.argv) > 1 and sys.argv[1] == "--hessian":       # round-2 additions: leave the other fixtures untouched
+        hessian_cases(gold)
+    elif len(sys.argv) > 1 and sys.argv[1] == "--intpol":
+        intpol_cases(gold)
     else:
         main()
-        hessian_cases(os.path.join(ROOT, "tests", "golden"))
+        hessian_cases(gold)
+        intpol_cases(gold)
