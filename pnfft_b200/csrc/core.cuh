@@ -672,13 +672,39 @@ template <class R> struct Core {
     cudaStream_t st = p->stream;
     C *W0 = (C *)p->d_work[0], *W1 = (C *)p->d_work[1], *PK = (C *)p->d_work[2];
     const bool peer = p->peer.on;
-    if (peer) peer_stage_forward(p, 0, W1); else run_stage_forward<C>(G.st[0], p->mesh, p->d_g1, W0, W1, PK, st, &p->launches);       // L1 in W1
-    if (p->own_fft[0]) { fft_strided_launch<C>(W1, (int)L.n[0], G.S1, G.S1, -1, (const C *)p->d_tw[0], st); p->launches++; }
-    else if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_FORWARD); p->lib_launches++; }
-    if (peer) peer_stage_forward(p, 1, W0); else run_stage_forward<C>(G.st[1], p->mesh, W1, W1, W0, PK, st, &p->launches);            // L3 in W0
-    if (p->own_fft[1]) { fft_strided_launch<C>(W0, (int)L.n[1], G.S3, G.S3, -1, (const C *)p->d_tw[1], st); p->launches++; }
-    else if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_FORWARD); p->lib_launches++; }
-    if (peer) peer_stage_forward(p, 2, W1); else run_stage_forward<C>(G.st[2], p->mesh, W0, W0, W1, PK, st, &p->launches);            // L4 in W1
+    auto fft_x = [&]() {
+      if (p->own_fft[0]) { fft_strided_launch<C>(W1, (int)L.n[0], G.S1, G.S1, -1, (const C *)p->d_tw[0], st); p->launches++; }
+      else if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_FORWARD); p->lib_launches++; }
+    };
+    auto fft_y = [&]() {
+      if (p->own_fft[1]) { fft_strided_launch<C>(W0, (int)L.n[1], G.S3, G.S3, -1, (const C *)p->d_tw[1], st); p->launches++; }
+      else if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_FORWARD); p->lib_launches++; }
+    };
+    if (peer) {
+      // Peer-memory re-distributions with FOUR flag barriers per transform instead of six: a stage's "every push has
+      // landed" barrier also tells that every rank is done with the stage's source buffers, which are the next stage's
+      // destinations, provided each rank zeroes what the next stage leaves untouched BEFORE it arrives.
+      //   W1 (L1) and W0 (L3) are idle when the transform starts: zeroed before the opening barrier;
+      //   W1 (L4) is the source of my stage-1 pushes: zeroed right after them, before the stage-1 barrier.
+      peer_zero_forward(p, 0, W1);
+      peer_zero_forward(p, 1, W0);
+      peer_barrier(p);                       // every rank is inside this transform, its L1 / L3 buffers zeroed and idle
+      peer_jobs<C>(p, LIST_FWD0 + 0);
+      peer_barrier(p);                       // L1 complete everywhere
+      fft_x();
+      peer_jobs<C>(p, LIST_FWD0 + 1);
+      peer_zero_forward(p, 2, W1);
+      peer_barrier(p);                       // L3 complete everywhere; every W1 zeroed and idle
+      fft_y();
+      peer_jobs<C>(p, LIST_FWD0 + 2);
+      peer_barrier(p);                       // L4 complete everywhere
+    } else {
+      run_stage_forward<C>(G.st[0], p->mesh, p->d_g1, W0, W1, PK, st, &p->launches);       // L1 in W1
+      fft_x();
+      run_stage_forward<C>(G.st[1], p->mesh, W1, W1, W0, PK, st, &p->launches);            // L3 in W0
+      fft_y();
+      run_stage_forward<C>(G.st[2], p->mesh, W0, W0, W1, PK, st, &p->launches);            // L4 in W1
+    }
     const long long lno0 = L.local_no[0], lno1 = L.local_no[1];
     if (p->own_fft[2]) {
       // z pass fused with the crop / embed into the padded grid
@@ -731,38 +757,47 @@ template <class R> struct Core {
       if (p->fft_z_bwd) { FftType<R>::exec_r2c(p->fft_z_bwd, (R *)W0, W1); p->lib_launches++; }
     }
     const bool peer = p->peer.on;
-    // L4 in W1 -> L3 in W0
-    if (peer) peer_stage_backward(p, 2, W0, G.L3_elems, L.no[1] < L.n[1]);
-    else if (L.no[1] < L.n[1]) stage_backward_zero(p, G.st[2], W1, W0, W0, G.L3_elems);
-    else run_stage_backward<C>(G.st[2], p->mesh, W1, W0, W0, PK, st, &p->launches);
-    if (p->own_fft[1]) { fft_strided_launch<C>(W0, (int)L.n[1], G.S3, G.S3, 1, (const C *)p->d_tw[1], st); p->launches++; }
-    else if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_INVERSE); p->lib_launches++; }
-    // L3 in W0 -> L1 in W1
-    if (peer) peer_stage_backward(p, 1, W1, G.L1_elems, L.no[0] < L.n[0]);
-    else if (L.no[0] < L.n[0]) stage_backward_zero(p, G.st[1], W0, W1, W1, G.L1_elems);
-    else run_stage_backward<C>(G.st[1], p->mesh, W0, W1, W1, PK, st, &p->launches);
-    if (p->own_fft[0]) { fft_strided_launch<C>(W1, (int)L.n[0], G.S1, G.S1, 1, (const C *)p->d_tw[0], st); p->launches++; }
-    else if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_INVERSE); p->lib_launches++; }
-    // L1 in W1 -> g1
-    if (peer) peer_stage_backward(p, 0, p->d_g1, 0, false);
-    else run_stage_backward<C>(G.st[0], p->mesh, W1, W0, p->d_g1, PK, st, &p->launches);
+    auto ifft_y = [&]() {
+      if (p->own_fft[1]) { fft_strided_launch<C>(W0, (int)L.n[1], G.S3, G.S3, 1, (const C *)p->d_tw[1], st); p->launches++; }
+      else if (p->fft_y) { FftType<R>::exec_c2c(p->fft_y, W0, CUFFT_INVERSE); p->lib_launches++; }
+    };
+    auto ifft_x = [&]() {
+      if (p->own_fft[0]) { fft_strided_launch<C>(W1, (int)L.n[0], G.S1, G.S1, 1, (const C *)p->d_tw[0], st); p->launches++; }
+      else if (p->fft_x) { FftType<R>::exec_c2c(p->fft_x, W1, CUFFT_INVERSE); p->lib_launches++; }
+    };
+    if (peer) {
+      // four barriers, as in fft_forward: W0 (L3) is idle at the start; W1 (L1) is the source of my stage-2 pushes and is
+      // zeroed right behind them; g1 is idle during the whole transform
+      if (L.no[1] < L.n[1]) PNB_CUDA(cudaMemsetAsync(W0, 0, sizeof(C) * (size_t)G.L3_elems, st));
+      peer_barrier(p);
+      peer_jobs<C>(p, LIST_BWD0 - 2);        // L4 in W1 -> L3 in W0
+      if (L.no[0] < L.n[0]) PNB_CUDA(cudaMemsetAsync(W1, 0, sizeof(C) * (size_t)G.L1_elems, st));
+      peer_barrier(p);
+      ifft_y();
+      peer_jobs<C>(p, LIST_BWD0 - 1);        // L3 in W0 -> L1 in W1
+      peer_barrier(p);
+      ifft_x();
+      peer_jobs<C>(p, LIST_BWD0 - 0);        // L1 in W1 -> g1
+      peer_barrier(p);
+    } else {
+      // L4 in W1 -> L3 in W0
+      if (L.no[1] < L.n[1]) stage_backward_zero(p, G.st[2], W1, W0, W0, G.L3_elems);
+      else run_stage_backward<C>(G.st[2], p->mesh, W1, W0, W0, PK, st, &p->launches);
+      ifft_y();
+      // L3 in W0 -> L1 in W1
+      if (L.no[0] < L.n[0]) stage_backward_zero(p, G.st[1], W0, W1, W1, G.L1_elems);
+      else run_stage_backward<C>(G.st[1], p->mesh, W0, W1, W1, PK, st, &p->launches);
+      ifft_x();
+      // L1 in W1 -> g1
+      run_stage_backward<C>(G.st[0], p->mesh, W1, W0, p->d_g1, PK, st, &p->launches);
+    }
   }
 
-  // One re-distribution of the pencil FFT over peer memory: zero what the stage leaves untouched, wait until every rank is
-  // ready to be written to, push my part of every rank's destination array, wait until every rank's pushes have landed.
-  static void peer_stage_forward(P *p, int s, C *dest) {
+  // what a forward stage leaves untouched in its destination array must be zero before any peer pushes into it
+  static void peer_zero_forward(P *p, int s, C *dest) {
     const Stage &S = p->pipe.st[s];
     if (S.zero_all) PNB_CUDA(cudaMemsetAsync(dest, 0, sizeof(C) * (size_t)S.dst_elems, p->stream));
     else if (S.zero_len > 0) PNB_CUDA(cudaMemsetAsync(dest + S.zero_off, 0, sizeof(C) * (size_t)S.zero_len, p->stream));
-    peer_barrier(p);
-    peer_jobs<C>(p, LIST_FWD0 + s);
-    peer_barrier(p);
-  }
-  static void peer_stage_backward(P *p, int s, C *out, long long out_elems, bool zero_out) {
-    if (zero_out) PNB_CUDA(cudaMemsetAsync(out, 0, sizeof(C) * (size_t)out_elems, p->stream));
-    peer_barrier(p);
-    peer_jobs<C>(p, LIST_BWD0 - s);
-    peer_barrier(p);
   }
 
   // backward stage whose source-side array has rows outside the pruned output range: they must be zero
