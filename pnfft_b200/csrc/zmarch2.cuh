@@ -58,6 +58,7 @@ template <int M_> struct Zm2Cfg {
   static constexpr int W = ZS + 2 * M_;          // register window (cells) per row
   static constexpr int NFL = (W + ZS - 1) / ZS;  // flushes until a touched window is all zero again
   static constexpr int XLEAD = XW - 1;           // zero padding in front of the x weights
+  static constexpr int YLEAD = T1 - 1;           // ... and of the y weights
   // z taps: true = the table stores psi_z unshifted and the node loops dispatch on the node's z offset inside its
   // sub-chunk (ZS statically indexed copies of the tap loop, 2m+1 taps each); false = psi_z stored shifted by that
   // offset and zero padded to W (one branch-free loop over all W window cells, (W - 2m - 1) / W of its FMAs on zeros)
@@ -78,13 +79,13 @@ struct Zm2Geom {
 // (Cfg::DZS: the node loops dispatch on the header's dz) or [0 x dz, psi_z[0..C), 0...] of length W, already aligned with
 // the register window of the node's sub-chunk (no dispatch, but W instead of 2m+1 taps per node and row);
 // the same three rows of dpsi when GRAD; vals = f (and grad_f) of the node for the adjoint.
-template <class R, int M_, bool GRAD, bool VALS, bool CPLX> struct Zm2Row {
-  typedef Zm2Cfg<M_> Cfg;
+template <class R, class Cfg_, bool GRAD, bool VALS, bool CPLX> struct ZmRowOf {
+  typedef Cfg_ Cfg;
   static constexpr int AL = 16 / (int)sizeof(R);
   static constexpr int up(int v) { return (v + AL - 1) / AL * AL; }
   static constexpr int C = Cfg::C;
   static constexpr int HDR = 32 / (int)sizeof(R);
-  static constexpr int XP = up(C + 2 * Cfg::XLEAD), YP = up(C + 2 * (Cfg::T1 - 1)), ZP = up(Cfg::W);
+  static constexpr int XP = up(C + 2 * Cfg::XLEAD), YP = up(C + 2 * Cfg::YLEAD), ZP = up(Cfg::W);
   static constexpr int oX = HDR, oY = oX + XP, oZ = oY + YP;
   static constexpr int oDX = oZ + ZP, oDY = oDX + XP, oDZ = oDY + YP;
   static constexpr int oV = GRAD ? oDZ + ZP : oZ + ZP;
@@ -93,6 +94,7 @@ template <class R, int M_, bool GRAD, bool VALS, bool CPLX> struct Zm2Row {
   static constexpr int ROWBYTES = ROWLEN * (int)sizeof(R);
   static_assert(ROWBYTES % 16 == 0, "bulk copies need 16-byte granules");
 };
+template <class R, int M_, bool GRAD, bool VALS, bool CPLX> struct Zm2Row : ZmRowOf<R, Zm2Cfg<M_>, GRAD, VALS, CPLX> {};
 
 constexpr int kZm2HdrBytes = 128;    // chunk header: {tz, count, first sorted index, 0, start[0..T0]}
 #ifndef ZM2_TABNODES
@@ -103,11 +105,11 @@ constexpr int kZm2TabNodes = ZM2_TABNODES;     // nodes per block of the table k
 // ------------------------------------------------------------------------------------------------
 // node table: one thread per (node, axis); rows assembled in shared memory, written out coalesced
 // ------------------------------------------------------------------------------------------------
-template <class R, int M_, bool GRAD, bool VALS, bool CPLX>
+template <class R, int M_, bool GRAD, bool VALS, bool CPLX, class Cfg_ = Zm2Cfg<M_>>
 __global__ void __launch_bounds__(3 * kZm2TabNodes)
 k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab, int first) {
-  typedef Zm2Cfg<M_> Cfg;
-  typedef Zm2Row<R, M_, GRAD, VALS, CPLX> Row;
+  typedef Cfg_ Cfg;
+  typedef ZmRowOf<R, Cfg_, GRAD, VALS, CPLX> Row;
   constexpr int C = Cfg::C, NCOMP = CPLX ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R *rows = reinterpret_cast<R *>(smem_raw);
@@ -205,7 +207,7 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab, int first) {
       for (int s = 0; s < C; s++) { psi[s] *= g.wscale; if (GRAD) dpsi[s] *= g.wscale; }
     }
     const int dzc = min(max(d, 0), Cfg::ZS - 1);
-    const int lead = t == 0 ? Cfg::XLEAD : (t == 1 ? Cfg::T1 - 1 : (Cfg::DZS ? 0 : dzc));
+    const int lead = t == 0 ? Cfg::XLEAD : (t == 1 ? Cfg::YLEAD : (Cfg::DZS ? 0 : dzc));
 #pragma unroll
     for (int s = 0; s < C; s++) { row[off + lead + s] = psi[s]; if (GRAD) row[off + (Row::oDX - Row::oX) + lead + s] = dpsi[s]; }
     while (slow) {
