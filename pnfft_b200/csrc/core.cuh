@@ -935,7 +935,7 @@ template <class R> struct Core {
     if ((flags & N_MALLOC_F) && nd->f) { if (is_device_ptr(nd->f)) cudaFree(nd->f); else cudaFreeHost(nd->f); }
     if ((flags & N_MALLOC_GRAD_F) && nd->grad_f) { if (is_device_ptr(nd->grad_f)) cudaFree(nd->grad_f); else cudaFreeHost(nd->grad_f); }
     if ((flags & N_MALLOC_HESSIAN_F) && nd->hessian_f) cudaFreeHost(nd->hessian_f);
-    cudaFree(nd->d_x); cudaFree(nd->d_f); cudaFree(nd->d_grad_f); cudaFree(nd->d_hess); cudaFree(nd->d_wtab); cudaFree(nd->d_vals);
+    cudaFree(nd->d_x); cudaFree(nd->d_x_alt); cudaFree(nd->d_f); cudaFree(nd->d_grad_f); cudaFree(nd->d_hess); cudaFree(nd->d_wtab); cudaFree(nd->d_vals);
     for (int k = 0; k < 2; k++) {
       BinState<R> &b = k ? nd->il : *static_cast<BinState<R> *>(nd);
       cudaFree(b.d_tile); cudaFree(b.d_tile_sorted); cudaFree(b.d_perm); cudaFree(b.d_idx);
@@ -1352,7 +1352,7 @@ template <class R> struct Core {
     return e ? atoi(e) != 0 : dflt;
   }
   // `after`: stream the coordinates were just written on (an upload), nullptr if they have been resident all along
-  static unsigned long long hash_device_x(P *p, Nd *nd, const R *dx, cudaStream_t after = nullptr) {
+  static void hash_device_x_queue(P *p, Nd *nd, const R *dx, cudaStream_t after = nullptr) {
     const size_t n = 3 * (size_t)nd->local_M;
     if (!nd->h_hash) {
       PNB_CUDA(cudaHostAlloc((void **)&nd->h_hash, sizeof(unsigned long long), cudaHostAllocDefault));
@@ -1365,12 +1365,19 @@ template <class R> struct Core {
     PNB_CUDA(cudaMemsetAsync(nd->d_hash, 0, sizeof(unsigned long long), p->copy_stream));
     if (n) k_hash_words<R><<<148 * 8, 256, 0, p->copy_stream>>>(dx, (long long)n, nd->d_hash);
     PNB_CUDA(cudaMemcpyAsync(nd->h_hash, nd->d_hash, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->copy_stream));
-    PNB_CUDA(cudaStreamSynchronize(p->copy_stream));
     p->launches++;
+  }
+  static unsigned long long hash_device_x_result(P *p, Nd *nd) {
+    PNB_CUDA(cudaStreamSynchronize(p->copy_stream));
     return *nd->h_hash | 1ull;      // never 0 (0 = "no hash")
   }
+  static unsigned long long hash_device_x(P *p, Nd *nd, const R *dx, cudaStream_t after = nullptr) {
+    hash_device_x_queue(p, nd, dx, after);
+    return hash_device_x_result(p, nd);
+  }
   // dx_known: the coordinates are on the device already (second interlacing pass)
-  static const R *prepare_nodes(P *p, Nd *nd, int ev_after_copy, int ev_after_bin, const R *dx_known = nullptr) {
+  // adj_spec: the caller is pnfft_adj and can redo its work (see Nodes::d_x_alt)
+  static const R *prepare_nodes(P *p, Nd *nd, int ev_after_copy, int ev_after_bin, const R *dx_known = nullptr, int adj_spec = -1) {
     const size_t M = (size_t)nd->local_M;
     static const bool env_static = env_flag("PNFFT_B200_X_STATIC", false);
     static const bool use_hash = env_flag("PNFFT_B200_X_HASH", true);
@@ -1380,7 +1387,22 @@ template <class R> struct Core {
     const int fam = kernel_family(p);
     const R *dx;
     unsigned long long h = 0;
-    if (dx_known) dx = dx_known;
+    static const bool spec_env = env_flag("PNFFT_B200_ADJ_SPECULATE", true);
+    const bool host_x = nd->x && !is_device_ptr(nd->x);
+    bool hashed_upload = false;
+    if (dx_known) { dx = dx_known; h = nd->known_hash; nd->known_hash = 0; }
+    else if (adj_spec == 1 && spec_env && host_x && use_hash && hash_up && !pinned && !is_static && M && nd->adj_same_x_last &&
+             nd->binned && nd->bin_plan == (const void *)p && nd->bin_family == fam && nd->d_x && nd->d_x_bound == nd->d_x && nd->bin_hash != 0) {
+      // the coordinates were the trafo's last time: start on the bins at hand, check behind the transform's back
+      ensure(&nd->d_x_alt, &nd->cap_x_alt, 3 * M);
+      PNB_CUDA(cudaEventRecord(p->ev_copy[0], p->stream));             // behind f / grad_f on the bus
+      PNB_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_copy[0], 0));
+      PNB_CUDA(cudaMemcpyAsync(nd->d_x_alt, nd->x, sizeof(R) * 3 * M, cudaMemcpyHostToDevice, p->copy_stream));
+      hash_device_x_queue(p, nd, nd->d_x_alt);
+      nd->spec_pending = true;
+      dx = nd->d_x;
+      h = nd->bin_hash;
+    }
     else if ((pinned || is_static) && nd->binned && nd->d_x_bound && nd->bin_plan == (const void *)p) dx = nd->d_x_bound;
     else if (nd->x && is_device_ptr(nd->x)) {
       dx = nd->x;
@@ -1398,15 +1420,16 @@ template <class R> struct Core {
       nd->x_uploaded = true;
       // the uploaded coordinates may be the ones the bins and the window table were made from (trafo then adj of one
       // step): one streaming pass over them tells, and saves the binning and the table
-      if (use_hash && hash_up && !pinned) h = hash_device_x(p, nd, dx, p->copy_stream);
+      if (use_hash && hash_up && !pinned) { h = hash_device_x(p, nd, dx, p->copy_stream); hashed_upload = true; }
     } else {
       dx = dev_in(p, nd->x, &nd->d_x, &nd->cap_x, 3 * M, true);
       nd->x_uploaded = true;
-      if (use_hash && hash_up && !pinned && M && nd->x && !is_device_ptr(nd->x)) h = hash_device_x(p, nd, dx, p->stream);
+      if (use_hash && hash_up && !pinned && M && host_x) { h = hash_device_x(p, nd, dx, p->stream); hashed_upload = true; }
     }
     if (ev_after_copy >= 0) PNB_CUDA(cudaEventRecord(p->ev[ev_after_copy], p->stream));
     bool valid = nd->binned && nd->bin_plan == (const void *)p && nd->bin_family == fam && nd->d_x_bound == dx;
     if (valid && !pinned && !is_static) valid = h != 0 && nd->bin_hash == h;     // device x: same content as last time?
+    if (adj_spec >= 0 && hashed_upload) nd->adj_same_x_last = valid;
     static const bool dbg = env_flag("PNFFT_B200_DEBUG_BIN", false);
     if (dbg) fprintf(stderr, "prepare_nodes: valid=%d binned=%d plan=%d fam=%d/%d bound=%p dx=%p h=%llx bin_hash=%llx static=%d pinned=%d\n", (int)valid, (int)nd->binned,
                      (int)(nd->bin_plan == (const void *)p), nd->bin_family, fam, (const void *)nd->d_x_bound, (const void *)dx, h, nd->bin_hash, (int)is_static, (int)pinned);
@@ -1568,17 +1591,24 @@ template <class R> struct Core {
       p->warned_hessian = true;
     }
     rec(p, 0);
+    const size_t M = nd ? (size_t)nd->local_M : 0;
+    static const bool no_prefetch = getenv("PNFFT_B200_NO_PREFETCH") && atoi(getenv("PNFFT_B200_NO_PREFETCH")) != 0;
+    // host-resident f_hat AND host-resident coordinates on one GPU: the coordinates go over the bus FIRST, so that binning
+    // and the window table (node stream) run while f_hat is still travelling and D and F wait for it; the other order
+    // leaves the table (6 ms at C3) behind both uploads.  PNFFT_B200_X_FIRST=0 restores f_hat first.
+    static const bool xf_env = env_flag("PNFFT_B200_X_FIRST", true);
+    const bool x_first = xf_env && !no_prefetch && !(cf & (C_OMIT_DECONV | C_OMIT_CONV)) && p->f_hat && !is_device_ptr(p->f_hat) && nd && nd->x &&
+                         !is_device_ptr(nd->x) && M > 0 && p->mesh.size == 1 && !(p->pnfft_flags & (F_DIFF_IK | F_INTERLACED)) &&
+                         kernel_family(p) == 2 && (cf & (C_F | C_GRAD_F)) && !(nd->precompute_flags & P_PRE_PSI);
     // ---- f_hat on the device ----
     const C *fh = nullptr;
     if (!(cf & C_OMIT_DECONV)) {
       if (!p->f_hat) { fprintf(stderr, "pnfft-b200: f_hat is not set\n"); return; }
       if (is_device_ptr(p->f_hat)) fh = p->f_hat;
-      else { PNB_CUDA(cudaMemcpyAsync(p->d_f_hat, p->f_hat, sizeof(C) * nloc, cudaMemcpyHostToDevice, st)); fh = p->d_f_hat; }
+      else { if (!x_first) PNB_CUDA(cudaMemcpyAsync(p->d_f_hat, p->f_hat, sizeof(C) * nloc, cudaMemcpyHostToDevice, st)); fh = p->d_f_hat; }
     }
-    rec(p, 1);
+    if (!x_first) rec(p, 1);
     // the x upload of this call may overtake D and F (prepare_nodes); PNFFT_B200_NO_PREFETCH=1 keeps the single queue
-    const size_t M = nd ? (size_t)nd->local_M : 0;
-    static const bool no_prefetch = getenv("PNFFT_B200_NO_PREFETCH") && atoi(getenv("PNFFT_B200_NO_PREFETCH")) != 0;
     PNB_CUDA(cudaEventRecord(p->ev_copy[0], st));
     p->x_via_copy_stream = !no_prefetch;
 
@@ -1587,13 +1617,16 @@ template <class R> struct Core {
     const bool conv = !(cf & C_OMIT_CONV);
     const bool acc = (cf & C_ACCUMULATED) != 0;
     p->side_nodes = false;
+    p->x_first = x_first;
     for (int pass = 0; pass < npass; pass++) {
       p->il_pass = pass;
       if (pass) nd->swap_il();
       const bool acc_pass = acc || pass > 0;       // the second pass adds to the first (reference assign.c:689-691)
       // ---- D ----
-      if (fh) run_deconv(p, fh, nullptr, false);
-      rec(p, 2);
+      if (!x_first) {
+        if (fh) run_deconv(p, fh, nullptr, false);
+        rec(p, 2);
+      }
       // node-side preparation is shared by all B passes of this call
       auto node_setup = [&]() {
         dx = prepare_nodes(p, nd, 4, 5, dx);
@@ -1620,7 +1653,7 @@ template <class R> struct Core {
         // step 36.57 -> 36.35 ms); on one GPU the two sides only compete for HBM (65.4 vs 65.5 ms) and the stage timers
         // stay cleaner without it.  PNFFT_B200_SIDE_STREAM=0 / 1 forces it off / on.
         static const int side_env = getenv("PNFFT_B200_SIDE_STREAM") ? atoi(getenv("PNFFT_B200_SIDE_STREAM")) : -1;
-        const bool want_side = side_env >= 0 ? side_env != 0 : p->mesh.size > 1;
+        const bool want_side = x_first || (side_env >= 0 ? side_env != 0 : p->mesh.size > 1);
         p->side_nodes = want_side && npass == 1 && conv && M > 0 && kernel_family(p) == 2 && (cf & (C_F | C_GRAD_F));
         NodeArgs<R> na_side;
         if (p->side_nodes) {
@@ -1637,6 +1670,12 @@ template <class R> struct Core {
           p->b_phase = 3;
           rec(p, 10);
           p->stream = st;
+        }
+        if (x_first) {      // the coordinates are on the device by now (prepare_nodes waited for their hash)
+          PNB_CUDA(cudaMemcpyAsync(p->d_f_hat, p->f_hat, sizeof(C) * nloc, cudaMemcpyHostToDevice, st));
+          rec(p, 1);
+          run_deconv(p, fh, nullptr, false);
+          rec(p, 2);
         }
         if (!(cf & C_OMIT_FFT)) fft_forward(p);
         rec(p, 3);
@@ -1736,55 +1775,69 @@ template <class R> struct Core {
       if (!acc) PNB_CUDA(cudaMemsetAsync(fh, 0, sizeof(C) * nloc, st));
       else if (!fh_dev) PNB_CUDA(cudaMemcpyAsync(fh, p->f_hat, sizeof(C) * nloc, cudaMemcpyHostToDevice, st));
     }
-    for (int pass = 0; pass < npass; pass++) {
-      p->il_pass = pass;
-      if (pass) nd->swap_il();
-      if (conv) dx = prepare_nodes(p, nd, 1, 2, dx); else { rec(p, 1); rec(p, 2); }
-      auto base_args = [&]() {
-        NodeArgs<R> na;
-        na.x = dx; na.perm = nd->d_perm; na.M = (int)M; na.f = nullptr; na.f_stride = 1; na.f_off = 0; na.grad = nullptr;
-        na.accumulate = 0;
-        const bool use_pre = (nd->precompute_flags & P_PRE_PSI) && nd->d_pre_psi;
-        na.pre_psi = use_pre ? nd->d_pre_psi : nullptr;
-        na.pre_dpsi = use_pre ? nd->d_pre_dpsi : nullptr;
-        return na;
-      };
-      auto spread = [&](R *fptr, long long stride, long long off, R *gptr, int e_zero, int e_b, int e_h) {
-        PNB_CUDA(cudaMemsetAsync(p->d_grid, 0, p->grid_bytes, st));   // reference ndft-parallel.c:2629-2635
-        if (e_zero >= 0) rec(p, e_zero);
-        NodeArgs<R> na = base_args();
-        na.f = fptr; na.f_stride = stride; na.f_off = off; na.grad = gptr;
-        if (na.grad && na.pre_psi && !na.pre_dpsi) na.pre_psi = nullptr;
-        if (fptr || gptr) launch_B_any(p, nd, na, true);
-        if (e_b >= 0) rec(p, e_b);
-        halo(p, true);
-        if (e_h >= 0) rec(p, e_h);
-      };
+    // host-resident coordinates that were the trafo's last time: run on the bins at hand while they are uploaded and hashed
+    // behind the transform (prepare_nodes); a different hash means new coordinates, and the adjoint is redone on them
+    const bool may_spec = conv && npass == 1 && !acc && p->mesh.size == 1;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      if (attempt && fh) PNB_CUDA(cudaMemsetAsync(fh, 0, sizeof(C) * nloc, st));
+      for (int pass = 0; pass < npass; pass++) {
+        p->il_pass = pass;
+        if (pass) nd->swap_il();
+        if (conv) dx = prepare_nodes(p, nd, 1, 2, dx, may_spec && attempt == 0 ? 1 : 0); else { rec(p, 1); rec(p, 2); }
+        auto base_args = [&]() {
+          NodeArgs<R> na;
+          na.x = dx; na.perm = nd->d_perm; na.M = (int)M; na.f = nullptr; na.f_stride = 1; na.f_off = 0; na.grad = nullptr;
+          na.accumulate = 0;
+          const bool use_pre = (nd->precompute_flags & P_PRE_PSI) && nd->d_pre_psi;
+          na.pre_psi = use_pre ? nd->d_pre_psi : nullptr;
+          na.pre_dpsi = use_pre ? nd->d_pre_dpsi : nullptr;
+          return na;
+        };
+        auto spread = [&](R *fptr, long long stride, long long off, R *gptr, int e_zero, int e_b, int e_h) {
+          PNB_CUDA(cudaMemsetAsync(p->d_grid, 0, p->grid_bytes, st));   // reference ndft-parallel.c:2629-2635
+          if (e_zero >= 0) rec(p, e_zero);
+          NodeArgs<R> na = base_args();
+          na.f = fptr; na.f_stride = stride; na.f_off = off; na.grad = gptr;
+          if (na.grad && na.pre_psi && !na.pre_dpsi) na.pre_psi = nullptr;
+          if (fptr || gptr) launch_B_any(p, nd, na, true);
+          if (e_b >= 0) rec(p, e_b);
+          halo(p, true);
+          if (e_h >= 0) rec(p, e_h);
+        };
 
-      if (!ik) {
-        if (conv) spread(df, 1, 0, dg, 3, 4, 5); else { rec(p, 3); rec(p, 4); rec(p, 5); }
-        if (!(cf & C_OMIT_FFT)) fft_backward(p);
-        rec(p, 6);
-      } else {
-        rec(p, 3); rec(p, 4); rec(p, 5);
-        if (!(cf & C_OMIT_DECONV)) PNB_CUDA(cudaMemsetAsync(p->d_g1_buffer, 0, sizeof(C) * nloc, st));
-        if (cf & C_F) {
-          if (conv) spread(df, 1, 0, nullptr, -1, -1, -1);
+        if (!ik) {
+          if (conv) spread(df, 1, 0, dg, 3, 4, 5); else { rec(p, 3); rec(p, 4); rec(p, 5); }
           if (!(cf & C_OMIT_FFT)) fft_backward(p);
-          run_ik(p, p->d_g1, p->d_g1_buffer, 2, 0);
-        }
-        if (cf & C_GRAD_F)
-          for (int dim = 0; dim < 3; dim++) {
-            if (conv) spread(dg, 3, dim, nullptr, -1, -1, -1);
+          rec(p, 6);
+        } else {
+          rec(p, 3); rec(p, 4); rec(p, 5);
+          if (!(cf & C_OMIT_DECONV)) PNB_CUDA(cudaMemsetAsync(p->d_g1_buffer, 0, sizeof(C) * nloc, st));
+          if (cf & C_F) {
+            if (conv) spread(df, 1, 0, nullptr, -1, -1, -1);
             if (!(cf & C_OMIT_FFT)) fft_backward(p);
-            if (!(cf & C_OMIT_DECONV)) run_ik(p, p->d_g1, p->d_g1_buffer, 1, dim);
+            run_ik(p, p->d_g1, p->d_g1_buffer, 2, 0);
           }
-        PNB_CUDA(cudaMemcpyAsync(p->d_g1, p->d_g1_buffer, sizeof(C) * nloc, cudaMemcpyDeviceToDevice, st));
-        rec(p, 6);
+          if (cf & C_GRAD_F)
+            for (int dim = 0; dim < 3; dim++) {
+              if (conv) spread(dg, 3, dim, nullptr, -1, -1, -1);
+              if (!(cf & C_OMIT_FFT)) fft_backward(p);
+              if (!(cf & C_OMIT_DECONV)) run_ik(p, p->d_g1, p->d_g1_buffer, 1, dim);
+            }
+          PNB_CUDA(cudaMemcpyAsync(p->d_g1, p->d_g1_buffer, sizeof(C) * nloc, cudaMemcpyDeviceToDevice, st));
+          rec(p, 6);
+        }
+        // ---- D^H: f_hat += g1 * 1/phi_hat ----
+        if (fh && !(cf & C_OMIT_DECONV)) run_deconv(p, nullptr, fh, true);
+        if (pass) nd->swap_il();
       }
-      // ---- D^H: f_hat += g1 * 1/phi_hat ----
-      if (fh && !(cf & C_OMIT_DECONV)) run_deconv(p, nullptr, fh, true);
-      if (pass) nd->swap_il();
+      if (!nd || !nd->spec_pending) break;
+      nd->spec_pending = false;
+      const unsigned long long hx = hash_device_x_result(p, nd);
+      if (hx == nd->bin_hash) break;
+      PNB_CUDA(cudaStreamSynchronize(st));
+      { R *t = nd->d_x; nd->d_x = nd->d_x_alt; nd->d_x_alt = t; const size_t c = nd->cap_x; nd->cap_x = nd->cap_x_alt; nd->cap_x_alt = c; }
+      nd->binned = false; nd->adj_same_x_last = false; nd->known_hash = hx;
+      dx = nd->d_x;
     }
     p->il_pass = 0;
     rec(p, 7);
@@ -1803,6 +1856,7 @@ template <class R> struct Core {
       s[5] = ms(p, 0, 1) + ms(p, 3, 4); s[6] = ms(p, 7, 8); s[7] = ms(p, 0, 8);
       if (p->side_nodes) {   // node side on its own stream: x upload ev[11]->ev[4], binning ev[4]->ev[5], node table ev[9]->ev[10]
         s[0] = ms(p, 6, 7) + ms(p, 9, 10); s[1] = ms(p, 4, 5); s[2] = ms(p, 3, 6); s[5] = ms(p, 0, 1) + ms(p, 11, 4);
+        if (p->x_first) s[5] = ms(p, 0, 1);      // coordinates, then f_hat: one after the other on the bus
       }
     } else {
       s[0] = ms(p, 3, 4); s[1] = ms(p, 1, 2); s[2] = ms(p, 2, 3) + ms(p, 4, 5); s[3] = ms(p, 5, 6); s[4] = ms(p, 6, 7);

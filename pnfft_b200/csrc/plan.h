@@ -185,6 +185,7 @@ template <class R> struct Plan {
   cudaStream_t node_stream = nullptr;   // trafo: binning + node table run here while D, F and the halo exchange run on `stream`
   int b_phase = 3;                      // what launch_B does: bit 0 = node table, bit 1 = gridding kernel (z-march v2 only)
   bool side_nodes = false;              // the current trafo ran its node side on node_stream (stage timers: ev[9..12])
+  bool x_first = false;                 // trafo: coordinates uploaded before f_hat (Core::trafo)
   bool x_via_copy_stream = false;       // set by trafo around prepare_nodes: ev_copy[0] marks where the x upload may start
   C *d_f_hat = nullptr;          // staging copy when the user's f_hat is a host pointer
   R *d_invphi[3] = {nullptr, nullptr, nullptr};  // 1/phi_hat tables incl. the (-1)^k fft-shift sign, [local_N[t]]
@@ -277,6 +278,14 @@ template <class R> struct Nodes : BinState<R> {
   bool x_uploaded = false;     // d_x holds the current host x
   unsigned long long x_hash = 0;   // device-resident x: content hash the binning belongs to (0 = none)
   unsigned long long *d_hash = nullptr, *h_hash = nullptr;
+  // pnfft_adj on host-resident coordinates that turned out unchanged last time (trafo then adj of one step): the next adj
+  // runs on the bins it has while the coordinates travel into d_x_alt and are hashed on the copy stream; a different hash
+  // makes d_x_alt the current mirror and the adjoint is redone (Core::adj)
+  R *d_x_alt = nullptr;
+  size_t cap_x_alt = 0;
+  bool adj_same_x_last = false;
+  bool spec_pending = false;
+  unsigned long long known_hash = 0;   // hash of the coordinates handed to prepare_nodes as dx_known (0: none)
 
   // per-call node table of the z-marching kernels (zmarch.cuh: ZmTab), grown on demand
   R *d_wtab = nullptr;

@@ -317,6 +317,38 @@ def test_x_static_and_device_hash():
     nodes.free(0); plan.finalize(0)
 
 
+def test_adj_runs_ahead_of_the_coordinate_check():
+    """pnfft_adj on HOST coordinates that were unchanged last time starts on the bins it has while x is uploaded and hashed
+    behind the transform (Core::adj / prepare_nodes); coordinates changed in place must still be noticed and the adjoint
+    redone on them."""
+    N, M = (32, 32, 32), 30000
+    x, fh, f, g = make_inputs(N, M, 46)
+    x2 = np.clip(x + 0.013, -0.5, np.nextafter(0.5, 0.0))
+    fresh = Run1(N, x2, m=6)
+    h_x2 = fresh.adj(f, g, F | G)
+    f_x2, g_x2 = fresh.trafo(fh, F | G)
+    fresh.close()
+    run = Run1(N, x.copy(), m=6)
+    run.trafo(fh, F | G)
+    h_a = run.adj(f, g, F | G)            # checked first: the coordinates are the trafo's
+    run.trafo(fh, F | G)
+    l0 = run.plan.kernel_launches()
+    h_b = run.adj(f, g, F | G)            # runs ahead of the check
+    ahead = run.plan.kernel_launches() - l0
+    assert rel_l2(h_b, h_a) <= 1e-15
+    run.x[...] = x2                       # same pointer, new content, no pnfft_set_x
+    l0 = run.plan.kernel_launches()
+    h_c = run.adj(f, g, F | G)            # the hash differs: redone on the new coordinates
+    redone = run.plan.kernel_launches() - l0
+    assert rel_l2(h_c, h_x2) <= 1e-14
+    assert redone > ahead
+    f_c, g_c = run.trafo(fh, F | G)
+    assert rel_l2(f_c, f_x2) <= 1e-14 and rel_l2(g_c, g_x2) <= 1e-14
+    h_d = run.adj(f, g, F | G)
+    assert rel_l2(h_d, h_x2) <= 1e-14
+    run.close()
+
+
 @pytest.mark.parametrize("win", [A.WINDOW_GAUSSIAN, A.WINDOW_GAUSSIAN | A.FAST_GAUSSIAN, A.WINDOW_BSPLINE])
 def test_c4_clustered_m8(ref, win):
     """BASELINE config 4 in miniature: strongly clustered (Gaussian blob, sigma = 0.05) nodes, Gaussian / fast Gaussian /
