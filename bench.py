@@ -275,6 +275,32 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
+def bind_rank_to_gpu_numa_node(torch, local_rank):
+    """What `mpirun --bind-to numa` does for a PNFFT caller: run this rank on the cores of the NUMA node its GPU hangs off,
+    so that the pinned host arrays it allocates next (first touch) are local to that GPU's PCIe root.  torchrun binds
+    nothing; with 8 ranks writing f / grad_f back at once, arrays that all sit on one socket cap the D2H side
+    (round 1: 10 GB/s per GPU at N = 8).  PNFFT_B200_BENCH_NUMA=0 switches it off.  Returns what was done."""
+    if os.environ.get("PNFFT_B200_BENCH_NUMA", "1") == "0":
+        return "off"
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return "no NUMA information for %s" % bus
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        mine = cpus & os.sched_getaffinity(0)
+        if not mine:
+            return "node %d of %s has no core in this process's cpuset" % (node, bus)
+        os.sched_setaffinity(0, mine)
+        return "node %d (%d cores) for GPU %s" % (node, len(mine), bus)
+    except Exception as e:      # the bench must run where sysfs says nothing
+        return "unavailable (%s)" % (str(e)[:80],)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -293,6 +319,7 @@ def run_gpu(args):
         raise SystemExit("unsupported number of GPUs %d" % world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_rank_to_gpu_numa_node(torch, local_rank) if world > 1 else "not bound (one rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     steps = args.steps if args.steps is not None else 10
@@ -505,7 +532,7 @@ def run_gpu(args):
         "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32" if single else "f64", "data": "synthetic (seeded nodes in each rank's [lo,up), seeded random f_hat)",
-        "config": config_dict(w, world),
+        "config": config_dict(w, world, {"host_numa_binding": numa}),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
                 "ms_per_step": ms_e2e / steps},
         "value_x_static": {"value": M_total / (ms_dev_static * 1e-3 / steps), "unit": UNIT, "ms_per_step": ms_dev_static / steps,

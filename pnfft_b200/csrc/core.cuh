@@ -7,7 +7,7 @@
 #include <cstring>
 
 #include "fftown.cuh"
-#include "zmarch3.cuh"
+#include "zmarch4.cuh"
 #include "gridops.cuh"
 
 namespace pnb {
@@ -968,6 +968,11 @@ template <class R> struct Core {
     const int m = p->L.m;
     const bool fits = (m == 4 || m == 6 || m == 8);
     const int kv = p->kernel_variant & 9;
+    // family 3 (double, m = 5, 7, 8): gather on the FP64 tensor cores with the window in shared memory (zmarch4.cuh); the
+    // scatter is v1's at m = 8 (same column tile, bins shared through ZmGeom::sub) and the generic kernel at m = 5, 7.
+    // PNFFT_B200_NO_MMA4=1 or any kernel variant bit switches it off.
+    static const bool off4 = getenv("PNFFT_B200_NO_MMA4") && atoi(getenv("PNFFT_B200_NO_MMA4")) != 0;
+    if (sizeof(R) == 8 && (m == 5 || m == 7 || m == 8) && !off4 && !(p->kernel_variant & 13)) return 3;
     if (kv == 1 || !fits) return 1;
     if (kv == 8 || m == 8) return 0;
     return 2;
@@ -984,6 +989,7 @@ template <class R> struct Core {
     const int fam = kernel_family(p);
     tg.sub = 1;
     if (fam == 2) { tg.T[0] = Zm2Cfg<6>::T0; tg.T[1] = 16 - 2 * m; tg.T[2] = Zm2Cfg<6>::ZS; tg.sub = Zm2Cfg<6>::SUB; }   // == Zm2Cfg<m>::T0, T1, ZS
+    else if (fam == 3) { tg.T[0] = Zm4Cfg<8>::T0; tg.T[1] = Zm4Cfg<8>::T1; tg.T[2] = Zm4Cfg<8>::ZS; tg.sub = Zm4Cfg<8>::SUB; }
     else if (fam == 0) { tg.T[0] = (m <= 6) ? 16 : 8; tg.T[1] = 4; tg.T[2] = (m <= 6) ? 8 : 4; }   // == ZmCfg<m>::T0, T1, ZS
     else { tg.T[0] = 8; tg.T[1] = 8; tg.T[2] = 16; }    // generic kernels: the bins only order the nodes for locality
     // a shifted node of an interlaced plan may sit one cell past the block (the extra ghost cell above)
@@ -1036,7 +1042,7 @@ template <class R> struct Core {
     cub::DeviceScan::ExclusiveSum(p->d_sort_tmp, tmp, nd->d_tile_count, nd->d_tile_start, (int)nt1, st);
     p->launches += 1;       // k_bin_nodes
     p->lib_launches += 2;   // cub radix sort + scan
-    if (kernel_family(p) == 2) {
+    if (kernel_family(p) == 2 || kernel_family(p) == 3) {
       // load-balance hint for the NEXT gridding launches: lands in pinned host memory by an async copy that nobody waits
       // for (the host reads whatever the last finished binning left there: the old value or the new one, never a zero)
       if (!nd->h_maxcol) {
@@ -1062,6 +1068,7 @@ template <class R> struct Core {
     ZmGeom zg;
     zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2];
     zg.nseg = (tg.nt[2] + Cfg::ZSEG - 1) / Cfg::ZSEG;
+    zg.sub = tg.sub;
     const unsigned nblk = (unsigned)(tg.nt[0] * tg.nt[1] * zg.nseg);
     // 1. node table: window factors evaluated once per node and axis (+ f / grad_f for the adjoint), sorted order
     const size_t need = (size_t)na.M * Tab::ROWLEN + 64;
@@ -1305,8 +1312,78 @@ template <class R> struct Core {
     }
   }
 
+  // z-march v4 (zmarch4.cuh, double only): the gather of family 3.  Rows without node values in nd->d_rows, cached like v3's.
+  template <bool CPLX, int M_, bool GRAD>
+  static void launch_zm4_gather(P *p, Nd *nd, const NodeArgs<R> &na) {
+    if constexpr (sizeof(R) == 8 && Zm4Ok<M_>::value) {
+      typedef Zm4Cfg<M_> Cfg;
+      typedef Zm4Smem<CPLX, M_> Sm;
+      const TileGeom tg = tile_geom(p, nullptr);
+      const GridGeom<R> g = geom(p);
+      const Zm2Geom zg = zm2_work_items(tg, nd, na.M);
+      const int ncol = tg.nt[0] * tg.nt[1];
+      const size_t len_g = ZmRowOf<R, Cfg, true, false, CPLX>::ROWLEN, len_f = ZmRowOf<R, Cfg, false, false, CPLX>::ROWLEN;
+      const char *rc = getenv("PNFFT_B200_ROW_CACHE");
+      const bool cache_on = !(rc && atoi(rc) == 0);
+      const bool reuse = cache_on && nd->binned && nd->rows_plan == (const void *)p && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
+      int flavor = reuse ? nd->rows_flavor : (GRAD ? 1 : 0);
+      if (!reuse && (p->b_phase & 1)) {
+        ensure(&nd->d_rows, &nd->cap_rows, (size_t)na.M * (flavor ? len_g : len_f) + 64);
+        const size_t psm = g.poly ? sizeof(R) * (size_t)2 * (g.poly_deg + 1) * 3 * Cfg::C : 0;
+        const unsigned ntb = (unsigned)((na.M + kZm2TabNodes - 1) / kZm2TabNodes);
+        auto table = [&](auto kt, size_t rowbytes) {
+          const size_t tsm = (size_t)kZm2TabNodes * rowbytes + psm;
+          PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+          kt<<<ntb, 3 * kZm2TabNodes, tsm, p->stream>>>(g, na, nd->d_rows, 0);
+          p->launches++;
+        };
+        if (flavor) table(k_node_table2<R, M_, true, false, CPLX, Cfg>, ZmRowOf<R, Cfg, true, false, CPLX>::ROWBYTES);
+        else table(k_node_table2<R, M_, false, false, CPLX, Cfg>, ZmRowOf<R, Cfg, false, false, CPLX>::ROWBYTES);
+        nd->rows_flavor = flavor; nd->rows_plan = p;
+      } else if (!reuse) {
+        flavor = nd->rows_flavor;      // the table phase of this call ran earlier (side stream)
+      }
+      if (p->b_phase & 2) {
+        const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::R0, Sm::R1, Cfg::ZS, 0);
+        const unsigned nblk = (unsigned)(ncol * zg.nseg);
+        GatherOut<R> out;
+        out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
+        auto go = [&](auto kern) {
+          PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
+          kern<<<nblk, (Cfg::NW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, nd->d_rows, nd->d_tile_start, out);
+          p->launches++;
+        };
+        if (flavor) go(k_gather_mma4<CPLX, M_, GRAD, true>);
+        else if constexpr (!GRAD) go(k_gather_mma4<CPLX, M_, false, false>);
+      }
+      PNB_CUDA(cudaGetLastError());
+    }
+  }
+  static void launch_generic(P *p, const NodeArgs<R> &na, bool scatter, bool cplx) {
+    const GridGeom<R> g = geom(p);
+    const int wpb = 8;
+    const size_t smem = (size_t)wpb * 6 * g.cutoff * sizeof(R);
+    const int nblk = (na.M + wpb - 1) / wpb;
+    if (cplx) {
+      if (!scatter) k_gather_generic<R, true><<<nblk, wpb * 32, smem, p->stream>>>(g, (const R *)p->d_grid, na);
+      else k_scatter_generic<R, true><<<nblk, wpb * 32, smem, p->stream>>>(g, (R *)p->d_grid, na);
+    } else {
+      if (!scatter) k_gather_generic<R, false><<<nblk, wpb * 32, smem, p->stream>>>(g, (const R *)p->d_grid, na);
+      else k_scatter_generic<R, false><<<nblk, wpb * 32, smem, p->stream>>>(g, (R *)p->d_grid, na);
+    }
+    PNB_CUDA(cudaGetLastError());
+    p->launches++;
+  }
+  template <bool CPLX, int M_, bool GRAD>
+  static void launch_fam3(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
+    if (!scatter) launch_zm4_gather<CPLX, M_, GRAD>(p, nd, na);
+    else if constexpr (M_ == 8) { if (p->b_phase & 2) launch_zm<CPLX, M_, GRAD>(p, nd, na, true); }
+    else { if (p->b_phase & 2) launch_generic(p, na, true, CPLX); }
+  }
+
   template <bool CPLX, int M_, bool GRAD>
   static void launch_zmarch(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
+    if (kernel_family(p) == 3) { launch_fam3<CPLX, M_, GRAD>(p, nd, na, scatter); return; }
     if (kernel_family(p) == 2) {
       if (use_mma<M_>(p)) launch_zm3<CPLX, M_, GRAD>(p, nd, na, scatter);
       else launch_zm2<CPLX, M_, GRAD>(p, nd, na, scatter);
@@ -1323,17 +1400,12 @@ template <class R> struct Core {
         case 4: if (grad) launch_zmarch<CPLX, 4, true>(p, nd, na, scatter); else launch_zmarch<CPLX, 4, false>(p, nd, na, scatter); return;
         case 6: if (grad) launch_zmarch<CPLX, 6, true>(p, nd, na, scatter); else launch_zmarch<CPLX, 6, false>(p, nd, na, scatter); return;
         case 8: if (grad) launch_zmarch<CPLX, 8, true>(p, nd, na, scatter); else launch_zmarch<CPLX, 8, false>(p, nd, na, scatter); return;
+        case 5: if (kernel_family(p) == 3) { if (grad) launch_fam3<CPLX, 5, true>(p, nd, na, scatter); else launch_fam3<CPLX, 5, false>(p, nd, na, scatter); return; } break;
+        case 7: if (kernel_family(p) == 3) { if (grad) launch_fam3<CPLX, 7, true>(p, nd, na, scatter); else launch_fam3<CPLX, 7, false>(p, nd, na, scatter); return; } break;
         default: break;
       }
     }
-    const GridGeom<R> g = geom(p);
-    const int wpb = 8;
-    const size_t smem = (size_t)wpb * 6 * g.cutoff * sizeof(R);
-    const int nblk = (na.M + wpb - 1) / wpb;
-    if (!scatter) k_gather_generic<R, CPLX><<<nblk, wpb * 32, smem, p->stream>>>(g, (const R *)p->d_grid, na);
-    else k_scatter_generic<R, CPLX><<<nblk, wpb * 32, smem, p->stream>>>(g, (R *)p->d_grid, na);
-    PNB_CUDA(cudaGetLastError());
-    p->launches++;
+    launch_generic(p, na, scatter, CPLX);
   }
   static void launch_B_any(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
     if (p->L.c2r) launch_B<false>(p, nd, na, scatter); else launch_B<true>(p, nd, na, scatter);

@@ -41,6 +41,7 @@ struct ZmGeom {
   int nc[2];       // column tiles per axis
   int nt2;         // z sub-chunks
   int nseg;        // work items per column
+  int sub;         // bins per (column, sub-chunk) in tile_start (1, or the x-offset bins of the tensor-core gather's sort key)
 };
 
 template <class R> struct WPair;
@@ -254,8 +255,8 @@ k_scatter_zm(const __grid_constant__ CUtensorMap tmap, ZmGeom zg, const R *__res
 
   const int col = blockIdx.x / zg.nseg, seg = blockIdx.x - col * zg.nseg;
   const int tz0 = seg * Cfg::ZSEG, tz1 = min(zg.nt2, tz0 + Cfg::ZSEG);
-  const int *ts = tile_start + (size_t)col * zg.nt2;
-  if (ts[tz0] == ts[tz1]) return;                                   // no nodes in this segment
+  const int *ts = tile_start + (size_t)col * zg.nt2 * zg.sub;
+  if (ts[(size_t)tz0 * zg.sub] == ts[(size_t)tz1 * zg.sub]) return;                                   // no nodes in this segment
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -269,7 +270,7 @@ k_scatter_zm(const __grid_constant__ CUtensorMap tmap, ZmGeom zg, const R *__res
     if (lane == 0) {
       int kb = 0;
       for (int tz = tz0; tz < tz1; tz++) {
-        const int s = ts[tz], e = ts[tz + 1];
+        const int s = ts[(size_t)tz * zg.sub], e = ts[(size_t)(tz + 1) * zg.sub];
         for (int b0 = s; b0 < e; b0 += GB, kb++) {
           const int st = kb % S;
           mbar_wait(&empty[st], ((unsigned)(kb / S) & 1u) ^ 1u);
@@ -310,7 +311,7 @@ k_scatter_zm(const __grid_constant__ CUtensorMap tmap, ZmGeom zg, const R *__res
 
   int kb = 0;
   for (int tz = tz0; tz < tz1; tz++) {
-    const int s = ts[tz], e = ts[tz + 1];
+    const int s = ts[(size_t)tz * zg.sub], e = ts[(size_t)(tz + 1) * zg.sub];
     const int zb = tz * ZS;
     for (int b0 = s; b0 < e; b0 += GB, kb++) {
       const int nb = min(GB, e - b0), st = kb % S;
@@ -466,8 +467,8 @@ k_gather_zm(const __grid_constant__ CUtensorMap tmap, ZmGeom zg, const R *__rest
 
   const int col = blockIdx.x / zg.nseg, seg = blockIdx.x - col * zg.nseg;
   const int tz0 = seg * Cfg::ZSEG, tz1 = min(zg.nt2, tz0 + Cfg::ZSEG);
-  const int *ts = tile_start + (size_t)col * zg.nt2;
-  if (ts[tz0] == ts[tz1]) return;
+  const int *ts = tile_start + (size_t)col * zg.nt2 * zg.sub;
+  if (ts[(size_t)tz0 * zg.sub] == ts[(size_t)tz1 * zg.sub]) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -482,7 +483,7 @@ k_gather_zm(const __grid_constant__ CUtensorMap tmap, ZmGeom zg, const R *__rest
     if (lane == 0) {
       int kb = 0;
       for (int tz = tz0; tz < tz1; tz++) {
-        const int s = ts[tz], e = ts[tz + 1];
+        const int s = ts[(size_t)tz * zg.sub], e = ts[(size_t)(tz + 1) * zg.sub];
         for (int b0 = s; b0 < e; b0 += GB, kb++) {
           const int st = kb % S;
           mbar_wait(&empty[st], ((unsigned)(kb / S) & 1u) ^ 1u);
@@ -584,7 +585,7 @@ k_gather_zm(const __grid_constant__ CUtensorMap tmap, ZmGeom zg, const R *__rest
 
   int kb = 0, prev_st = -1, prev_b0 = 0, prev_nb = 0;
   for (int tz = tz0; tz < tz1; tz++) {
-    const int s = ts[tz], e = ts[tz + 1];
+    const int s = ts[(size_t)tz * zg.sub], e = ts[(size_t)(tz + 1) * zg.sub];
     const int zb = tz * ZS;
     const bool more = tz + 1 < tz1;
     // prefetch the cells the next advance needs: [zb + W, zb + W + ZS)

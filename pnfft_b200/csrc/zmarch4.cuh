@@ -1,0 +1,289 @@
+// Tensor-core gather for the cutoffs whose window does not fit the register file (v4: m = 5, 7, 8 in double; the
+// clustered BASELINE config 4 runs Gaussian / B-spline windows with m = 8).
+// Reference loops replaced: kernel/assign.c:667-1130 (assign_f / assign_f_and_grad_f), kernel/ndft-parallel.c:2703-2888.
+//
+// v3 (zmarch3.cuh) keeps every grid row of a column tile in the registers of the warp that owns it; at m = 8 a tile's
+// footprint is (T + 16)^2 rows x 20 z cells and no longer fits beside the MMA fragments.  v4 keeps the window in SHARED
+// memory instead: a ring of KS + 1 z sub-chunks of the footprint [R0][R1][4] cells, each brought in by ONE TMA box, and a
+// warp reads its B fragments from there (one conflict-free LDS.64 per DMMA pair; +4 % issue time in the cost model of
+// profiles/r2_dmma_overlap_ubench.log).  With the window shared, rows have no owner:
+//   * whole node batches (8 nodes, consecutive in the chunk's dx order) go to whichever warp asks next (one ticket counter
+//     per CTA); the warp contracts z for exactly the x rows its batch touches and ALL y rows on the tensor cores
+//     (T[node, column] = sum_k psi_z[node, k] * window[k, column], M = 8 nodes, N = 8 columns, K = 4 cells per DMMA), runs
+//     the x-y contraction on its C fragments and writes the finished nodes out: no cross-warp reduction, no partial
+//     stages, and clustered node sets balance themselves inside a CTA;
+//   * warps may be at different z sub-chunks at the same time: a window chunk is re-used once every consumer warp has
+//     walked past it (one mbarrier per slot, NW arrivals), and every warp derives the load sequence (and with it the wait
+//     parity of every slot) from the bin table itself, exactly as the service warp that issues the loads does;
+//   * node-table rows (ZmRowOf over Zm4Cfg, built by k_node_table2) are read straight from global memory: a batch keeps a
+//     warp busy for >= 10^4 cycles, the 20 row loads in front of it and the two x weights fetched one row ahead cost nothing.
+// The sort key is v2 / v3's (column tile, z sub-chunk, dx) on the column tile of the v1 kernels of the same cutoff (8 x 4
+// cells at m = 8), so the v1 scatter of the adjoint runs on the same bins (ZmGeom::sub).
+#pragma once
+#include "zmarch3.cuh"
+
+namespace pnb {
+
+template <int M_> struct Zm4Ok { static constexpr bool value = (M_ == 5 || M_ == 7 || M_ == 8); };
+
+template <int M_> struct Zm4Cfg {
+  static constexpr int C = 2 * M_ + 1;
+  static constexpr int T0 = 8, T1 = 4, ZS = 4;   // column tile and z sub-chunk (cells)
+  static constexpr int SUB = 8;                  // x-offset bins per tile in the sort key
+  static constexpr int KS = (ZS + 2 * M_ + 3) / 4;   // window chunks = k-steps per row
+  static constexpr int W = 4 * KS;               // z weights per node, zero padded (pre-shifted by the node's dz)
+  static constexpr int R0 = T0 + 2 * M_;         // footprint rows along x
+  static constexpr int R1C = (T1 + 2 * M_ + 3) / 4 * 4, R1R = (T1 + 2 * M_ + 7) / 8 * 8;   // y rows in whole n-blocks (c2c / c2r)
+  static constexpr int XLEAD = T0 - 1;
+  static constexpr int YLEAD = (R1R - C > T1 - 1) ? R1R - C : T1 - 1;   // a lane reads the y weight of every row of its n-blocks
+  static constexpr bool DZS = false;
+  static constexpr int NSLOT = KS + 1;           // window ring: the chunks of one window plus the one being loaded
+  static constexpr int NW = 15;                  // consumer warps (+ 1 service warp = 512 threads, 128 registers)
+};
+
+template <bool CPLX, int M_> struct Zm4Smem {
+  typedef Zm4Cfg<M_> Cfg;
+  static constexpr int NCOMP = CPLX ? 2 : 1, CELLB = 8 * NCOMP;
+  static constexpr int R1 = CPLX ? Cfg::R1C : Cfg::R1R;
+  static constexpr int NYB = R1 * NCOMP / 8;     // n-blocks per x row
+  static constexpr int SLOTB = Cfg::R0 * R1 * Cfg::ZS * CELLB;
+  static constexpr int off_bar = Cfg::NSLOT * SLOTB;
+  static constexpr int gather = off_bar + (2 * Cfg::NSLOT + 2) * 8;
+  static_assert(SLOTB % 128 == 0, "alignment");
+  static_assert(gather <= 232448, "shared-memory budget of one CTA exceeded");
+};
+
+__device__ __forceinline__ double ldg_f64(const unsigned char *p) { return __ldg(reinterpret_cast<const double *>(p)); }
+
+// ------------------------------------------------------------------------------------------------
+// gather (trafo B)
+// ------------------------------------------------------------------------------------------------
+template <bool CPLX, int M_, bool GRAD, bool RG>
+__global__ void __launch_bounds__((Zm4Cfg<M_>::NW + 1) * 32, 1)
+k_gather_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double *__restrict__ tab, const int *__restrict__ bin_start,
+              GatherOut<double> out) {
+  static_assert(RG || !GRAD, "a gradient kernel needs rows with derivative sections");
+  typedef Zm4Cfg<M_> Cfg;
+  typedef Zm4Smem<CPLX, M_> Sm;
+  typedef ZmRowOf<double, Cfg, RG, false, CPLX> Row;
+  constexpr int C = Cfg::C, ZS = Cfg::ZS, KS = Cfg::KS, NW = Cfg::NW, NSLOT = Cfg::NSLOT, SUB = Cfg::SUB;
+  constexpr int NCOMP = Sm::NCOMP, CELLB = Sm::CELLB, R1 = Sm::R1, NYB = Sm::NYB, SLOTB = Sm::SLOTB;
+  constexpr int NVAL = NCOMP * (GRAD ? 4 : 1), ROWBYTES = Row::ROWBYTES;
+  constexpr int NWY = CPLX ? NYB : 2 * NYB;        // y weights a lane needs: one per C-fragment row it holds
+  constexpr int dOff = RG ? (Row::oDX - Row::oX) * 8 : 0;
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *win = smem_raw;
+  unsigned long long *wfull = reinterpret_cast<unsigned long long *>(smem_raw + Sm::off_bar);
+  unsigned long long *wempty = wfull + NSLOT;
+  int *ticket = reinterpret_cast<int *>(wempty + NSLOT);
+
+  const int colr = blockIdx.x / zg.nseg, seg = blockIdx.x - colr * zg.nseg, col = zg.col0 + colr;
+  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
+  const int *bs = bin_start + (size_t)col * zg.nt2 * SUB;
+  if (bs[(size_t)tz0 * SUB] == bs[(size_t)tz1 * SUB]) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cx = col / zg.nc[1], cy = col - cx * zg.nc[1];
+  const int o0 = cx * Cfg::T0, o1 = cy * Cfg::T1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; i++) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], NW); }
+    *ticket = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ---- service warp: the window chunks of every populated sub-chunk, in order ----
+    if (lane == 0) {
+      int hi = INT_MIN;             // chunks below hi have been requested
+      unsigned loads[NSLOT];        // loads issued into each slot so far
+#pragma unroll
+      for (int i = 0; i < NSLOT; i++) loads[i] = 0;
+      int prev = bs[(size_t)tz0 * SUB];
+      for (int tz = tz0; tz < tz1; tz++) {
+        const int nxt = bs[(size_t)(tz + 1) * SUB];
+        if (nxt == prev) continue;
+        prev = nxt;
+        for (int c = max(tz, hi); c < tz + KS; c++) {
+          const int sl = c % NSLOT;
+#pragma unroll
+          for (int i = 0; i < NSLOT; i++)
+            if (i == sl) {
+              if (loads[i] > 0) mbar_wait_park(&wempty[i], (loads[i] - 1) & 1u);
+              loads[i]++;
+            }
+          mbar_expect_tx(&wfull[sl], (unsigned)SLOTB);
+          tma_load_3d(win + (size_t)sl * SLOTB, &tmap, c * ZS * NCOMP, o1, o0, &wfull[sl]);
+        }
+        hi = tz + KS;
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warps ----
+  const int g = lane >> 2, t = lane & 3;
+  // my element of an n-block inside a window slot: [x row][y row][z][comp]; 256 contiguous bytes per n-block and warp
+  const int frag_off = CPLX ? ((g >> 1) * (ZS * CELLB) + t * CELLB + (g & 1) * 8) : (g * (ZS * CELLB) + t * CELLB);
+  const int aYl = (Row::oY + Cfg::YLEAD + (CPLX ? t : 2 * t)) * 8;
+  const int aXl = (Row::oX + Cfg::XLEAD) * 8;
+  const unsigned char *tabb = reinterpret_cast<const unsigned char *>(tab);
+
+  // walk state, identical in every warp: position, first sorted node and batch count of the sub-chunk at the position,
+  // batches in front of it, last populated sub-chunk at or before the position, and the load sequence replayed so far
+  int pos = tz0, s_pos = bs[(size_t)tz0 * SUB], e_pos = bs[(size_t)(tz0 + 1) * SUB];
+  int base = 0, last_ne = INT_MIN / 2, hi = INT_MIN;
+  unsigned parbits = 0;            // bit sl: parity of the number of loads into slot sl
+  for (;;) {
+    int T = 0;
+    if (lane == 0) T = atomicAdd(ticket, 1);
+    T = __shfl_sync(0xffffffffu, T, 0);
+    // advance to the sub-chunk that holds batch T
+    bool done = false;
+    for (;;) {
+      const int nb = (e_pos - s_pos + 7) >> 3;
+      if (nb > 0 && last_ne != pos) {            // first visit of a populated sub-chunk: replay its loads
+        for (int c = max(pos, hi); c < pos + KS; c++) parbits ^= 1u << (c % NSLOT);
+        hi = pos + KS;
+        last_ne = pos;
+      }
+      if (T < base + nb) break;
+      // leave pos: its chunk is part of no later window.  The release must land in the mbarrier phase of THIS occupant of
+      // the slot: a warp that skips sub-chunks whose batches others took could otherwise arrive before the chunk was
+      // even loaded (its load waits for the slowest warp to release the previous occupant) and complete the wrong phase
+      if (pos - last_ne < KS) {
+        const int sl = pos % NSLOT;
+        mbar_wait_park(&wfull[sl], ((parbits >> sl) & 1u) ^ 1u);
+        if (lane == 0) mbar_arrive(&wempty[sl]);
+      }
+      base += nb;
+      pos++;
+      if (pos >= tz1) { done = true; break; }
+      s_pos = e_pos;
+      e_pos = bs[(size_t)(pos + 1) * SUB];
+    }
+    if (done) break;
+    const int tz = pos;
+    const unsigned char *slot[KS];
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+      const int sl = (tz + q) % NSLOT;
+      mbar_wait_park(&wfull[sl], ((parbits >> sl) & 1u) ^ 1u);
+      slot[q] = win + (size_t)sl * SLOTB + frag_off;
+    }
+    const int b0 = s_pos + (T - base) * 8;
+    const int i = min(b0 + g, e_pos - 1);
+    const bool live = b0 + g < e_pos;
+    const unsigned char *row = tabb + (size_t)i * ROWBYTES;
+    const int4 hd = __ldg(reinterpret_cast<const int4 *>(row));       // {-dx*8, -dy*8, dz, dx}
+    const int j = __ldg(reinterpret_cast<const int *>(row) + 4);
+    double az[KS], adz[GRAD ? KS : 1];
+#pragma unroll
+    for (int q = 0; q < KS; q++) {
+      az[q] = ldg_f64(row + (Row::oZ + 4 * q + t) * 8);
+      if (GRAD) adz[q] = ldg_f64(row + (Row::oZ + 4 * q + t) * 8 + dOff);
+    }
+    double wy[NWY], dwy[GRAD ? NWY : 1];
+#pragma unroll
+    for (int q = 0; q < NWY; q++) {
+      const int yo = CPLX ? 4 * q : (8 * (q >> 1) + (q & 1));
+      wy[q] = ldg_f64(row + aYl + yo * 8 + hd.y);
+      if (GRAD) dwy[q] = ldg_f64(row + aYl + yo * 8 + dOff + hd.y);
+    }
+    // x rows the batch touches: the nodes are in dx order
+    const int xlo = __shfl_sync(0xffffffffu, hd.w, 0), xhi = __shfl_sync(0xffffffffu, hd.w, 28) + C;
+    const unsigned char *xw = row + aXl + hd.x;
+    double v[NVAL];
+#pragma unroll
+    for (int q = 0; q < NVAL; q++) v[q] = 0;
+    double wx_n = ldg_f64(xw + xlo * 8), dwx_n = GRAD ? ldg_f64(xw + xlo * 8 + dOff) : 0.0;
+    for (int X = xlo; X < xhi; X++) {
+      const double wx = wx_n, dwx = dwx_n;
+      if (X + 1 < xhi) {
+        wx_n = ldg_f64(xw + (X + 1) * 8);
+        if (GRAD) dwx_n = ldg_f64(xw + (X + 1) * 8 + dOff);
+      }
+      const int xoff = X * (R1 * ZS * CELLB);
+      double a[NCOMP], bb[NCOMP], c[NCOMP];
+#pragma unroll
+      for (int q = 0; q < NCOMP; q++) { a[q] = 0; bb[q] = 0; c[q] = 0; }
+#pragma unroll
+      for (int nb = 0; nb < NYB; nb++) {
+        double cp[2] = {0, 0}, cd[2] = {0, 0};
+#pragma unroll
+        for (int q = 0; q < KS; q++) {
+          const double B = *reinterpret_cast<const double *>(slot[q] + xoff + nb * 256);
+          dmma884(cp, az[q], B);
+          if (GRAD) dmma884(cd, adz[q], B);
+        }
+        if constexpr (CPLX) {
+          a[0] = fma(wy[nb], cp[0], a[0]); a[1] = fma(wy[nb], cp[1], a[1]);
+          if (GRAD) {
+            bb[0] = fma(dwy[nb], cp[0], bb[0]); bb[1] = fma(dwy[nb], cp[1], bb[1]);
+            c[0] = fma(wy[nb], cd[0], c[0]); c[1] = fma(wy[nb], cd[1], c[1]);
+          }
+        } else {
+          a[0] = fma(wy[2 * nb], cp[0], a[0]); a[0] = fma(wy[2 * nb + 1], cp[1], a[0]);
+          if (GRAD) {
+            bb[0] = fma(dwy[2 * nb], cp[0], bb[0]); bb[0] = fma(dwy[2 * nb + 1], cp[1], bb[0]);
+            c[0] = fma(wy[2 * nb], cd[0], c[0]); c[0] = fma(wy[2 * nb + 1], cd[1], c[0]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NCOMP; q++) {
+        v[q] = fma(wx, a[q], v[q]);
+        if (GRAD) {
+          v[NCOMP + q] = fma(dwx, a[q], v[NCOMP + q]);
+          v[2 * NCOMP + q] = fma(wx, bb[q], v[2 * NCOMP + q]);
+          v[3 * NCOMP + q] = fma(wx, c[q], v[3 * NCOMP + q]);
+        }
+      }
+    }
+    // sum over the lane quad (the quad's lanes hold different y rows); every value of node g ends in exactly one lane
+    if constexpr (NVAL >= 4) {
+      constexpr int H = NVAL / 2, Q = NVAL / 4;
+      const bool hi2 = (t & 2) != 0, hi1 = (t & 1) != 0;
+      double k2[H];
+#pragma unroll
+      for (int q = 0; q < H; q++) {
+        const double send = hi2 ? v[q] : v[q + H], keep = hi2 ? v[q + H] : v[q];
+        k2[q] = keep + shfl_xor(send, 2);
+      }
+      double k1[Q];
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        const double send = hi1 ? k2[q] : k2[q + Q], keep = hi1 ? k2[q + Q] : k2[q];
+        k1[q] = keep + shfl_xor(send, 1);
+      }
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          const int vi = t * Q + q;          // value index: [f, grad x, grad y, grad z] x NCOMP
+          double *o = nullptr;
+          if (vi < NCOMP) { if (out.f) o = out.f + ((size_t)j * out.f_stride + out.f_off) * NCOMP + vi; }
+          else if (out.grad) o = out.grad + (size_t)j * 3 * NCOMP + (vi - NCOMP);
+          if (o) *o = out.accumulate ? *o + k1[q] : k1[q];
+        }
+      }
+    } else if constexpr (NVAL == 2) {
+      const bool hi2 = (t & 2) != 0;
+      double k = (hi2 ? v[1] : v[0]) + shfl_xor(hi2 ? v[0] : v[1], 2);
+      k += shfl_xor(k, 1);
+      if (live && (t & 1) == 0 && out.f) {
+        double *o = out.f + ((size_t)j * out.f_stride + out.f_off) * NCOMP + (t >> 1);
+        *o = out.accumulate ? *o + k : k;
+      }
+    } else {
+      double k = v[0] + shfl_xor(v[0], 2);
+      k += shfl_xor(k, 1);
+      if (live && t == 0 && out.f) {
+        double *o = out.f + ((size_t)j * out.f_stride + out.f_off) * NCOMP;
+        *o = out.accumulate ? *o + k : k;
+      }
+    }
+  }
+}
+
+}  // namespace pnb

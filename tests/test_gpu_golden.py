@@ -143,6 +143,37 @@ def test_hessian_only_and_accumulated():
     run.close()
 
 
+@pytest.mark.parametrize("c2r", [False, True])
+@pytest.mark.parametrize("m", [5, 7, 8])
+def test_family3_shared_window_gather(ref, m, c2r):
+    """Kernel family 3 (double, m = 5, 7, 8): the tensor-core gather with the window in shared memory (zmarch4.cuh) and the
+    scatter that shares its bins (v1 at m = 8, generic at m = 5, 7), on a node set with a dense cluster, sparse
+    surroundings and empty sub-chunks, against the generic kernels (independent code path) and a node subset against the
+    compiled reference; F alone, F with the gradient, and accumulation into the outputs."""
+    N, M = (32, 32, 32), 30000
+    x, fh, f, g = make_inputs(N, M, 52, c2r=c2r)
+    rng = np.random.default_rng(5)
+    x[: M // 2] = np.clip(rng.normal(0.1, 0.04, (M // 2, 3)), -0.5, np.nextafter(0.5, 0.0))     # the cluster
+    x[M // 2: M // 2 + 64, 2] = -0.5                                                          # nodes on the lowest grid plane
+    res = []
+    for variant in (0, 1):
+        run = Run1(N, x, m=m, c2r=c2r, variant=variant)
+        f1, _ = run.trafo(fh, F)
+        f2, g2 = run.trafo(fh, F | G)
+        run.f[...] = 1.0; run.g[...] = 2.0
+        run.plan.trafo(run.nodes, F | G | A.COMPUTE_ACCUMULATED)
+        f3, g3 = run.f.copy(), run.g.copy()
+        fho = run.adj(f, g, F | G)
+        run.close()
+        res.append((f1, f2, g2, f3 - 1.0, g3 - 2.0, fho))
+    for a, b in zip(res[0], res[1]):
+        assert rel_l2(a, b) <= 1e-13
+    assert rel_l2(res[0][0], res[0][1]) <= 1e-15       # F and F|GRAD instantiations
+    sub = slice(0, 2048)
+    rt = ref.trafo(N, x[sub], fh, m=m, compute_flags=F | G, c2r=c2r)
+    assert rel_l2(res[0][1][sub], rt["f"]) <= 1e-13 and rel_l2(res[0][2][sub], rt["grad_f"]) <= 1e-13
+
+
 @pytest.mark.parametrize("m", [4, 6])
 @pytest.mark.parametrize("single", [False, True])
 @pytest.mark.parametrize("c2r", [False, True])
