@@ -151,10 +151,23 @@ template <class R> PNB_HD void bspline_taps(int m, R frac, R n, R *psi, R *dpsi)
 // One tap of a point-wise window: y = l - n x (grid units), z = -y.  want_d: also the AD gradient weight.
 // exp(x) for 0 <= x < 700 without the range / special-case handling of the library routine: x = k ln2 + r with
 // |r| <= ln2 / 2 (two-term Cody-Waite), degree-13 Taylor polynomial (truncation < 2^-57), 2^k through the exponent field.
+#if defined(__CUDACC__)
+// Taylor coefficients 1/13! ... 1/0! in constant memory: a DFMA takes them as a c[bank][offset] operand; as literals each
+// costs two UMOVs per use (18 % of the node-table kernel's instructions, profiles/r2_ncu_full.md)
+static __constant__ double kExpTaylor[14] = {
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+#endif
 PNB_HD double exp_pos(double x) {
   const double k = rint(x * 1.4426950408889634074);
   double r = fma(-k, 6.93147180369123816490e-01, x);
   r = fma(-k, 1.90821492927058770002e-10, r);
+#if defined(__CUDA_ARCH__)
+  double p = kExpTaylor[0];
+#pragma unroll
+  for (int i = 1; i < 14; i++) p = fma(p, r, kExpTaylor[i]);
+  return __longlong_as_double(__double_as_longlong(p) + ((long long)(int)k << 52));
+#else
   double p = 1.0 / 6227020800.0;
   p = fma(p, r, 1.0 / 479001600.0);
   p = fma(p, r, 1.0 / 39916800.0);
@@ -169,12 +182,34 @@ PNB_HD double exp_pos(double x) {
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-#if defined(__CUDA_ARCH__)
-  return __longlong_as_double(__double_as_longlong(p) + ((long long)(int)k << 52));
-#else
   return ldexp(p, (int)k);
 #endif
 }
+
+#if defined(__CUDA_ARCH__)
+// sqrt(d) and 1 / sqrt(d) for a normal, positive d: MUFU.RSQ64H seed and two coupled Newton steps (no special-case branch;
+// the library sqrt and the IEEE division each carry one).  Both results within 1 ulp.
+__device__ __forceinline__ void sqrt_rsqrt_pos(double d, double *s, double *rs) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double g = d * y, h = 0.5 * y;
+  double e = fma(-g, h, 0.5);
+  g = fma(g, e, g); h = fma(h, e, h);
+  e = fma(-g, h, 0.5);
+  g = fma(g, e, g); h = fma(h, e, h);
+  *s = g; *rs = h + h;
+}
+// 1 / p for a normal p: MUFU.RCP64H seed and two Newton steps
+__device__ __forceinline__ double rcp_pos(double p) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+  double e = fma(-p, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-p, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+#endif
 
 // Kaiser-Bessel tap and derivative in double with ONE exponential and ONE division (kernel/ndft-parallel.c:2241-2269
 // evaluates sinh, cosh and three quotients per tap).  Same formulas, a few ulp from the library-call version; taps with
@@ -182,6 +217,24 @@ PNB_HD double exp_pos(double x) {
 PNB_HD bool kb_tap_fast(double y, double n, double b, int m, bool want_d, double *psi_out, double *dpsi_out) {
   const double d = (double)m * (double)m - y * y;
   const double inv_pi = 0.31830988618379067154;
+#if defined(__CUDA_ARCH__)
+  const double ad = fabs(d);
+  if (!(ad >= 1e-300)) return false;             // on the edge of the support: the library-call path
+  double r, inv_r;
+  sqrt_rsqrt_pos(ad, &r, &inv_r);
+  const double x = b * r;
+  if (!(x >= 0.5)) return false;
+  if (d < 0.0) {                                   // the tap beyond the main lobe: sin / cos, one argument reduction
+    double sn, cs;
+    sincos(x, &sn, &cs);
+    const double psi = sn * inv_r * inv_pi;
+    *psi_out = psi;
+    if (want_d) *dpsi_out = n * y * (inv_r * inv_r) * (psi - (b * inv_pi) * cs);
+    return true;
+  }
+  const double e = exp_pos(x);
+  const double ei = rcp_pos(e);
+#else
   const double r = sqrt(fabs(d)), x = b * r;
   if (!(x >= 0.5)) return false;
   if (d < 0.0) {                                   // the tap beyond the main lobe: sin / cos, one argument reduction
@@ -196,6 +249,7 @@ PNB_HD bool kb_tap_fast(double y, double n, double b, int m, bool want_d, double
   const double e = exp_pos(x);
   const double q = 1.0 / (e * r);
   const double ei = q * r, inv_r = q * e;          // 1 / e, 1 / r
+#endif
   const double psi = (0.5 * (e - ei)) * inv_r * inv_pi;
   *psi_out = psi;
   if (want_d) *dpsi_out = n * (-y) * (inv_r * inv_r) * (psi - (b * inv_pi) * (0.5 * (e + ei)));
