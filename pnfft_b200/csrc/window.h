@@ -186,6 +186,19 @@ PNB_HD double exp_pos(double x) {
 #endif
 }
 
+#if defined(__CUDACC__)
+// exp(x) for -700 < x < 700 (0 below): exp_pos's reduction and polynomial; the exponent is added as a multiple of 2^52
+__device__ __forceinline__ double exp_mid(double x) {
+  const double k = rint(x * 1.4426950408889634074);
+  double r = fma(-k, 6.93147180369123816490e-01, x);
+  r = fma(-k, 1.90821492927058770002e-10, r);
+  double p = kExpTaylor[0];
+#pragma unroll
+  for (int i = 1; i < 14; i++) p = fma(p, r, kExpTaylor[i]);
+  const double v = __longlong_as_double(__double_as_longlong(p) + (long long)(int)k * 4503599627370496LL);
+  return x > -700.0 ? v : 0.0;
+}
+#endif
 #if defined(__CUDA_ARCH__)
 // sqrt(d) and 1 / sqrt(d) for a normal, positive d: MUFU.RSQ64H seed and two coupled Newton steps (no special-case branch;
 // the library sqrt and the IEEE division each carry one).  Both results within 1 ulp.

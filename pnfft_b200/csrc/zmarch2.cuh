@@ -172,6 +172,20 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab, int first) {
         psi[s] = (R)a;
         if (GRAD) dpsi[s] = (R)b;
       }
+    } else if (sizeof(R) == 8 && g.kind == WIN_GAUSSIAN && !g.fast_gauss) {
+      // Gaussian taps in double (window.h: window_tap) with the branch-free exponential of the Kaiser-Bessel path and one
+      // division per thread instead of two per tap: psi = exp(-y^2 / b) / sqrt(pi b), dpsi = 2 n / b * y * psi
+      const double ib = 1.0 / (double)g.b[t];
+      const double c0 = 1.0 / sqrt(3.14159265358979323846 * (double)g.b[t]);
+      const double c1 = 2.0 * (double)g.n[t] * ib;
+      const double y0 = (double)(flv - nxv) - (double)M_;
+#pragma unroll
+      for (int s = 0; s < C; s++) {
+        const double y = y0 + (double)s;
+        const double a = exp_mid(-(y * y) * ib) * c0;
+        psi[s] = (R)a;
+        if (GRAD) dpsi[s] = (R)(c1 * y * a);
+      }
     } else {
       // exact formulas (nodes on a grid line, windows without a polynomial fit): through a local scratch row
       R tp[C], td[C];
