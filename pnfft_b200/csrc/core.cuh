@@ -1312,21 +1312,19 @@ template <class R> struct Core {
     }
   }
 
-  // z-march v4 (zmarch4.cuh, double only): the gather of family 3.  Rows without node values in nd->d_rows, cached like v3's.
+  // z-march v4 (zmarch4.cuh, double only): gather and scatter of family 3.  Rows without node values in nd->d_rows, cached
+  // like v3's; the scatter streams f / grad_f from the sorted value array of k_pack_vals.
   template <bool CPLX, int M_, bool GRAD>
-  static void launch_zm4_gather(P *p, Nd *nd, const NodeArgs<R> &na) {
+  static int zm4_rows(P *p, Nd *nd, const NodeArgs<R> &na) {      // returns the flavor of the rows at hand
+    int flavor = -1;
     if constexpr (sizeof(R) == 8 && Zm4Ok<M_>::value) {
       typedef Zm4Cfg<M_> Cfg;
-      typedef Zm4Smem<CPLX, M_> Sm;
-      const TileGeom tg = tile_geom(p, nullptr);
       const GridGeom<R> g = geom(p);
-      const Zm2Geom zg = zm2_work_items(tg, nd, na.M);
-      const int ncol = tg.nt[0] * tg.nt[1];
       const size_t len_g = ZmRowOf<R, Cfg, true, false, CPLX>::ROWLEN, len_f = ZmRowOf<R, Cfg, false, false, CPLX>::ROWLEN;
       const char *rc = getenv("PNFFT_B200_ROW_CACHE");
       const bool cache_on = !(rc && atoi(rc) == 0);
       const bool reuse = cache_on && nd->binned && nd->rows_plan == (const void *)p && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
-      int flavor = reuse ? nd->rows_flavor : (GRAD ? 1 : 0);
+      flavor = reuse ? nd->rows_flavor : (GRAD ? 1 : 0);
       if (!reuse && (p->b_phase & 1)) {
         ensure(&nd->d_rows, &nd->cap_rows, (size_t)na.M * (flavor ? len_g : len_f) + 64);
         const size_t psm = g.poly ? sizeof(R) * (size_t)2 * (g.poly_deg + 1) * 3 * Cfg::C : 0;
@@ -1343,18 +1341,48 @@ template <class R> struct Core {
       } else if (!reuse) {
         flavor = nd->rows_flavor;      // the table phase of this call ran earlier (side stream)
       }
+    }
+    return flavor;
+  }
+  template <bool CPLX, int M_, bool GRAD>
+  static void launch_zm4(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
+    if constexpr (sizeof(R) == 8 && Zm4Ok<M_>::value) {
+      typedef Zm4Cfg<M_> Cfg;
+      typedef Zm4Smem<CPLX, M_> Sm;
+      const TileGeom tg = tile_geom(p, nullptr);
+      const Zm2Geom zg = zm2_work_items(tg, nd, na.M);
+      const int ncol = tg.nt[0] * tg.nt[1];
+      if (scatter && (p->b_phase & 2)) {       // node values in sorted order
+        constexpr int NVP = Sm::template Scat<GRAD, GRAD>::NVP;
+        ensure(&nd->d_vals, &nd->cap_vals, (size_t)na.M * NVP + 64);
+        const long long n = (long long)na.M * NVP;
+        k_pack_vals<CPLX, GRAD><<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(na, nd->d_vals);
+        p->launches++;
+      }
+      const int flavor = zm4_rows<CPLX, M_, GRAD>(p, nd, na);
       if (p->b_phase & 2) {
-        const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::R0, Sm::R1, Cfg::ZS, 0);
         const unsigned nblk = (unsigned)(ncol * zg.nseg);
-        GatherOut<R> out;
-        out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
-        auto go = [&](auto kern) {
-          PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
-          kern<<<nblk, (Cfg::NW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, nd->d_rows, nd->d_tile_start, out);
-          p->launches++;
-        };
-        if (flavor) go(k_gather_mma4<CPLX, M_, GRAD, true>);
-        else if constexpr (!GRAD) go(k_gather_mma4<CPLX, M_, false, false>);
+        if (!scatter) {
+          const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::R0, Sm::R1, Cfg::ZS, 0);
+          GatherOut<R> out;
+          out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
+          auto go = [&](auto kern) {
+            PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
+            kern<<<nblk, (Cfg::NW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, nd->d_rows, nd->d_tile_start, out);
+            p->launches++;
+          };
+          if (flavor) go(k_gather_mma4<CPLX, M_, GRAD, true>);
+          else if constexpr (!GRAD) go(k_gather_mma4<CPLX, M_, false, false>);
+        } else {
+          const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, 1, Sm::RH, Cfg::ZS, 0);
+          auto go = [&](auto kern, int smem) {
+            PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            kern<<<2 * nblk, (Sm::NCW + 1) * 32, (size_t)smem, p->stream>>>(tm, zg, nd->d_rows, nd->d_vals, nd->d_tile_start);
+            p->launches++;
+          };
+          if (flavor) go(k_scatter_mma4<CPLX, M_, GRAD, true>, Sm::template Scat<GRAD, true>::bytes);
+          else if constexpr (!GRAD) go(k_scatter_mma4<CPLX, M_, false, false>, Sm::template Scat<false, false>::bytes);
+        }
       }
       PNB_CUDA(cudaGetLastError());
     }
@@ -1374,9 +1402,11 @@ template <class R> struct Core {
     PNB_CUDA(cudaGetLastError());
     p->launches++;
   }
+  // PNFFT_B200_MMA4_SCATTER=0: the adjoint of family 3 on the round-1 kernels (v1 z-march at m = 8, generic at m = 5, 7)
   template <bool CPLX, int M_, bool GRAD>
   static void launch_fam3(P *p, Nd *nd, const NodeArgs<R> &na, bool scatter) {
-    if (!scatter) launch_zm4_gather<CPLX, M_, GRAD>(p, nd, na);
+    static const bool sc4 = env_flag("PNFFT_B200_MMA4_SCATTER", true);
+    if (!scatter || sc4) launch_zm4<CPLX, M_, GRAD>(p, nd, na, scatter);
     else if constexpr (M_ == 8) { if (p->b_phase & 2) launch_zm<CPLX, M_, GRAD>(p, nd, na, true); }
     else { if (p->b_phase & 2) launch_generic(p, na, true, CPLX); }
   }

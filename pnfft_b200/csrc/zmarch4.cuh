@@ -31,7 +31,9 @@ template <int M_> struct Zm4Cfg {
   static constexpr int T0 = 8, T1 = 4, ZS = 4;   // column tile and z sub-chunk (cells)
   static constexpr int SUB = 8;                  // x-offset bins per tile in the sort key
   static constexpr int KS = (ZS + 2 * M_ + 3) / 4;   // window chunks = k-steps per row
-  static constexpr int W = 4 * KS;               // z weights per node, zero padded (pre-shifted by the node's dz)
+  static constexpr int W = (ZS + 2 * M_ + 7) / 8 * 8;   // z weights per node, zero padded (pre-shifted by the node's dz): the
+                                                 // gather reads 4 KS of them, the scatter's circular accumulator window all W
+  static constexpr int NFL = (ZS + 2 * M_ + ZS - 1) / ZS;   // flushes until a touched accumulator window is all zero again
   static constexpr int R0 = T0 + 2 * M_;         // footprint rows along x
   static constexpr int R1C = (T1 + 2 * M_ + 3) / 4 * 4, R1R = (T1 + 2 * M_ + 7) / 8 * 8;   // y rows in whole n-blocks (c2c / c2r)
   static constexpr int XLEAD = T0 - 1;
@@ -51,6 +53,24 @@ template <bool CPLX, int M_> struct Zm4Smem {
   static constexpr int gather = off_bar + (2 * Cfg::NSLOT + 2) * 8;
   static_assert(SLOTB % 128 == 0, "alignment");
   static_assert(gather <= 232448, "shared-memory budget of one CTA exceeded");
+  // scatter: a CTA owns one y half of the footprint (NYB0 n-blocks of whole rows, the second half may be shorter), one x
+  // row per consumer warp; two staging boxes [1][RH][ZS] per warp, ring of SS stages {header, SGB rows, SGB value rows}
+  static constexpr int NYB0 = (NYB + 1) / 2, NYB1 = NYB - NYB0;
+  static constexpr int RH = NYB0 * 8 / NCOMP;    // y rows of a half's TMA box
+  static constexpr int NCW = Cfg::R0;            // consumer warps
+  static constexpr int WARP_BOX = RH * Cfg::ZS * CELLB;
+  static constexpr int SS = 3, SGB = 16;
+  template <bool GRAD, bool RG> struct Scat {
+    typedef ZmRowOf<double, Cfg, RG, false, CPLX> Row;
+    static constexpr int NVAL = NCOMP * (GRAD ? 4 : 1), NVP = (NVAL + 1) / 2 * 2;
+    static constexpr int off_vals = kZm2HdrBytes + SGB * Row::ROWBYTES;
+    static constexpr int stage = off_vals + SGB * NVP * 8;
+    static constexpr int off_ring = (NCW * 2 * WARP_BOX + 127) / 128 * 128;
+    static constexpr int off_bar = off_ring + SS * stage;
+    static constexpr int bytes = off_bar + 2 * SS * 8;
+    static_assert(stage % 16 == 0 && off_vals % 16 == 0 && WARP_BOX % 128 == 0, "alignment");
+    static_assert(bytes <= 232448, "shared-memory budget of one CTA exceeded");
+  };
 };
 
 __device__ __forceinline__ double ldg_f64(const unsigned char *p) { return __ldg(reinterpret_cast<const double *>(p)); }
@@ -284,6 +304,250 @@ k_gather_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter (adjoint B^T): v3's tensor-core scatter (zmarch3.cuh: k_scatter_mma) on the v4 geometry
+// ------------------------------------------------------------------------------------------------
+// window[k, column] += sum_node psi_z[node, k] * amp[node, column], M = 8 z cells, N = 8 columns, K = 4 nodes per DMMA.  The
+// accumulator window of a row does not fit one warp's registers at m = 8 together with its neighbours', so a CTA owns one
+// y HALF of the column tile's footprint (blockIdx parity) and each of its R0 consumer warps ONE x row of it: NYBH n-blocks
+// x W / 8 cell blocks of C fragments.  The window is circular in its W cell slots (W = 24 at m = 7, 8: not a power of two);
+// everything else is v3's: the service warp streams rows and sorted node values into a ring, a warp meets the nodes whose x
+// support covers its row (a contiguous range of the chunk's dx-sorted nodes), finished chunks leave through a staging box
+// and ONE TMA reduce-add per warp and advance.
+template <bool CPLX, int M_, bool GRAD, bool RG, int NYBH, class Sm, class Sc>
+__device__ __forceinline__ void zm4_scatter_rows(const CUtensorMap &tmap, unsigned char *smem_raw, int warp, int lane, int col, int yh,
+                                                 const Zm2Geom &zg, int tz0) {
+  typedef Zm4Cfg<M_> Cfg;
+  typedef typename Sc::Row Row;
+  constexpr int C = Cfg::C, T0 = Cfg::T0, ZS = Cfg::ZS, W = Cfg::W, NZB = W / 8;
+  constexpr int NCOMP = Sm::NCOMP, S = Sm::SS, ROWBYTES = Row::ROWBYTES, STAGE = Sc::stage, NVP = Sc::NVP;
+  constexpr bool PF = !GRAD;             // operands of the next batch built while this batch's MMAs run (register budget)
+  unsigned char *ring = smem_raw + Sc::off_ring;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + Sc::off_bar);
+  unsigned long long *empty = full + S;
+
+  const int g = lane >> 2, t = lane & 3;
+  const int cx = col / zg.nc[1], cy = col - cx * zg.nc[1];
+  const int o0 = cx * T0 + warp, o1 = cy * Cfg::T1 + yh * Sm::RH;
+  const int dxlo = max(0, warp - (C - 1)), dxhi1 = min(T0 - 1, warp) + 1;
+  unsigned char *mystg = smem_raw + (size_t)warp * 2 * Sm::WARP_BOX;
+  // B fragment: column 8 nb + g is component g & 1 of row 4 nb + (g >> 1) (complex) or row 8 nb + g (real) of my half
+  const int aX = (Row::oX + Cfg::XLEAD + warp) * 8;
+  const int aY = (Row::oY + Cfg::YLEAD + yh * Sm::RH + (CPLX ? (g >> 1) : g)) * 8;
+  const int aV = CPLX ? (g & 1) * 8 : 0;
+  constexpr int dOff = RG ? (Row::oDX - Row::oX) * 8 : 0;
+  // C fragment -> staging box [RH][4]: cell z = g & 3 of row 4 nb + t (complex), rows 8 nb + 2t, 2t + 1 (real)
+  const int stg_off = CPLX ? (t * 64 + (g & 3) * 16) : (2 * t * 32 + (g & 3) * 8);
+
+  double acc[NYBH][NZB][2];
+#pragma unroll
+  for (int nb = 0; nb < NYBH; nb++)
+#pragma unroll
+    for (int zb = 0; zb < NZB; zb++) { acc[nb][zb][0] = 0; acc[nb][zb][1] = 0; }
+  int cur = tz0, dirty = 0, nfl = 0;
+
+  auto flush_advance = [&]() {
+    unsigned char *sb = mystg + (nfl & 1) * Sm::WARP_BOX;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box issued two flushes ago was read
+    __syncwarp();
+    const int slot0 = (cur * ZS) % W;
+    const bool mine = (g >> 2) == ((slot0 >> 2) & 1);
+    const int zsel = slot0 >> 3;
+    if (NYBH * 8 / NCOMP < Sm::RH) {       // the shorter half: rows of the box my n-blocks do not cover stay zero
+      for (int i = lane; i < Sm::WARP_BOX / 16; i += 32) reinterpret_cast<uint4 *>(sb)[i] = make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int zb = 0; zb < NZB; zb++)
+      if (zb == zsel) {
+#pragma unroll
+        for (int nb = 0; nb < NYBH; nb++) {
+          if (mine) {
+            if constexpr (CPLX) {
+              *reinterpret_cast<double2 *>(sb + nb * 256 + stg_off) = make_double2(acc[nb][zb][0], acc[nb][zb][1]);
+            } else {
+              *reinterpret_cast<double *>(sb + nb * 256 + stg_off) = acc[nb][zb][0];
+              *reinterpret_cast<double *>(sb + nb * 256 + stg_off + 32) = acc[nb][zb][1];
+            }
+            acc[nb][zb][0] = 0; acc[nb][zb][1] = 0;
+          }
+        }
+      }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      tma_reduce_add_3d(sb, &tmap, cur * ZS * NCOMP, o1, o0);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    nfl++;
+    cur++;
+  };
+
+  for (int kb = 0;; kb++) {
+    const int st = kb % S;
+    mbar_wait_park(&full[st], ((unsigned)(kb / S)) & 1u);
+    const unsigned char *sp = ring + (size_t)st * STAGE;
+    const int *h = reinterpret_cast<const int *>(sp);
+    const int tz = h[0];
+    if (tz == INT_MAX) break;
+    const int lo = h[4 + dxlo], hi = h[4 + dxhi1];
+    if (hi > lo) {
+      while (cur < tz) {
+        if (dirty > 0) { flush_advance(); dirty--; }
+        else cur = tz;
+      }
+      // z weight offsets of my cell slots for this window position
+      int offA[NZB];
+#pragma unroll
+      for (int zb = 0; zb < NZB; zb++) offA[zb] = (Row::oZ + (((8 * zb + g - cur * ZS) % W + W) % W)) * 8;
+      constexpr int NZG = GRAD ? NZB : 1, NYG = GRAD ? NYBH : 1;
+      auto prep = [&](int b0, double (&az)[NZB], double (&adz)[NZG], double (&bA)[NYBH], double (&bB)[NYG]) {
+        const bool valid = b0 + t < hi;
+        const int i = min(b0 + t, hi - 1);
+        const unsigned char *row = sp + kZm2HdrBytes + (size_t)i * ROWBYTES;
+        const int4 hd = *reinterpret_cast<const int4 *>(row);       // {-dx*8, -dy*8, dz, dx}
+#pragma unroll
+        for (int zb = 0; zb < NZB; zb++) {
+          az[zb] = *reinterpret_cast<const double *>(row + offA[zb]);
+          if (GRAD) adz[zb] = *reinterpret_cast<const double *>(row + offA[zb] + dOff);
+        }
+        const unsigned char *vrow = sp + Sc::off_vals + (size_t)i * NVP * 8 + aV;
+        double f = *reinterpret_cast<const double *>(vrow);
+        if (!valid) f = 0;
+        double g0 = 0, g1 = 0, g2 = 0;
+        if (GRAD) {
+          g0 = *reinterpret_cast<const double *>(vrow + NCOMP * 8);
+          g1 = *reinterpret_cast<const double *>(vrow + 2 * NCOMP * 8);
+          g2 = *reinterpret_cast<const double *>(vrow + 3 * NCOMP * 8);
+          if (!valid) { g0 = 0; g1 = 0; g2 = 0; }
+        }
+        // amplitudes: A = psi_x (psi_y f + dpsi_y g1) + dpsi_x psi_y g0, B = psi_x psi_y g2 (paired with dpsi_z)
+        const double w0 = *reinterpret_cast<const double *>(row + aX + hd.x);
+        double ax = w0 * f, bx = 0, cxw = 0;
+        if (GRAD) {
+          const double dw0 = *reinterpret_cast<const double *>(row + aX + dOff + hd.x);
+          ax = fma(dw0, g0, ax);
+          bx = w0 * g1;
+          cxw = w0 * g2;
+        }
+#pragma unroll
+        for (int jy = 0; jy < NYBH; jy++) {
+          const int yo = CPLX ? 4 * jy : 8 * jy;
+          const double w1 = *reinterpret_cast<const double *>(row + aY + yo * 8 + hd.y);
+          bA[jy] = w1 * ax;
+          if (GRAD) {
+            const double dw1 = *reinterpret_cast<const double *>(row + aY + yo * 8 + dOff + hd.y);
+            bA[jy] = fma(dw1, bx, bA[jy]);
+            bB[jy] = w1 * cxw;
+          }
+        }
+      };
+      double az[NZB], adz[NZG], bA[NYBH], bB[NYG];
+      if constexpr (PF) {
+        double az_n[NZB], adz_n[NZG], bA_n[NYBH], bB_n[NYG];
+        prep(lo, az, adz, bA, bB);
+        for (int b0 = lo; b0 < hi; b0 += 4) {
+          prep(b0 + 4, az_n, adz_n, bA_n, bB_n);
+#pragma unroll
+          for (int nb = 0; nb < NYBH; nb++)
+#pragma unroll
+            for (int zb = 0; zb < NZB; zb++) dmma884(acc[nb][zb], az[zb], bA[nb]);
+#pragma unroll
+          for (int zb = 0; zb < NZB; zb++) az[zb] = az_n[zb];
+#pragma unroll
+          for (int nb = 0; nb < NYBH; nb++) bA[nb] = bA_n[nb];
+        }
+      } else {
+        for (int b0 = lo; b0 < hi; b0 += 4) {
+          prep(b0, az, adz, bA, bB);
+#pragma unroll
+          for (int nb = 0; nb < NYBH; nb++) {
+#pragma unroll
+            for (int zb = 0; zb < NZB; zb++) dmma884(acc[nb][zb], az[zb], bA[nb]);
+            if (GRAD) {
+#pragma unroll
+              for (int zb = 0; zb < NZB; zb++) dmma884(acc[nb][zb], adz[zb], bB[nb]);
+            }
+          }
+        }
+      }
+      dirty = Cfg::NFL;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+  while (dirty > 0) { flush_advance(); dirty--; }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive the bulk reads
+}
+
+template <bool CPLX, int M_, bool GRAD, bool RG>
+__global__ void __launch_bounds__((Zm4Cfg<M_>::R0 + 1) * 32, 1)
+k_scatter_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double *__restrict__ tab, const double *__restrict__ vals,
+               const int *__restrict__ bin_start) {
+  typedef Zm4Cfg<M_> Cfg;
+  typedef Zm4Smem<CPLX, M_> Sm;
+  typedef typename Sm::template Scat<GRAD, RG> Sc;
+  typedef typename Sc::Row Row;
+  constexpr int T0 = Cfg::T0, NCW = Sm::NCW, S = Sm::SS, GB = Sm::SGB, ROWBYTES = Row::ROWBYTES, STAGE = Sc::stage, NVP = Sc::NVP;
+  static_assert(GB % 4 == 0 && 4 + T0 + 1 <= kZm2HdrBytes / 4, "ring stages hold whole node batches; header layout");
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *ring = smem_raw + Sc::off_ring;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + Sc::off_bar);
+  unsigned long long *empty = full + S;
+
+  const int yh = blockIdx.x & 1, item = blockIdx.x >> 1;
+  const int colr = item / zg.nseg, seg = item - colr * zg.nseg, col = zg.col0 + colr;
+  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
+  const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
+  if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;            // no nodes in this work item
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < S; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCW) {
+    // service warp: rows and sorted node values of GB nodes per ring stage, with the chunk's dx prefix table
+    const unsigned char *tabb = reinterpret_cast<const unsigned char *>(tab);
+    int kb = 0;
+    int gs_next = (lane <= T0) ? bs[(size_t)tz0 * Cfg::SUB + lane] : 0;
+    for (int tz = tz0; tz < tz1; tz++) {
+      const int gs = gs_next;
+      if (tz + 1 < tz1) gs_next = (lane <= T0) ? bs[(size_t)(tz + 1) * Cfg::SUB + lane] : 0;
+      const int s0 = __shfl_sync(0xffffffffu, gs, 0), e = __shfl_sync(0xffffffffu, gs, T0);
+      for (int c0 = s0; c0 < e; c0 += GB, kb++) {
+        const int st = kb % S;
+        mbar_wait_park(&empty[st], (((unsigned)(kb / S)) & 1u) ^ 1u);
+        const int cnt = min(GB, e - c0);
+        unsigned char *sp = ring + (size_t)st * STAGE;
+        int *h = reinterpret_cast<int *>(sp);
+        if (lane <= T0) h[4 + lane] = min(max(gs - c0, 0), cnt);
+        if (lane == 0) { h[0] = tz; h[1] = cnt; h[2] = c0; h[3] = 0; }
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned rb = (unsigned)(cnt * ROWBYTES), vb = (unsigned)(cnt * NVP * 8);
+          mbar_expect_tx(&full[st], rb + vb);
+          bulk_load_1d(sp + kZm2HdrBytes, tabb + (size_t)c0 * ROWBYTES, rb, &full[st]);
+          bulk_load_1d(sp + Sc::off_vals, vals + (size_t)c0 * NVP, vb, &full[st]);
+        }
+      }
+    }
+    const int st = kb % S;
+    mbar_wait_park(&empty[st], (((unsigned)(kb / S)) & 1u) ^ 1u);
+    if (lane == 0) {
+      int *h = reinterpret_cast<int *>(ring + (size_t)st * STAGE);
+      h[0] = INT_MAX; h[1] = 0;
+      mbar_arrive(&full[st]);
+    }
+    return;
+  }
+  if (yh == 0) zm4_scatter_rows<CPLX, M_, GRAD, RG, Sm::NYB0, Sm, Sc>(tmap, smem_raw, warp, lane, col, 0, zg, tz0);
+  else if constexpr (Sm::NYB1 > 0) zm4_scatter_rows<CPLX, M_, GRAD, RG, Sm::NYB1, Sm, Sc>(tmap, smem_raw, warp, lane, col, 1, zg, tz0);
 }
 
 }  // namespace pnb

@@ -146,8 +146,8 @@ def test_hessian_only_and_accumulated():
 @pytest.mark.parametrize("c2r", [False, True])
 @pytest.mark.parametrize("m", [5, 7, 8])
 def test_family3_shared_window_gather(ref, m, c2r):
-    """Kernel family 3 (double, m = 5, 7, 8): the tensor-core gather with the window in shared memory (zmarch4.cuh) and the
-    scatter that shares its bins (v1 at m = 8, generic at m = 5, 7), on a node set with a dense cluster, sparse
+    """Kernel family 3 (double, m = 5, 7, 8): the tensor-core gather with the window in shared memory and the tensor-core
+    scatter on the same bins (zmarch4.cuh), on a node set with a dense cluster, sparse
     surroundings and empty sub-chunks, against the generic kernels (independent code path) and a node subset against the
     compiled reference; F alone, F with the gradient, and accumulation into the outputs."""
     N, M = (32, 32, 32), 30000
@@ -164,14 +164,18 @@ def test_family3_shared_window_gather(ref, m, c2r):
         run.plan.trafo(run.nodes, F | G | A.COMPUTE_ACCUMULATED)
         f3, g3 = run.f.copy(), run.g.copy()
         fho = run.adj(f, g, F | G)
+        fho_f = run.adj(f, None, F)
+        fho_acc = run.adj(f, None, F | A.COMPUTE_ACCUMULATED, f_hat0=fh) - fh
         run.close()
-        res.append((f1, f2, g2, f3 - 1.0, g3 - 2.0, fho))
+        res.append((f1, f2, g2, f3 - 1.0, g3 - 2.0, fho, fho_f, fho_acc))
     for a, b in zip(res[0], res[1]):
         assert rel_l2(a, b) <= 1e-13
     assert rel_l2(res[0][0], res[0][1]) <= 1e-15       # F and F|GRAD instantiations
     sub = slice(0, 2048)
     rt = ref.trafo(N, x[sub], fh, m=m, compute_flags=F | G, c2r=c2r)
     assert rel_l2(res[0][1][sub], rt["f"]) <= 1e-13 and rel_l2(res[0][2][sub], rt["grad_f"]) <= 1e-13
+    ra = ref.adj(N, x, f=f, grad_f=g, m=m, compute_flags=F | G, c2r=c2r)
+    assert rel_l2(res[0][5], ra["f_hat"]) <= 1e-13
 
 
 @pytest.mark.parametrize("m", [4, 6])
