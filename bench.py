@@ -210,8 +210,11 @@ def reference_step(w, sample_log2M, seed=0):
         x = np.mod(rng.normal(0.0, 0.05, (Ms, 3)) + 0.5, 1.0) - 0.5
     x = np.clip(x, -0.5, np.nextafter(0.5, 0.0))
     fh = global_f_hat(w)
+    # the reference cannot run PNFFT_PRE_PSI together with COMPUTE_GRAD_F: it never allocates pre_dpsi (its PNFFT_DIFF_AD
+    # test is always false, SURVEY 8a defect 2) and dereferences it in the node loop; its on-the-fly path is timed then
+    ref_pre = bool(w["pre_psi"]) and not (w["cf_trafo"] & CF_GRAD)
     kw = dict(n=w["n"], m=w["m"], np_mesh=mesh, pnfft_flags=w["flags"], c2r=w["c2r"],
-              precompute_flags=6 if w["pre_psi"] else 0)
+              precompute_flags=6 if ref_pre else 0)
     t0 = time.time()
     rt = ref.trafo(w["N"], x, fh, compute_flags=w["cf_trafo"], **kw)
     t1 = time.time()
@@ -233,8 +236,10 @@ def reference_step(w, sample_log2M, seed=0):
         full = sample_s * scale
     det.update(sample_s=float(sample_s), extrapolated_full_s=float(full), cores=mesh[0] * mesh[1], kind=ref.kind,
                sample="N=%d^3 n=%d^3 m=%d plan, 2^%d of 2^%d nodes, %dx%d ranks (one thread each); node loop scaled x%d, "
-                      "D/F/ghost cells as measured (F by the oracle shim's host FFT, FFTW/PFFT are absent)"
-                      % (w["N"][0], w["n"][0], w["m"], sample_log2M, w["log2M"], mesh[0], mesh[1], int(scale)))
+                      "D/F/ghost cells as measured (F by the oracle shim's host FFT, FFTW/PFFT are absent)%s"
+                      % (w["N"][0], w["n"][0], w["m"], sample_log2M, w["log2M"], mesh[0], mesh[1], int(scale),
+                         "; window factors on the fly (the reference segfaults with PNFFT_PRE_PSI and COMPUTE_GRAD_F: pre_dpsi "
+                         "is never allocated)" if (w["pre_psi"] and not ref_pre) else ""))
     return w["M_total"] / full, det
 
 
@@ -509,7 +514,7 @@ def run_gpu(args):
         "peak_source": "FP64 FMA: measured live (independent DFMA chains on all SMs, pnfft_b200_measure_fp64_tflops); HBM: "
                        + hbm_src + prec_note,
         "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac_hbm"]},
-        "algorithmic": "flops/node: gather F+grad 16*(2m+1)^3, gather / scatter F 4*(2m+1)^3 (c2c; r2r half); bytes: grid "
+        "algorithmic": "flops/node: gather F+grad 16*(2m+1)^3 = the reference's four weighted sums per tap (a separable evaluation needs about half: frac may exceed 1 for large m), gather / scatter F 4*(2m+1)^3 (c2c; r2r half); bytes: grid "
                        "block once + x,f[,grad_f] once (SURVEY.md 8d); the kernel time of the slowest rank against the "
                        "node count of the fullest rank; kernel ms include the node-table kernel of the call "
                        "(new coordinates every step: pnfft_trafo builds the table, pnfft_adj of the same step reuses it)",

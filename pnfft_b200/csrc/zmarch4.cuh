@@ -491,7 +491,7 @@ k_scatter_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const doubl
   typedef typename Sm::template Scat<GRAD, RG> Sc;
   typedef typename Sc::Row Row;
   constexpr int T0 = Cfg::T0, NCW = Sm::NCW, S = Sm::SS, GB = Sm::SGB, ROWBYTES = Row::ROWBYTES, STAGE = Sc::stage, NVP = Sc::NVP;
-  static_assert(GB % 4 == 0 && 4 + T0 + 1 <= kZm2HdrBytes / 4, "ring stages hold whole node batches; header layout");
+  static_assert(GB % 4 == 0 && GB <= 32 && 4 + T0 + 1 <= kZm2HdrBytes / 4 && (Row::oDX * 8) % 16 == 0, "ring stages hold whole node batches; header layout");
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *ring = smem_raw + Sc::off_ring;
@@ -529,11 +529,20 @@ k_scatter_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const doubl
         if (lane <= T0) h[4 + lane] = min(max(gs - c0, 0), cnt);
         if (lane == 0) { h[0] = tz; h[1] = cnt; h[2] = c0; h[3] = 0; }
         __syncwarp();
+        // an F-only scatter on rows that carry derivative sections reads the first (psi) half of every row only
+        constexpr bool HALF = RG && !GRAD;
+        constexpr unsigned PSIB = (unsigned)Row::oDX * 8u;
+        const unsigned vb = (unsigned)(cnt * NVP * 8);
         if (lane == 0) {
-          const unsigned rb = (unsigned)(cnt * ROWBYTES), vb = (unsigned)(cnt * NVP * 8);
+          const unsigned rb = HALF ? (unsigned)cnt * PSIB : (unsigned)(cnt * ROWBYTES);
           mbar_expect_tx(&full[st], rb + vb);
-          bulk_load_1d(sp + kZm2HdrBytes, tabb + (size_t)c0 * ROWBYTES, rb, &full[st]);
+          if (!HALF) bulk_load_1d(sp + kZm2HdrBytes, tabb + (size_t)c0 * ROWBYTES, rb, &full[st]);
           bulk_load_1d(sp + Sc::off_vals, vals + (size_t)c0 * NVP, vb, &full[st]);
+        }
+        if (HALF) {
+          __syncwarp();      // the expected byte count is posted before any copy can complete
+          if (lane < cnt)
+            bulk_load_1d(sp + kZm2HdrBytes + (size_t)lane * ROWBYTES, tabb + (size_t)(c0 + lane) * ROWBYTES, PSIB, &full[st]);
         }
       }
     }
