@@ -1217,7 +1217,18 @@ template <class R> struct Core {
       typedef Zm2Cfg<M_> Cfg;
       typedef Zm3Smem<CPLX, M_, GRAD, RG> Sm;
       const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::XW, 16, Cfg::ZB, 0);   // boxes are read 256 contiguous bytes per n-block: no swizzle
-      if (!scatter) {
+      // PNFFT_B200_GATHER4=1: the shared-window gather of zmarch4.cuh on v3's bins and rows instead of k_gather_mma
+      static const bool g4 = env_flag("PNFFT_B200_GATHER4", false);
+      if (!scatter && g4) {
+        typedef Zm4on2Cfg<M_> C4;
+        typedef Zm4Smem<CPLX, M_, C4> Sm4;
+        const CUtensorMap tm4 = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, C4::R0, Sm4::R1, C4::ZS, 0);
+        GatherOut<R> out;
+        out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
+        auto kern = k_gather_mma4<CPLX, M_, GRAD, RG, C4>;
+        PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm4::gather));
+        kern<<<nblk, (C4::NW + 1) * 32, Sm4::gather, p->stream>>>(tm4, zg, tab, nd->d_tile_start, out);
+      } else if (!scatter) {
         GatherOut<R> out;
         out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
         auto kern = k_gather_mma<CPLX, M_, GRAD, RG>;

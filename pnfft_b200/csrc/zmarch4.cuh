@@ -43,8 +43,21 @@ template <int M_> struct Zm4Cfg {
   static constexpr int NW = 15;                  // consumer warps (+ 1 service warp = 512 threads, 128 registers)
 };
 
-template <bool CPLX, int M_> struct Zm4Smem {
-  typedef Zm4Cfg<M_> Cfg;
+// The shared-window gather on v3's geometry (m = 6: column tile 10 x 4, 16 x-offset bins, v3's node-table rows, so that it
+// pairs with v3's scatter on one binning and one table).  v3's rows carry ONE leading zero in front of the x weights, not
+// T0 - 1: the gather tests the tap range instead of reading padding (Zm4Smem::XPRED).
+template <int M_> struct Zm4on2Cfg : Zm2Cfg<M_> {
+  typedef Zm2Cfg<M_> B;
+  static constexpr int KS = (B::ZS + 2 * M_ + 3) / 4;
+  static constexpr int NSLOT = KS + 1;
+  static constexpr int R1C = (B::T1 + 2 * M_ + 3) / 4 * 4, R1R = (B::T1 + 2 * M_ + 7) / 8 * 8;
+  static constexpr int NW = 19;                  // consumer warps (+ 1 service warp = 640 threads, 102 registers)
+  static_assert(R1R - B::C <= B::YLEAD, "y weights of every footprint row must lie inside the row's y section");
+};
+
+template <bool CPLX, int M_, class Cfg_ = Zm4Cfg<M_>> struct Zm4Smem {
+  typedef Cfg_ Cfg;
+  static constexpr bool XPRED = Cfg::XLEAD < Cfg::T0 - 1;
   static constexpr int NCOMP = CPLX ? 2 : 1, CELLB = 8 * NCOMP;
   static constexpr int R1 = CPLX ? Cfg::R1C : Cfg::R1R;
   static constexpr int NYB = R1 * NCOMP / 8;     // n-blocks per x row
@@ -78,13 +91,13 @@ __device__ __forceinline__ double ldg_f64(const unsigned char *p) { return __ldg
 // ------------------------------------------------------------------------------------------------
 // gather (trafo B)
 // ------------------------------------------------------------------------------------------------
-template <bool CPLX, int M_, bool GRAD, bool RG>
-__global__ void __launch_bounds__((Zm4Cfg<M_>::NW + 1) * 32, 1)
+template <bool CPLX, int M_, bool GRAD, bool RG, class Cfg_ = Zm4Cfg<M_>>
+__global__ void __launch_bounds__((Cfg_::NW + 1) * 32, 1)
 k_gather_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double *__restrict__ tab, const int *__restrict__ bin_start,
               GatherOut<double> out) {
   static_assert(RG || !GRAD, "a gradient kernel needs rows with derivative sections");
-  typedef Zm4Cfg<M_> Cfg;
-  typedef Zm4Smem<CPLX, M_> Sm;
+  typedef Cfg_ Cfg;
+  typedef Zm4Smem<CPLX, M_, Cfg_> Sm;
   typedef ZmRowOf<double, Cfg, RG, false, CPLX> Row;
   constexpr int C = Cfg::C, ZS = Cfg::ZS, KS = Cfg::KS, NW = Cfg::NW, NSLOT = Cfg::NSLOT, SUB = Cfg::SUB;
   constexpr int NCOMP = Sm::NCOMP, CELLB = Sm::CELLB, R1 = Sm::R1, NYB = Sm::NYB, SLOTB = Sm::SLOTB;
@@ -217,13 +230,18 @@ k_gather_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
     double v[NVAL];
 #pragma unroll
     for (int q = 0; q < NVAL; q++) v[q] = 0;
-    double wx_n = ldg_f64(xw + xlo * 8), dwx_n = GRAD ? ldg_f64(xw + xlo * 8 + dOff) : 0.0;
+    // x weight of row X for my node: padding in the row (v4's own rows), or the tap range tested (v3's rows)
+    auto ld_wx = [&](int X, double &w, double &dw) {
+      if (!Sm::XPRED || (unsigned)(X - hd.w) < (unsigned)C) {
+        w = ldg_f64(xw + X * 8);
+        if (GRAD) dw = ldg_f64(xw + X * 8 + dOff);
+      } else { w = 0; dw = 0; }
+    };
+    double wx_n = 0, dwx_n = 0;
+    ld_wx(xlo, wx_n, dwx_n);
     for (int X = xlo; X < xhi; X++) {
       const double wx = wx_n, dwx = dwx_n;
-      if (X + 1 < xhi) {
-        wx_n = ldg_f64(xw + (X + 1) * 8);
-        if (GRAD) dwx_n = ldg_f64(xw + (X + 1) * 8 + dOff);
-      }
+      if (X + 1 < xhi) ld_wx(X + 1, wx_n, dwx_n);
       const int xoff = X * (R1 * ZS * CELLB);
       double a[NCOMP], bb[NCOMP], c[NCOMP];
 #pragma unroll

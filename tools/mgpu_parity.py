@@ -40,7 +40,10 @@ def main():
     cases = [((32, 32, 32), 20000, 6, 0, False), ((32, 48, 40), 15000, 4, A.WINDOW_GAUSSIAN, False),
              ((32, 32, 32), 20000, 6, A.DIFF_IK, False), ((32, 32, 32), 20000, 6, 0, True),
              ((32, 48, 40), 15000, 6, A.TRANSPOSED_F_HAT, False), ((32, 32, 32), 20000, 4, A.TRANSPOSED_F_HAT, True),
-             ((32, 32, 32), 20000, 6, A.INTERLACED, False), ((32, 48, 40), 15000, 4, A.INTERLACED | A.TRANSPOSED_F_HAT | A.DIFF_IK, False)]
+             ((32, 32, 32), 20000, 6, A.INTERLACED, False), ((32, 48, 40), 15000, 4, A.INTERLACED | A.TRANSPOSED_F_HAT | A.DIFF_IK, False),
+             # kernel family 3 (tensor-core gather / scatter with the window in shared memory): m = 8, 5, 7
+             ((32, 32, 32), 20000, 8, A.WINDOW_GAUSSIAN, False), ((32, 48, 40), 15000, 5, A.WINDOW_BSPLINE, True),
+             ((32, 32, 32), 20000, 7, A.INTERLACED, False)]
     if len(sys.argv) > 1:       # a larger problem: N^3 with M nodes, Kaiser-Bessel m=6 (python tools/mgpu_parity.py N M)
         cases = [((int(sys.argv[1]),) * 3, int(sys.argv[2]), 6, 0, False)]
     for ci, (N, M, m, flags, c2r) in enumerate(cases):
