@@ -378,10 +378,16 @@ template <class R> struct Core {
           }
         }
       }
-    PNB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    // the plan's stream carries F and the ghost-cell exchange, whose peer-memory stages other ranks wait for: it gets the
+    // highest priority, the node-side stream (binning, window table: 10^5 small blocks that would otherwise occupy every
+    // SM while F's kernels queue behind them) the lowest.  PNFFT_B200_STREAM_PRIO=0 creates them all alike.
+    int prio_lo = 0, prio_hi = 0;
+    static const bool use_prio = env_flag("PNFFT_B200_STREAM_PRIO", true);
+    if (use_prio) PNB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    PNB_CUDA(cudaStreamCreateWithPriority(&p->stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 16; i++) PNB_CUDA(cudaEventCreate(&p->ev[i]));
     PNB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-    PNB_CUDA(cudaStreamCreateWithFlags(&p->node_stream, cudaStreamNonBlocking));
+    PNB_CUDA(cudaStreamCreateWithPriority(&p->node_stream, cudaStreamNonBlocking, prio_lo));
     for (int i = 0; i < 3; i++) PNB_CUDA(cudaEventCreateWithFlags(&p->ev_copy[i], cudaEventDisableTiming));
     memset(p->timer_trafo, 0, sizeof p->timer_trafo);
     memset(p->timer_adj, 0, sizeof p->timer_adj);
@@ -1769,6 +1775,15 @@ template <class R> struct Core {
         const bool want_side = x_first || (side_env >= 0 ? side_env != 0 : p->mesh.size > 1);
         p->side_nodes = want_side && npass == 1 && conv && M > 0 && kernel_family(p) == 2 && (cf & (C_F | C_GRAD_F));
         NodeArgs<R> na_side;
+        // the grid side is queued FIRST unless the coordinates go over the bus first: prepare_nodes blocks the host until
+        // an upload of host-resident coordinates has been hashed, and F must not wait in the host's queue behind that
+        const bool grid_first = p->side_nodes && !x_first;
+        if (grid_first) {
+          if (!(cf & C_OMIT_FFT)) fft_forward(p);
+          rec(p, 3);
+          halo(p, false);
+          rec(p, 6);
+        }
         if (p->side_nodes) {
           p->stream = p->node_stream;
           PNB_CUDA(cudaStreamWaitEvent(p->node_stream, p->ev_copy[0], 0));   // the node stream starts where this call started
@@ -1790,12 +1805,17 @@ template <class R> struct Core {
           run_deconv(p, fh, nullptr, false);
           rec(p, 2);
         }
-        if (!(cf & C_OMIT_FFT)) fft_forward(p);
-        rec(p, 3);
+        if (!grid_first) {
+          if (!(cf & C_OMIT_FFT)) fft_forward(p);
+          rec(p, 3);
+        }
         if (p->side_nodes) {
-          halo(p, false);
-          rec(p, 6);
+          if (!grid_first) {
+            halo(p, false);
+            rec(p, 6);
+          }
           PNB_CUDA(cudaStreamWaitEvent(st, p->ev[10], 0));
+          rec(p, 12);                    // grid side and node side have met: the gather starts here
           p->b_phase = 2;
           if (df || dg) launch_B_any(p, nd, na_side, false);
           p->b_phase = 3;
@@ -1968,7 +1988,7 @@ template <class R> struct Core {
       s[0] = ms(p, 6, 7); s[1] = ms(p, 4, 5); s[2] = ms(p, 5, 6); s[3] = ms(p, 2, 3); s[4] = ms(p, 1, 2);
       s[5] = ms(p, 0, 1) + ms(p, 3, 4); s[6] = ms(p, 7, 8); s[7] = ms(p, 0, 8);
       if (p->side_nodes) {   // node side on its own stream: x upload ev[11]->ev[4], binning ev[4]->ev[5], node table ev[9]->ev[10]
-        s[0] = ms(p, 6, 7) + ms(p, 9, 10); s[1] = ms(p, 4, 5); s[2] = ms(p, 3, 6); s[5] = ms(p, 0, 1) + ms(p, 11, 4);
+        s[0] = ms(p, 12, 7) + ms(p, 9, 10); s[1] = ms(p, 4, 5); s[2] = ms(p, 3, 6); s[5] = ms(p, 0, 1) + ms(p, 11, 4);
         if (p->x_first) s[5] = ms(p, 0, 1);      // coordinates, then f_hat: one after the other on the bus
       }
     } else {
