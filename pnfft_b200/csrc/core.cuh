@@ -1718,7 +1718,8 @@ template <class R> struct Core {
     static const bool xf_env = env_flag("PNFFT_B200_X_FIRST", true);
     const bool x_first = xf_env && !no_prefetch && !(cf & (C_OMIT_DECONV | C_OMIT_CONV)) && p->f_hat && !is_device_ptr(p->f_hat) && nd && nd->x &&
                          !is_device_ptr(nd->x) && M > 0 && p->mesh.size == 1 && !(p->pnfft_flags & (F_DIFF_IK | F_INTERLACED)) &&
-                         kernel_family(p) == 2 && (cf & (C_F | C_GRAD_F)) && !(nd->precompute_flags & P_PRE_PSI);
+                         kernel_family(p) == 2 && (cf & (C_F | C_GRAD_F)) && !(nd->precompute_flags & P_PRE_PSI) &&
+                         (double)M * 108.0 * sizeof(R) <= 24.0 * 1073741824.0;   // the two-phase launch builds the whole window table at once
     // ---- f_hat on the device ----
     const C *fh = nullptr;
     if (!(cf & C_OMIT_DECONV)) {
