@@ -4,7 +4,7 @@
 //
 // v3 (zmarch3.cuh) keeps every grid row of a column tile in the registers of the warp that owns it; at m = 8 a tile's
 // footprint is (T + 16)^2 rows x 20 z cells and no longer fits beside the MMA fragments.  v4 keeps the window in SHARED
-// memory instead: a ring of KS + 1 z sub-chunks of the footprint [R0][R1][4] cells, each brought in by ONE TMA box, and a
+// memory instead: a ring of >= KS + 1 z sub-chunks of the footprint [R0][R1][4] cells, each brought in by ONE TMA box, and a
 // warp reads its B fragments from there (one conflict-free LDS.64 per DMMA pair; +4 % issue time in the cost model of
 // profiles/r2_dmma_overlap_ubench.log).  With the window shared, rows have no owner:
 //   * whole node batches (8 nodes, consecutive in the chunk's dx order) go to whichever warp asks next (one ticket counter
@@ -39,7 +39,6 @@ template <int M_> struct Zm4Cfg {
   static constexpr int XLEAD = T0 - 1;
   static constexpr int YLEAD = (R1R - C > T1 - 1) ? R1R - C : T1 - 1;   // a lane reads the y weight of every row of its n-blocks
   static constexpr bool DZS = false;
-  static constexpr int NSLOT = KS + 1;           // window ring: the chunks of one window plus the one being loaded
   static constexpr int NW = 15;                  // consumer warps (+ 1 service warp = 512 threads, 128 registers)
 };
 
@@ -49,7 +48,6 @@ template <int M_> struct Zm4Cfg {
 template <int M_> struct Zm4on2Cfg : Zm2Cfg<M_> {
   typedef Zm2Cfg<M_> B;
   static constexpr int KS = (B::ZS + 2 * M_ + 3) / 4;
-  static constexpr int NSLOT = KS + 1;
   static constexpr int R1C = (B::T1 + 2 * M_ + 3) / 4 * 4, R1R = (B::T1 + 2 * M_ + 7) / 8 * 8;
   static constexpr int NW = 19;                  // consumer warps (+ 1 service warp = 640 threads, 102 registers)
   static_assert(R1R - B::C <= B::YLEAD, "y weights of every footprint row must lie inside the row's y section");
@@ -62,8 +60,13 @@ template <bool CPLX, int M_, class Cfg_ = Zm4Cfg<M_>> struct Zm4Smem {
   static constexpr int R1 = CPLX ? Cfg::R1C : Cfg::R1R;
   static constexpr int NYB = R1 * NCOMP / 8;     // n-blocks per x row
   static constexpr int SLOTB = Cfg::R0 * R1 * Cfg::ZS * CELLB;
-  static constexpr int off_bar = Cfg::NSLOT * SLOTB;
-  static constexpr int gather = off_bar + (2 * Cfg::NSLOT + 2) * 8;
+  // window ring: the chunks of one window plus as many more as shared memory holds (at most 16).  The consumer warps may
+  // be spread over NSLOT - KS + 1 window positions at a time; with few nodes per sub-chunk (uniform node sets: 2-3 batches
+  // per position) that spread is what keeps them busy
+  static constexpr int NSLOT_FIT = (232448 - 1024) / SLOTB;
+  static constexpr int NSLOT = NSLOT_FIT > 16 ? 16 : (NSLOT_FIT < Cfg::KS + 1 ? Cfg::KS + 1 : NSLOT_FIT);
+  static constexpr int off_bar = NSLOT * SLOTB;
+  static constexpr int gather = off_bar + (2 * NSLOT + 2) * 8;
   static_assert(SLOTB % 128 == 0, "alignment");
   static_assert(gather <= 232448, "shared-memory budget of one CTA exceeded");
   // scatter: a CTA owns one y half of the footprint (NYB0 n-blocks of whole rows, the second half may be shorter), one x
@@ -99,7 +102,7 @@ k_gather_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
   typedef Cfg_ Cfg;
   typedef Zm4Smem<CPLX, M_, Cfg_> Sm;
   typedef ZmRowOf<double, Cfg, RG, false, CPLX> Row;
-  constexpr int C = Cfg::C, ZS = Cfg::ZS, KS = Cfg::KS, NW = Cfg::NW, NSLOT = Cfg::NSLOT, SUB = Cfg::SUB;
+  constexpr int C = Cfg::C, ZS = Cfg::ZS, KS = Cfg::KS, NW = Cfg::NW, NSLOT = Sm::NSLOT, SUB = Cfg::SUB;
   constexpr int NCOMP = Sm::NCOMP, CELLB = Sm::CELLB, R1 = Sm::R1, NYB = Sm::NYB, SLOTB = Sm::SLOTB;
   constexpr int NVAL = NCOMP * (GRAD ? 4 : 1), ROWBYTES = Row::ROWBYTES;
   constexpr int NWY = CPLX ? NYB : 2 * NYB;        // y weights a lane needs: one per C-fragment row it holds
