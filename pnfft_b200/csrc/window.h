@@ -148,6 +148,39 @@ template <class R> PNB_HD void bspline_taps(int m, R frac, R n, R *psi, R *dpsi)
   if (k == 1 && dpsi) { dpsi[0] = dpsi[1] = (R)0; }
 }
 
+// The same recursion with the order known at compile time: every loop unrolls, the triangle stays in registers and the
+// level reciprocals are constants (bit-identical to bspline_taps: same operations in the same order).
+template <class R, int M, bool WANT_D> PNB_HD void bspline_taps_fixed(R frac, R n, R (&psi)[2 * M + 1], R (&dpsi)[WANT_D ? 2 * M + 1 : 1]) {
+  constexpr int k = 2 * M;
+  const R v = (R)1 - frac;  // in (0,1]
+  R a[k + 1];
+#pragma unroll
+  for (int j = 0; j <= k; j++) a[j] = (R)0;
+  a[0] = (R)1;
+#pragma unroll
+  for (int q = 2; q <= k; q++) {
+    if (q == k && WANT_D) {
+      dpsi[0] = (R)0;
+#pragma unroll
+      for (int s = 1; s <= k; s++) {
+        const R hi = (s - 1 <= k - 2) ? a[s - 1] : (R)0;
+        const R lo = (s - 2 >= 0) ? a[s - 2] : (R)0;
+        dpsi[s] = n * (lo - hi);
+      }
+    }
+    const R inv = (R)1 / (R)(q - 1);
+#pragma unroll
+    for (int j = q - 1; j >= 0; j--) {
+      const R t = v + (R)j;
+      const R lo = j > 0 ? a[j - 1] : (R)0;
+      a[j] = (t * a[j] + ((R)q - t) * lo) * inv;
+    }
+  }
+  psi[0] = (R)0;
+#pragma unroll
+  for (int s = 1; s <= k; s++) psi[s] = a[s - 1];
+}
+
 // One tap of a point-wise window: y = l - n x (grid units), z = -y.  want_d: also the AD gradient weight.
 // exp(x) for 0 <= x < 700 without the range / special-case handling of the library routine: x = k ln2 + r with
 // |r| <= ln2 / 2 (two-term Cody-Waite), degree-13 Taylor polynomial (truncation < 2^-57), 2^k through the exponent field.

@@ -172,6 +172,8 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab, int first) {
         psi[s] = (R)a;
         if (GRAD) dpsi[s] = (R)b;
       }
+    } else if (g.kind == WIN_BSPLINE) {
+      bspline_taps_fixed<R, M_, GRAD>(fr, g.n[t], psi, dpsi);      // de Boor triangle in registers
     } else if (sizeof(R) == 8 && g.kind == WIN_GAUSSIAN && !g.fast_gauss) {
       // Gaussian taps in double (window.h: window_tap) with the branch-free exponential of the Kaiser-Bessel path and one
       // division per thread instead of two per tap: psi = exp(-y^2 / b) / sqrt(pi b), dpsi = 2 n / b * y * psi
