@@ -174,6 +174,18 @@ k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab, int first) {
       }
     } else if (g.kind == WIN_BSPLINE) {
       bspline_taps_fixed<R, M_, GRAD>(fr, g.n[t], psi, dpsi);      // de Boor triangle in registers
+    } else if (g.kind == WIN_GAUSSIAN && g.fast_gauss) {
+      // PNFFT_FAST_GAUSSIAN (reference ndft-parallel.c:1790-1822): two exponentials per axis, the taps by recurrence
+      const R d = nxv - (flv - (R)M_);
+      const R e_sqr = m_exp(-(d * d) / g.b[t]), e_lin = m_exp((R)2 * d / g.b[t]);
+      R tmp = e_sqr;
+#pragma unroll
+      for (int s = 0; s < C; s++) {
+        const R v = tmp * g.exp_const[t * C + s];
+        psi[s] = v;
+        if (GRAD) dpsi[s] = (R)(-2.0) * g.n[t] / g.b[t] * (d - (R)s) * v;
+        tmp *= e_lin;
+      }
     } else if (sizeof(R) == 8 && g.kind == WIN_GAUSSIAN && !g.fast_gauss) {
       // Gaussian taps in double (window.h: window_tap) with the branch-free exponential of the Kaiser-Bessel path and one
       // division per thread instead of two per tap: psi = exp(-y^2 / b) / sqrt(pi b), dpsi = 2 n / b * y * psi
