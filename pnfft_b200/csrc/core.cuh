@@ -1376,16 +1376,15 @@ template <class R> struct Core {
         k_pack_vals<CPLX, GRAD><<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(na, nd->d_vals);
         p->launches++;
       }
-      const int flavor = zm4_rows<CPLX, M_, GRAD>(p, nd, na);
-      if (p->b_phase & 2) {
-        const unsigned nblk = (unsigned)(ncol * zg.nseg);
+      // kernels of one launch: all columns, or one column batch with its own piece of the table
+      auto run = [&](const Zm2Geom &zgk, unsigned nblk, const R *tab, int flavor) {
         if (!scatter) {
           const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::R0, Sm::R1, Cfg::ZS, 0);
           GatherOut<R> out;
           out.perm = na.perm; out.f = na.f; out.f_stride = na.f_stride; out.f_off = na.f_off; out.grad = na.grad; out.accumulate = na.accumulate;
           auto go = [&](auto kern) {
             PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::gather));
-            kern<<<nblk, (Cfg::NW + 1) * 32, Sm::gather, p->stream>>>(tm, zg, nd->d_rows, nd->d_tile_start, out);
+            kern<<<nblk, (Cfg::NW + 1) * 32, Sm::gather, p->stream>>>(tm, zgk, tab, nd->d_tile_start, out);
             p->launches++;
           };
           if (flavor) go(k_gather_mma4<CPLX, M_, GRAD, true>);
@@ -1394,11 +1393,49 @@ template <class R> struct Core {
           const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, 1, Sm::RH, Cfg::ZS, 0);
           auto go = [&](auto kern, int smem) {
             PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            kern<<<2 * nblk, (Sm::NCW + 1) * 32, (size_t)smem, p->stream>>>(tm, zg, nd->d_rows, nd->d_vals, nd->d_tile_start);
+            kern<<<2 * nblk, (Sm::NCW + 1) * 32, (size_t)smem, p->stream>>>(tm, zgk, tab, nd->d_vals, nd->d_tile_start);
             p->launches++;
           };
           if (flavor) go(k_scatter_mma4<CPLX, M_, GRAD, true>, Sm::template Scat<GRAD, true>::bytes);
           else if constexpr (!GRAD) go(k_scatter_mma4<CPLX, M_, false, false>, Sm::template Scat<false, false>::bytes);
+        }
+      };
+      const size_t rowlen = ZmRowOf<R, Cfg, GRAD, false, CPLX>::ROWLEN;
+      static const double cap_gb = getenv("PNFFT_B200_TABLE_GB") ? atof(getenv("PNFFT_B200_TABLE_GB")) : 24.0;
+      const double need_gb = (double)na.M * rowlen * sizeof(R) / 1073741824.0;
+      const bool cached = nd->binned && nd->rows_plan == (const void *)p && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
+      if (need_gb <= cap_gb || p->b_phase != 3 || cached) {
+        const int flavor = zm4_rows<CPLX, M_, GRAD>(p, nd, na);
+        if (p->b_phase & 2) run(zg, (unsigned)(ncol * zg.nseg), nd->d_rows, flavor);
+      } else {
+        // the table would not fit the budget: built and consumed in column batches, nothing kept (as launch_zm3)
+        const GridGeom<R> g = geom(p);
+        const int nbatch = std::min(ncol, (int)std::ceil(2.0 * need_gb / cap_gb));
+        std::vector<int> cb((size_t)nbatch + 1), nb((size_t)nbatch + 1);
+        for (int k = 0; k <= nbatch; k++) cb[(size_t)k] = (int)((long long)ncol * k / nbatch);
+        nb[0] = 0; nb[(size_t)nbatch] = na.M;
+        const size_t per_col = (size_t)tg.nt[2] * Cfg::SUB;
+        for (int k = 1; k < nbatch; k++)
+          PNB_CUDA(cudaMemcpyAsync(&nb[(size_t)k], nd->d_tile_start + (size_t)cb[(size_t)k] * per_col, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        PNB_CUDA(cudaStreamSynchronize(p->stream));
+        size_t max_rows = 0;
+        for (int k = 0; k < nbatch; k++) max_rows = std::max(max_rows, (size_t)(nb[(size_t)k + 1] - nb[(size_t)k]));
+        ensure(&nd->d_wtab, &nd->cap_wtab, max_rows * rowlen + 64);
+        const size_t psm = g.poly ? sizeof(R) * (size_t)2 * (g.poly_deg + 1) * 3 * Cfg::C : 0;
+        for (int k = 0; k < nbatch; k++) {
+          const int first = nb[(size_t)k], last = nb[(size_t)k + 1];
+          if (last <= first) continue;
+          NodeArgs<R> nb_args = na;
+          nb_args.M = last;
+          R *tab = nd->d_wtab - (size_t)first * rowlen;        // rows are addressed by their absolute sorted position
+          Zm2Geom zgk = zg;
+          zgk.col0 = cb[(size_t)k];
+          auto kt = k_node_table2<R, M_, GRAD, false, CPLX, Cfg>;
+          const size_t tsm = (size_t)kZm2TabNodes * ZmRowOf<R, Cfg, GRAD, false, CPLX>::ROWBYTES + psm;
+          PNB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+          kt<<<(unsigned)((last - first + kZm2TabNodes - 1) / kZm2TabNodes), 3 * kZm2TabNodes, tsm, p->stream>>>(g, nb_args, tab, first);
+          p->launches++;
+          run(zgk, (unsigned)((cb[(size_t)k + 1] - cb[(size_t)k]) * zg.nseg), tab, GRAD ? 1 : 0);
         }
       }
       PNB_CUDA(cudaGetLastError());

@@ -143,6 +143,25 @@ def test_hessian_only_and_accumulated():
     run.close()
 
 
+@pytest.mark.parametrize("m", [6, 8])
+def test_table_in_column_batches(m, tmp_path):
+    """PNFFT_B200_TABLE_GB: above the budget the window rows are built and consumed in column batches (BASELINE config 5 needs
+    it at 2^27 nodes).  A budget of 1 MB forces a dozen batches on 30000 nodes; the results must not change.  The switch is
+    read once per process, hence the two subprocesses."""
+    import subprocess, sys
+    res = []
+    for gb in (None, "0.001"):
+        env = dict(os.environ)
+        if gb:
+            env["PNFFT_B200_TABLE_GB"] = gb
+        out = str(tmp_path / ("r_%s.npz" % (gb or "all")))
+        subprocess.run([sys.executable, os.path.join(os.path.dirname(GOLD), os.pardir, "tools", "run_small_case.py"), out, str(m), "0"],
+                       env=env, check=True, timeout=300)
+        res.append(np.load(out))
+    for k in ("f", "g", "fh"):
+        assert rel_l2(res[1][k], res[0][k]) <= 1e-14
+
+
 @pytest.mark.parametrize("c2r", [False, True])
 @pytest.mark.parametrize("m", [5, 7, 8])
 def test_family3_shared_window_gather(ref, m, c2r):
