@@ -1112,25 +1112,8 @@ template <class R> struct Core {
       const GridGeom<R> g = geom(p);
       typedef typename CellT<R, CPLX>::type Cell;
       const CUtensorMap tm = make_grid_tmap<R>(p->d_grid, p->L, CPLX ? 2 : 1, Cfg::XW, 16, Cfg::ZB, zm2_swizzle_mode<Cell, Cfg::ZB>());
-      Zm2Geom zg;
-      zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2];
-      // whole columns per work item when there are enough columns to fill the GPU, else split along z
+      Zm2Geom zg = zm2_work_items(p, tg, nd, na.M);
       const int ncol = tg.nt[0] * tg.nt[1];
-      int nseg = 1;
-      while (ncol * nseg < 8 * 148 && nseg * 2 <= tg.nt[2]) nseg *= 2;
-      // clustered node sets put most nodes into few columns: splitting every column along z gives the scheduler
-      // smaller work items to balance (each segment pays one window prologue / epilogue)
-      // (measured, C4-like Gaussian blob sigma = 0.05: -25 % with 4 segments; uniform nodes: +2 %, so only on a hint)
-      static const int nseg_env = getenv("PNFFT_B200_NSEG") ? atoi(getenv("PNFFT_B200_NSEG")) : 0;
-      int nseg_min = nseg_env;
-      if (!nseg_env && nd->h_maxcol) {
-        const long long maxcol = *(volatile int *)nd->h_maxcol;      // from the previous binning of this node set
-        if (maxcol * ncol > 4LL * na.M) nseg_min = 4;
-        if (maxcol * ncol > 32LL * na.M) nseg_min = 8;
-      }
-      while (nseg < nseg_min && nseg * 2 <= tg.nt[2]) nseg *= 2;
-      zg.zseg = (tg.nt[2] + nseg - 1) / nseg;
-      zg.nseg = (tg.nt[2] + zg.zseg - 1) / zg.zseg;
       const size_t psm = g.poly ? sizeof(R) * (size_t)2 * (g.poly_deg + 1) * 3 * Cfg::C : 0;
       typedef typename Sm::RowG RowG;
       typedef typename Sm::RowS RowS;
@@ -1195,22 +1178,35 @@ template <class R> struct Core {
 
   // work items of the family-2 geometry: whole columns when there are enough of them to fill the GPU, else split along z;
   // clustered node sets (hint from the previous binning) get smaller items
-  static Zm2Geom zm2_work_items(const TileGeom &tg, const Nd *nd, int M) {
+  static Zm2Geom zm2_work_items(const P *p, const TileGeom &tg, const Nd *nd, int M) {
     Zm2Geom zg;
     zg.nc[0] = tg.nt[0]; zg.nc[1] = tg.nt[1]; zg.nt2 = tg.nt[2]; zg.col0 = 0;
     const int ncol = tg.nt[0] * tg.nt[1];
+    // a column is cut into items of about `target` nodes (zm_segment): a quarter of an SM's share of the node set
+    zg.target = std::max(256, M / (148 * 4));
+    const int target_nodes = zg.target;
     int nseg = 1;
     while (ncol * nseg < 8 * 148 && nseg * 2 <= tg.nt[2]) nseg *= 2;
+    zg.fill = nseg;                          // whole columns per item when there are enough of them to fill the GPU
     static const int nseg_env = getenv("PNFFT_B200_NSEG") ? atoi(getenv("PNFFT_B200_NSEG")) : 0;
     int nseg_min = nseg_env;
     if (!nseg_env && nd->h_maxcol) {
-      const long long maxcol = *(volatile int *)nd->h_maxcol;      // from the previous binning of this node set
-      if (maxcol * ncol > 4LL * M) nseg_min = 4;
-      if (maxcol * ncol > 32LL * M) nseg_min = 8;
+      // clustered node sets put most nodes into few columns (hint: the largest column of the previous binning)
+      const long long maxcol = *(volatile int *)nd->h_maxcol;
+      nseg_min = 1;
+      while (nseg_min < 32 && (long long)nseg_min * target_nodes < maxcol) nseg_min *= 2;
     }
     while (nseg < nseg_min && nseg * 2 <= tg.nt[2]) nseg *= 2;
+    if (nseg_env) zg.fill = nseg;            // a forced count splits every column
+    // Pieces of equal node count only where the heaviest item bounds the launch: a rank of a multi-GPU plan that holds a
+    // part of a cluster in few columns (C4 on 2x4 GPUs: 28.4 -> 22.4 ms per step).  On one GPU (C4: 16384 columns) pieces of
+    // equal LENGTH measured 9 % faster (light columns in several concurrent items make up for the few batches per window
+    // position), and uniform node sets have nothing to balance.  PNFFT_B200_SEG_BALANCE=0 / 1 forces the choice.
+    static const int bal_env = getenv("PNFFT_B200_SEG_BALANCE") ? atoi(getenv("PNFFT_B200_SEG_BALANCE")) : -1;
+    const bool balance = bal_env >= 0 ? bal_env != 0 : (p->mesh.size > 1 && nseg_min > 1 && !nseg_env);
+    if (!balance) zg.target = 0;
     zg.zseg = (tg.nt[2] + nseg - 1) / nseg;
-    zg.nseg = (tg.nt[2] + zg.zseg - 1) / zg.zseg;
+    zg.nseg = nseg;
     return zg;
   }
 
@@ -1267,7 +1263,7 @@ template <class R> struct Core {
       typedef Zm2Cfg<M_> Cfg;
       const TileGeom tg = tile_geom(p, nullptr);
       const GridGeom<R> g = geom(p);
-      Zm2Geom zg = zm2_work_items(tg, nd, na.M);
+      Zm2Geom zg = zm2_work_items(p, tg, nd, na.M);
       const int ncol = tg.nt[0] * tg.nt[1];
       if (scatter && (p->b_phase & 2)) {       // node values in sorted order
         constexpr int NVP = Zm3Smem<CPLX, M_, GRAD, GRAD>::NVP;
@@ -1367,7 +1363,7 @@ template <class R> struct Core {
       typedef Zm4Cfg<M_> Cfg;
       typedef Zm4Smem<CPLX, M_> Sm;
       const TileGeom tg = tile_geom(p, nullptr);
-      const Zm2Geom zg = zm2_work_items(tg, nd, na.M);
+      const Zm2Geom zg = zm2_work_items(p, tg, nd, na.M);
       const int ncol = tg.nt[0] * tg.nt[1];
       if (scatter && (p->b_phase & 2)) {       // node values in sorted order
         constexpr int NVP = Sm::template Scat<GRAD, GRAD>::NVP;

@@ -72,7 +72,40 @@ struct Zm2Geom {
   int zseg;        // sub-chunks per work item
   int nseg;        // work items per column
   int col0;        // first column of this launch (the node table may be built and consumed in column batches)
+  int target;      // nodes per work item a heavy column is cut into (zm_segment)
+  int fill;        // pieces every column is cut into regardless (few columns: fills the GPU)
 };
+
+// Work items of a column: up to nseg pieces along z with (nearly) equal NODE counts, cut at sub-chunk boundaries found in
+// the column's bin prefix; a column is split into as many pieces as it has multiples of `target` nodes (at least `fill`), so light
+// columns stay whole (every piece pays a window prologue) and the items of a heavy column weigh about `target` each.  Equal-length
+// pieces leave half of a clustered column (a Gaussian blob along z) in one item, and the heaviest item bounds the launch
+// once the node set is spread over several GPUs (C4 on 8 GPUs).  Items beyond the column's piece count are empty.
+__device__ __forceinline__ void zm_segment(const int *__restrict__ bs, int nt2, int sub, int seg, int nseg, int target, int fill, int &tz0, int &tz1) {
+  if (nseg <= 1) { tz0 = 0; tz1 = nt2; return; }
+  if (target <= 0) {            // pieces of equal length
+    const int zseg = (nt2 + nseg - 1) / nseg;
+    tz0 = min(nt2, seg * zseg); tz1 = min(nt2, tz0 + zseg);
+    return;
+  }
+  const int s0 = bs[0];
+  const long long total = bs[(size_t)nt2 * sub] - s0;
+  const int pieces = (int)min((long long)nseg, max((long long)max(fill, 1), (total + target - 1) / max(target, 1)));
+  auto cut = [&](int k) -> int {      // smallest sub-chunk t with at least total * k / pieces nodes in front of it
+    if (k <= 0) return 0;
+    if (k >= pieces) return nt2;
+    const long long goal = total * k / pieces;
+    int lo = 0, hi = nt2;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((long long)(bs[(size_t)mid * sub] - s0) >= goal) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
+  if (seg >= pieces) { tz0 = 0; tz1 = 0; return; }
+  tz0 = cut(seg);
+  tz1 = cut(seg + 1);
+}
 
 // Node-table row (units of R).  hdr = 8 ints {-dx*sizeof(R), -dy*sizeof(R), dz, dx, node index j, 0, 0, 0};
 // X = [0 x XLEAD, psi_x[0..C), 0 x XLEAD...], Y = [0 x (T1-1), psi_y[0..C), 0 x (T1-1)...], Z = psi_z[0..C) zero padded to ZP
@@ -106,7 +139,9 @@ constexpr int kZm2TabNodes = ZM2_TABNODES;     // nodes per block of the table k
 // node table: one thread per (node, axis); rows assembled in shared memory, written out coalesced
 // ------------------------------------------------------------------------------------------------
 template <class R, int M_, bool GRAD, bool VALS, bool CPLX, class Cfg_ = Zm2Cfg<M_>>
-__global__ void __launch_bounds__(3 * kZm2TabNodes)
+// (four blocks per SM is what shared memory allows for v3's rows; without the bound the register-resident B-spline /
+// fast-Gaussian branches raise the kernel to 96 registers and cost every window a block of occupancy)
+__global__ void __launch_bounds__(3 * kZm2TabNodes, 4)
 k_node_table2(GridGeom<R> g, NodeArgs<R> na, R *__restrict__ tab, int first) {
   typedef Cfg_ Cfg;
   typedef ZmRowOf<R, Cfg_, GRAD, VALS, CPLX> Row;
@@ -471,8 +506,9 @@ k_scatter_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__r
   unsigned long long *empty = full + S;
 
   const int colr = blockIdx.x / zg.nseg, seg = blockIdx.x - colr * zg.nseg, col = zg.col0 + colr;
-  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
   const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
+  int tz0, tz1;
+  zm_segment(bs, zg.nt2, Cfg::SUB, seg, zg.nseg, zg.target, zg.fill, tz0, tz1);
   if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;            // no nodes in this work item
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -752,8 +788,9 @@ k_gather_zm2(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const R *__re
   unsigned long long *wbar = pempty + P;
 
   const int colr = blockIdx.x / zg.nseg, seg = blockIdx.x - colr * zg.nseg, col = zg.col0 + colr;
-  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
   const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
+  int tz0, tz1;
+  zm_segment(bs, zg.nt2, Cfg::SUB, seg, zg.nseg, zg.target, zg.fill, tz0, tz1);
   if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 

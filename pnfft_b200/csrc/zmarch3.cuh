@@ -135,8 +135,9 @@ k_gather_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double 
   unsigned long long *wbar = pempty + P;
 
   const int colr = blockIdx.x / zg.nseg, seg = blockIdx.x - colr * zg.nseg, col = zg.col0 + colr;
-  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
   const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
+  int tz0, tz1;
+  zm_segment(bs, zg.nt2, Cfg::SUB, seg, zg.nseg, zg.target, zg.fill, tz0, tz1);
   if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -470,8 +471,9 @@ k_scatter_mma(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
   unsigned long long *empty = full + S;
 
   const int colr = blockIdx.x / zg.nseg, seg = blockIdx.x - colr * zg.nseg, col = zg.col0 + colr;
-  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
   const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
+  int tz0, tz1;
+  zm_segment(bs, zg.nt2, Cfg::SUB, seg, zg.nseg, zg.target, zg.fill, tz0, tz1);
   if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;            // no nodes in this work item
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 

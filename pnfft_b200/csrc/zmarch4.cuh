@@ -115,8 +115,9 @@ k_gather_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const double
   int *ticket = reinterpret_cast<int *>(wempty + NSLOT);
 
   const int colr = blockIdx.x / zg.nseg, seg = blockIdx.x - colr * zg.nseg, col = zg.col0 + colr;
-  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
   const int *bs = bin_start + (size_t)col * zg.nt2 * SUB;
+  int tz0, tz1;
+  zm_segment(bs, zg.nt2, SUB, seg, zg.nseg, zg.target, zg.fill, tz0, tz1);
   if (bs[(size_t)tz0 * SUB] == bs[(size_t)tz1 * SUB]) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cx = col / zg.nc[1], cy = col - cx * zg.nc[1];
@@ -521,8 +522,9 @@ k_scatter_mma4(const __grid_constant__ CUtensorMap tmap, Zm2Geom zg, const doubl
 
   const int yh = blockIdx.x & 1, item = blockIdx.x >> 1;
   const int colr = item / zg.nseg, seg = item - colr * zg.nseg, col = zg.col0 + colr;
-  const int tz0 = seg * zg.zseg, tz1 = min(zg.nt2, tz0 + zg.zseg);
   const int *bs = bin_start + (size_t)col * zg.nt2 * Cfg::SUB;
+  int tz0, tz1;
+  zm_segment(bs, zg.nt2, Cfg::SUB, seg, zg.nseg, zg.target, zg.fill, tz0, tz1);
   if (bs[(size_t)tz0 * Cfg::SUB] == bs[(size_t)tz1 * Cfg::SUB]) return;            // no nodes in this work item
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
