@@ -197,6 +197,9 @@ typedef float pnfftf_complex[2];
   /* host-only self check of the pencil FFT's composed "own chunk" maps for rank (c0, c1) of a p0 x p1 \
    * mesh: self transfers checked, -1 on a mismatch, -2 if one did not compose (no GPU needed) */       \
   int PNX(b200_check_self_maps)(const ptrdiff_t *N, const ptrdiff_t *n, int m, int p0, int p1, int c0, int c1, int c2r); \
+  /* host-only: the z range [tz0, tz1) of work item `seg` of a column whose bins (nt2 sub-chunks x sub x-offset bins, prefix \
+   * sums `prefix[nt2 * sub + 1]`) are cut into up to nseg pieces as the gridding kernels do (target <= 0: equal length) */  \
+  void PNX(b200_column_piece)(const int *prefix, int nt2, int sub, int seg, int nseg, int target, int fill, int *tz0, int *tz1); \
   /* the plan's cudaStream_t (all work of trafo/adj is issued on it; calls synchronise it on return) */ \
   void *PNX(b200_get_stream)(PNX(plan) ths);
 

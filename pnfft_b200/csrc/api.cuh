@@ -500,6 +500,13 @@ void PNX(b200_kb_taps_host)(const double *x, INT M, const INT *n, const double *
 // every re-distribution stage is emulated on index arrays, once through pack -> chunk -> unpack and once through the
 // composed map, forward and backward.  Returns the number of self transfers checked, -1 on a mismatch, -2 if a self
 // transfer did not compose.  Needs no GPU (tests/test_abi.py).
+// Host evaluation of the work-item cutter of the gridding kernels (zmarch2.cuh: zm_segment), for the CPU test suite.
+void PNX(b200_column_piece)(const int *prefix, int nt2, int sub, int seg, int nseg, int target, int fill, int *tz0, int *tz1) {
+  int a = 0, b = 0;
+  pnb::zm_segment(prefix, nt2, sub, seg, nseg, target, fill, a, b);
+  *tz0 = a; *tz1 = b;
+}
+
 int PNX(b200_check_self_maps)(const INT *N, const INT *n, int m, int p0, int p1, int c0, int c1, int c2r) {
   pnb::Mesh M;
   M.np[0] = p0; M.np[1] = p1; M.co[0] = c0; M.co[1] = c1; M.size = p0 * p1; M.rank = M.rank_of(c0, c1);

@@ -81,16 +81,18 @@ struct Zm2Geom {
 // columns stay whole (every piece pays a window prologue) and the items of a heavy column weigh about `target` each.  Equal-length
 // pieces leave half of a clustered column (a Gaussian blob along z) in one item, and the heaviest item bounds the launch
 // once the node set is spread over several GPUs (C4 on 8 GPUs).  Items beyond the column's piece count are empty.
-__device__ __forceinline__ void zm_segment(const int *__restrict__ bs, int nt2, int sub, int seg, int nseg, int target, int fill, int &tz0, int &tz1) {
+__host__ __device__ __forceinline__ void zm_segment(const int *__restrict__ bs, int nt2, int sub, int seg, int nseg, int target, int fill, int &tz0, int &tz1) {
   if (nseg <= 1) { tz0 = 0; tz1 = nt2; return; }
   if (target <= 0) {            // pieces of equal length
     const int zseg = (nt2 + nseg - 1) / nseg;
-    tz0 = min(nt2, seg * zseg); tz1 = min(nt2, tz0 + zseg);
+    tz0 = seg * zseg < nt2 ? seg * zseg : nt2; tz1 = tz0 + zseg < nt2 ? tz0 + zseg : nt2;
     return;
   }
   const int s0 = bs[0];
   const long long total = bs[(size_t)nt2 * sub] - s0;
-  const int pieces = (int)min((long long)nseg, max((long long)max(fill, 1), (total + target - 1) / max(target, 1)));
+  long long want = (total + target - 1) / (target > 0 ? target : 1);
+  if (want < (fill > 1 ? fill : 1)) want = fill > 1 ? fill : 1;
+  const int pieces = (int)(want < nseg ? want : nseg);
   auto cut = [&](int k) -> int {      // smallest sub-chunk t with at least total * k / pieces nodes in front of it
     if (k <= 0) return 0;
     if (k >= pieces) return nt2;

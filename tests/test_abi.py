@@ -114,3 +114,50 @@ def test_fft_self_maps_equal_pack_unpack(N, n, m, mesh, c2r):
             assert r >= 0, "rank (%d,%d): %s" % (c0, c1, "mismatch" if r == -1 else "self transfer did not compose")
             total += r
     assert total > 0
+
+
+@pytest.mark.parametrize("target", [0, 40, 400])
+@pytest.mark.parametrize("dist", ["uniform", "blob", "empty", "one_chunk"])
+def test_column_pieces_partition_the_column(dist, target):
+    """Work items of a grid column (csrc/zmarch2.cuh: zm_segment, host-only probe): the pieces of every column are disjoint,
+    in order and cover all its nodes; with a node target the pieces of a heavy column weigh about the same (one sub-chunk
+    is the granule), a light column stays whole unless `fill` asks otherwise, and items beyond the piece count are empty."""
+    fn = A.lib().pnfft_b200_column_piece
+    fn.restype = None
+    fn.argtypes = [C.POINTER(C.c_int)] + [C.c_int] * 6 + [C.POINTER(C.c_int)] * 2
+    rng = np.random.default_rng(9)
+    nt2, sub = 37, 8
+    if dist == "uniform":
+        cnt = rng.integers(0, 6, nt2 * sub)
+    elif dist == "blob":
+        z = np.arange(nt2)[:, None]
+        cnt = rng.poisson(60.0 * np.exp(-0.5 * ((z - 17.3) / 2.5) ** 2) * np.ones((1, sub))).ravel()
+    elif dist == "empty":
+        cnt = np.zeros(nt2 * sub, int)
+    else:
+        cnt = np.zeros(nt2 * sub, int); cnt[5 * sub + 3] = 1000
+    prefix = np.concatenate([[123], 123 + np.cumsum(cnt)]).astype(np.int32)     # a column in the middle of the table
+    total = int(cnt.sum())
+    per_chunk = cnt.reshape(nt2, sub).sum(1)
+    pv = prefix.ctypes.data_as(C.POINTER(C.c_int))
+    for nseg, fill in [(1, 1), (4, 1), (4, 4), (32, 2)]:
+        pieces, prev_end = [], 0
+        for seg in range(nseg):
+            a, b = C.c_int(-1), C.c_int(-1)
+            fn(pv, nt2, sub, seg, nseg, target, fill, C.byref(a), C.byref(b))
+            a, b = a.value, b.value
+            assert 0 <= a <= b <= nt2
+            n_in = int(per_chunk[a:b].sum())
+            if n_in:
+                assert a >= prev_end, "pieces overlap"
+                assert int(per_chunk[prev_end:a].sum()) == 0, "nodes between two pieces"
+                prev_end = b
+                pieces.append(n_in)
+        assert sum(pieces) == total
+        if target > 0 and nseg > 1 and total:
+            want = min(nseg, max(fill, -(-total // target)))
+            assert len(pieces) <= want
+            if want > 1 and dist == "blob":
+                assert max(pieces) <= total / want + per_chunk.max()       # equal counts up to one sub-chunk
+            if want == 1:
+                assert pieces == [total]                                   # a light column stays whole
