@@ -203,11 +203,11 @@ void PNX(zero_f_hat)(PNX(plan) ths) {
 
 RT PNX(inv_phi_hat)(const PNX(plan) ths, int dim, INT k) {
   const PlanT *p = AS_PLAN(ths);
-  return pnb::phi_hat_any<RT>(p->kind, (long)k, (long)p->L.n[dim], p->b[dim], p->L.m, true);
+  return pnb::phi_hat_any<RT>(pnb::window_hat_kind(p->pnfft_flags), (long)k, (long)p->L.n[dim], p->b[dim], p->L.m, true);
 }
 RT PNX(phi_hat)(const PNX(plan) ths, int dim, INT k) {
   const PlanT *p = AS_PLAN(ths);
-  return pnb::phi_hat_any<RT>(p->kind, (long)k, (long)p->L.n[dim], p->b[dim], p->L.m, false);
+  return pnb::phi_hat_any<RT>(pnb::window_hat_kind(p->pnfft_flags), (long)k, (long)p->L.n[dim], p->b[dim], p->L.m, false);
 }
 // psi(x), dpsi(x): window at offset x (reference kernel/ndft-parallel.c:2288-2316)
 RT PNX(psi)(const PNX(plan) ths, int dim, RT x) {
@@ -495,6 +495,14 @@ void PNX(b200_kb_taps_host)(const double *x, INT M, const INT *n, const double *
         if (dpsi) dpsi[((size_t)j * 3 + t) * c + s] = d;
       }
     }
+}
+// Host evaluation of the window's Fourier coefficients exactly as the D tables (Core::upload_window_tables) and
+// pnfft_phi_hat / pnfft_inv_phi_hat compute them: out[i] = phi_hat(k[i]) (inverse = 0) or 1 / phi_hat(k[i]) for the window
+// the plan flags select, oversampled size n, shape parameter b (<= 0: the default of that window at sigma = n / N).
+void PNX(b200_phi_hat_host)(unsigned pnfft_flags, INT N, INT n, RT b, int m, const INT *k, INT len, int inverse, RT *out) {
+  const int kind = pnb::window_kind(pnfft_flags), hat = pnb::window_hat_kind(pnfft_flags);
+  const RT bb = b > 0 ? b : pnb::window_shape<RT>(kind, m, (RT)n / (RT)N);
+  for (INT i = 0; i < len; i++) out[i] = pnb::phi_hat_any<RT>(hat, (long)k[i], (long)n, bb, m, inverse != 0);
 }
 // Host-only check of the pencil FFT's composed self maps (fftpipe.cuh: compose_self_map) for one rank of a p0 x p1 mesh:
 // every re-distribution stage is emulated on index arrays, once through pack -> chunk -> unpack and once through the

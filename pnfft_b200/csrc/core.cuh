@@ -46,6 +46,13 @@ inline int window_kind(unsigned flags) {
   return WIN_KAISER_BESSEL;
 }
 
+// window kind of the Fourier coefficients (D matrix, pnfft_phi_hat / pnfft_inv_phi_hat): PNFFT_WINDOW_GAUSSIAN_T keeps the
+// Gaussian psi and takes the coefficients of its truncation (reference kernel/matrix_D.c:195-217)
+inline int window_hat_kind(unsigned flags) {
+  const int kind = window_kind(flags);
+  return (kind == WIN_GAUSSIAN && (flags & F_USE_FK_GAUSSIAN_T)) ? WIN_GAUSSIAN_T : kind;
+}
+
 inline bool get_mesh(MPI_Comm comm, Mesh &M) {
   int nd = 0, dims[3] = {1, 1, 1}, periods[3], coords[3] = {0, 0, 0};
   if (MPI_Comm_rank(comm, &M.rank) != MPI_SUCCESS) return false;
@@ -183,7 +190,7 @@ template <class R> struct Core {
       const INT len = L.local_N[t];
       std::vector<R> h((size_t)(len > 0 ? len : 1));
       for (INT i = 0; i < len; i++)
-        h[(size_t)i] = phi_hat_any<R>(p->kind, (long)(L.local_N_start[t] + i), (long)L.n[t], p->b[t], L.m, true);
+        h[(size_t)i] = phi_hat_any<R>(window_hat_kind(p->pnfft_flags), (long)(L.local_N_start[t] + i), (long)L.n[t], p->b[t], L.m, true);
       if (!p->d_invphi[t]) PNB_CUDA(cudaMalloc(&p->d_invphi[t], sizeof(R) * h.size()));
       PNB_CUDA(cudaMemcpy(p->d_invphi[t], h.data(), sizeof(R) * h.size(), cudaMemcpyHostToDevice));
     }
@@ -328,11 +335,6 @@ template <class R> struct Core {
       if (n[t] < N[t]) { fprintf(stderr, "pnfft-b200: n < N\n"); return nullptr; }
     }
     if (m < 1 || m > kMaxM) { fprintf(stderr, "pnfft-b200: window cutoff m must be in [1,%d]\n", kMaxM); return nullptr; }
-    if ((pnfft_flags & F_USE_FK_GAUSSIAN_T) && (pnfft_flags & F_WIN_GAUSSIAN)) {
-      // the truncated-Gaussian Fourier coefficients need the complex error function (reference kernel/matrix_D.c:195-217, cerf/)
-      fprintf(stderr, "pnfft-b200: PNFFT_WINDOW_GAUSSIAN_T (truncated-Gaussian phi_hat) is not supported; use PNFFT_WINDOW_GAUSSIAN\n");
-      return nullptr;
-    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
       fprintf(stderr, "pnfft-b200: no CUDA device -- this library has no CPU path\n");

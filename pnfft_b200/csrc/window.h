@@ -15,7 +15,10 @@
 
 namespace pnb {
 
-enum WindowKind { WIN_KAISER_BESSEL = 0, WIN_GAUSSIAN = 1, WIN_BSPLINE = 2, WIN_SINC_POWER = 3, WIN_BESSEL_I0 = 4 };
+enum WindowKind { WIN_KAISER_BESSEL = 0, WIN_GAUSSIAN = 1, WIN_BSPLINE = 2, WIN_SINC_POWER = 3, WIN_BESSEL_I0 = 4,
+                  // Fourier coefficients only (phi_hat_any): the Gaussian window with the coefficients of its truncation to
+                  // [-m/n, m/n] (PNFFT_WINDOW_GAUSSIAN_T); psi itself is WIN_GAUSSIAN
+                  WIN_GAUSSIAN_T = 5 };
 
 constexpr int kMaxM = 16;               // 2m+1 <= 33 taps per axis
 constexpr int kMaxCutoff = 2 * kMaxM + 1;
@@ -388,12 +391,70 @@ template <class R> PNB_HD R window_ddtap(int kind, R y, R n, R b, int m, R psi, 
 }
 
 // ---- Fourier coefficients of the window (host only in practice: 3 tables per plan) ----
+// Re erf(a + i c) for real a, c -- the factor that turns the Gaussian's Fourier coefficient into the one of the Gaussian
+// truncated at the cutoff (reference kernel/matrix_D.c:37-65, which calls libcerf's cerf).  Own evaluation: along the
+// vertical path t = a + i s,  erf(a + i c) = erf(a) + 2/sqrt(pi) * Int_0^c exp(s^2 - a^2) (sin(2 a s) + i cos(2 a s)) ds,
+// the real part integrated by composite 32-point Gauss-Legendre in long double (the integrand is entire; panels of at
+// most 0.5 in s and 8 rad in phase).  Even in c.
+inline const long double *gauss_legendre_32(bool weights) {
+  static long double xs[32], ws[32];
+  static const bool ready = [] {
+    const int n = 32;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int i = 0; i < n; i++) {
+      long double x = cosl(pi * ((long double)i + 0.75L) / ((long double)n + 0.5L)), dp = 1.0L;
+      for (int it = 0; it < 100; it++) {
+        long double p0 = 1.0L, p1 = x;                     // Legendre recurrence up to P_n(x)
+        for (int k = 2; k <= n; k++) { const long double pk = (((long double)(2 * k - 1)) * x * p1 - ((long double)(k - 1)) * p0) / (long double)k; p0 = p1; p1 = pk; }
+        dp = (long double)n * (x * p1 - p0) / (x * x - 1.0L);
+        const long double dx = p1 / dp;
+        x -= dx;
+        if (fabsl(dx) < 1e-19L) break;
+      }
+      {
+        long double p0 = 1.0L, p1 = x;
+        for (int k = 2; k <= n; k++) { const long double pk = (((long double)(2 * k - 1)) * x * p1 - ((long double)(k - 1)) * p0) / (long double)k; p0 = p1; p1 = pk; }
+        dp = (long double)n * (x * p1 - p0) / (x * x - 1.0L);
+      }
+      xs[i] = x;
+      ws[i] = 2.0L / ((1.0L - x * x) * dp * dp);
+    }
+    return true;
+  }();
+  (void)ready;
+  return weights ? ws : xs;
+}
+inline long double re_erf_complex(long double a, long double c) {
+  const long double *xs = gauss_legendre_32(false), *ws = gauss_legendre_32(true);
+  const long double ac = fabsl(c);
+  long panels_l = (long)ceill(ac / 0.5L), panels_p = (long)ceill(2.0L * fabsl(a) * ac / 8.0L);
+  long panels = panels_l > panels_p ? panels_l : panels_p;
+  if (panels < 1) panels = 1;
+  const long double h = ac / (long double)panels;
+  long double sum = 0.0L;
+  for (long q = 0; q < panels; q++) {
+    const long double mid = ((long double)q + 0.5L) * h;
+    for (int i = 0; i < 32; i++) {
+      const long double s = mid + 0.5L * h * xs[i];
+      sum += ws[i] * expl(s * s - a * a) * sinl(2.0L * a * s);
+    }
+  }
+  sum *= 0.5L * h;
+  return erfl(a) + 1.12837916709551257389615890312154517L * sum;   // 2 / sqrt(pi)
+}
 template <class R> inline R phi_hat_any(int kind, long k, long n, R b, int m, bool inverse) {
   const R pi = m_pi<R>();
   switch (kind) {
     case WIN_GAUSSIAN: {
       const R e = (pi * (R)k / (R)n) * (pi * (R)k / (R)n) * b;
       return inverse ? m_exp(e) : m_exp(-e);
+    }
+    case WIN_GAUSSIAN_T: {   // reference kernel/matrix_D.c:37-65: exp(-(pi k / n)^2 b) * Re erf(m / sqrt(b) + i pi k sqrt(b) / n)
+      const R sqrtb = m_sqrt(b);
+      const R w = (R)re_erf_complex((long double)((R)m / sqrtb), (long double)(pi * (R)k * sqrtb / (R)n));
+      const R e = (pi * (R)k / (R)n) * (pi * (R)k / (R)n) * b;
+      const R coeff = m_exp(-e) * w;
+      return inverse ? (R)1 / coeff : coeff;
     }
     case WIN_BSPLINE: {
       const R s = sinc<R>((R)k * pi / (R)n);

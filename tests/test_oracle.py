@@ -161,6 +161,42 @@ def test_fast_kaiser_bessel_taps_match_reference(m):
     assert rel_l2(dpsi[far], dpsi_r[far]) <= 1e-14
 
 
+@pytest.mark.parametrize("single", [False, True])
+@pytest.mark.parametrize("window", ["kaiser_bessel", "gaussian", "gaussian_t", "bspline", "sinc_power", "bessel_i0"])
+def test_window_fourier_coefficients_match_reference(window, single):
+    """phi_hat / 1/phi_hat as the product builds its D tables (Core::upload_window_tables, pnfft_phi_hat, pnfft_inv_phi_hat),
+    run on the host through pnfft_b200_phi_hat_host, against the compiled reference's pnfft_phi_hat / pnfft_inv_phi_hat
+    (kernel/matrix_D.c:30-132, 191-225) for every window -- PNFFT_WINDOW_GAUSSIAN_T included, whose coefficients carry
+    Re erf(m / sqrt(b) + i pi k sqrt(b) / n) (libcerf in the reference, an own quadrature here) -- on even, ragged and
+    strongly oversampled sizes."""
+    import ctypes as C
+    from pnfft_b200 import api as A
+    if not refdrv.available(single):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    ref = refdrv.get(single)
+    flags = {"kaiser_bessel": 0, "gaussian": 1 << 13, "gaussian_t": (1 << 13) | (1 << 17), "bspline": 1 << 14,
+             "sinc_power": 1 << 15, "bessel_i0": 1 << 16}[window]
+    fn = getattr(A.lib(), ("pnfftf_" if single else "pnfft_") + "b200_phi_hat_host")
+    fn.restype = None
+    fn.argtypes = [C.c_uint, C.c_ssize_t, C.c_ssize_t, C.c_float if single else C.c_double, C.c_int, C.c_void_p, C.c_ssize_t,
+                   C.c_int, C.c_void_p]
+    tol = 1e-5 if single else 1e-13
+    for N, n, m in [((16, 16, 16), (32, 32, 32), 6), ((8, 12, 10), (16, 24, 20), 5), ((24, 32, 20), (48, 64, 40), 4),
+                    ((16, 16, 16), (20, 24, 64), 8)]:
+        for dim in range(3):
+            k = np.arange(-N[dim] // 2, N[dim] // 2).astype(np.int64)
+            for inverse, name in ((1, "inv_phi_hat"), (0, "phi_hat")):
+                want = ref.probe(name, dim, k, N, n=n, m=m, pnfft_flags=flags)
+                got = np.zeros(len(k), np.float32 if single else np.float64)
+                fn(flags, N[dim], n[dim], 0.0, m, k.ctypes.data, len(k), inverse, got.ctypes.data)
+                assert np.all(np.abs(got - want) <= tol * np.abs(want)), (window, N[dim], n[dim], m, name)
+    if window == "gaussian_t" and not single:   # the truncation is visible: not the plain Gaussian's coefficients
+        k = np.arange(-8, 8).astype(np.int64)
+        plain = ref.probe("inv_phi_hat", 0, k, (16, 16, 16), m=6, pnfft_flags=1 << 13)
+        trunc = ref.probe("inv_phi_hat", 0, k, (16, 16, 16), m=6, pnfft_flags=flags)
+        assert np.abs(trunc / plain - 1).max() > 1e-8
+
+
 HCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "[hi]_*.npz")))
 
 

@@ -238,13 +238,42 @@ def intpol_cases(out):
     return names
 
 
+def gauss_t_cases(out):
+    """PNFFT_WINDOW_GAUSSIAN_T: the Gaussian window with the Fourier coefficients of its truncation to the cutoff (D matrix
+    only, reference kernel/matrix_D.c:37-65, 195-217; libcerf's cerf inside the compiled reference)."""
+    GT = WIN["gaussian"] | (1 << 17)
+    names = []
+    seed = 1500
+    for name, m, flags, c2r, single in [("t_gaussian_t_ad_c2c_m5_d", 5, GT, False, False),
+                                        ("t_gaussian_t_ik_c2c_m5_d", 5, GT | DIFF_IK, False, False),
+                                        ("t_gaussian_t_ad_c2r_m4_d", 4, GT, True, False),
+                                        ("t_fast_gaussian_t_ad_c2c_m6_d", 6, GT | (1 << 1), False, False),
+                                        ("t_il_gaussian_t_ad_c2c_m5_d", 5, GT | INTERLACED, False, False),
+                                        ("t_gaussian_t_ad_c2c_m5_f", 5, GT, False, True)]:
+        ref = refdrv.get(single)
+        N, M = (8, 12, 10), 120
+        seed += 1
+        x, fh, f, g = inputs(N, M, seed, c2r, single)
+        rt = ref.trafo(N, x, fh, m=m, pnfft_flags=flags, compute_flags=3, c2r=c2r)
+        ra = ref.adj(N, x, f=f, grad_f=g, m=m, pnfft_flags=flags, compute_flags=3, c2r=c2r)
+        psi, dpsi = ref.probe_tensor(x[:16], N, m=m, pnfft_flags=flags & ~INTERLACED)
+        np.savez_compressed(os.path.join(out, name + ".npz"), N=np.array(N), m=m, flags=flags, c2r=c2r, single=single, x=x,
+                            f_hat=fh, f=f, grad_f=g, out_f=rt["f"], out_grad_f=rt["grad_f"], out_f_hat=ra["f_hat"], psi=psi, dpsi=dpsi)
+        names.append(name)
+    print("wrote %d truncated-Gaussian cases" % len(names))
+    return names
+
+
 if __name__ == "__main__":
     gold = os.path.join(ROOT, "tests", "golden")
     if len(sys.argv) > 1 and sys.argv[1] == "--hessian":       # round-2 additions: leave the other fixtures untouched
         hessian_cases(gold)
     elif len(sys.argv) > 1 and sys.argv[1] == "--intpol":
         intpol_cases(gold)
+    elif len(sys.argv) > 1 and sys.argv[1] == "--gauss-t":
+        gauss_t_cases(gold)
     else:
         main()
         hessian_cases(gold)
         intpol_cases(gold)
+        gauss_t_cases(gold)
