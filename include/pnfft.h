@@ -197,6 +197,8 @@ typedef float pnfftf_complex[2];
   /* host evaluation of the window's Fourier coefficients as the D tables hold them: out[i] = phi_hat(k[i]) or, with       \
    * inverse != 0, 1 / phi_hat(k[i]) for the window of pnfft_flags (b <= 0: that window's default shape at sigma = n / N) */ \
   void PNX(b200_phi_hat_host)(unsigned pnfft_flags, ptrdiff_t N, ptrdiff_t n, R b, int m, const ptrdiff_t *k, ptrdiff_t len, int inverse, R *out); \
+  /* host evaluation of pnfft_psi (which = 0), pnfft_dpsi (1), pnfft_ddpsi (2) at offsets x[len] for the window of pnfft_flags */ \
+  void PNX(b200_psi_host)(unsigned pnfft_flags, ptrdiff_t N, ptrdiff_t n, R b, int m, int which, const R *x, ptrdiff_t len, R *out); \
   /* host-only self check of the pencil FFT's composed "own chunk" maps for rank (c0, c1) of a p0 x p1 \
    * mesh: self transfers checked, -1 on a mismatch, -2 if one did not compose (no GPU needed) */       \
   int PNX(b200_check_self_maps)(const ptrdiff_t *N, const ptrdiff_t *n, int m, int p0, int p1, int c0, int c1, int c2r); \

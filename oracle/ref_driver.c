@@ -51,6 +51,7 @@ typedef struct {
   INT *sort_perm;        /* optional out [M]: global node index in the rank's processing order */
   double b_out[3];       /* out: window shape parameters */
   R *hessian_f;          /* optional out [M][6] complex interleaved or real (PNFFT_COMPUTE_HESSIAN_F) */
+  double b_in[3];        /* b_in[0] > 0: pnfft_set_b(b_in) right after the plan is made (api/api-basic.c:587-596) */
 } DRV(job);
 
 typedef struct {
@@ -122,6 +123,7 @@ static void rank_main(int rank, void *arg)
     }
   }
   if (J->borders) for (int t = 0; t < 3; t++) { J->borders[6 * rank + t] = lo[t]; J->borders[6 * rank + 3 + t] = up[t]; }
+  if (J->b_in[0] > 0) PNX(set_b)((R)J->b_in[0], (R)J->b_in[1], (R)J->b_in[2], ths);
   if (rank == 0) for (int t = 0; t < 3; t++) J->b_out[t] = (double)ths->b[t];
 
   /* node ownership: the caller of PNFFT has to hand every rank the nodes with
@@ -243,7 +245,7 @@ static PNX(plan) probe_plan(const DRV(probe_cfg) *P, MPI_Comm *comm)
                 : PNX(init_guru)(3, P->N, P->n, x_max, P->m, P->pnfft_flags, PFFT_ESTIMATE, *comm);
 }
 
-/* which: 0 psi, 1 dpsi, 2 inv_phi_hat, 3 phi_hat.  arg: x (real) for 0/1, k (as R) for 2/3 */
+/* which: 0 psi, 1 dpsi, 2 inv_phi_hat, 3 phi_hat, 4 ddpsi.  arg: x (real) for 0/1/4, k (as R) for 2/3 */
 void DRV(probe)(const DRV(probe_cfg) *P, int which, int dim, INT count, const R *arg, R *out)
 {
   MPI_Comm comm;
@@ -253,6 +255,7 @@ void DRV(probe)(const DRV(probe_cfg) *P, int which, int dim, INT count, const R 
       case 0: out[i] = PNX(psi)(ths, dim, arg[i]); break;
       case 1: out[i] = PNX(dpsi)(ths, dim, arg[i]); break;
       case 2: out[i] = PNX(inv_phi_hat)(ths, dim, (INT)arg[i]); break;
+      case 4: out[i] = PNX(ddpsi)(ths, dim, arg[i]); break;
       default: out[i] = PNX(phi_hat)(ths, dim, (INT)arg[i]); break;
     }
   }

@@ -66,6 +66,7 @@ def _job_struct(real):
             ("sort_perm", C.POINTER(INT)),
             ("b_out", C.c_double * 3),
             ("hessian_f", RP),
+            ("b_in", C.c_double * 3),
         ]
 
     class Probe(C.Structure):
@@ -104,7 +105,7 @@ class RefLib:
     def run(self, op, N, n=None, m=6, x=None, f_hat=None, f=None, grad_f=None, np_mesh=(1, 1),
             x_max=(0.5, 0.5, 0.5), pnfft_flags=0, precompute_flags=0, compute_flags=COMPUTE_F, c2r=False,
             grid=None, g1=None, set_grid=False, get_grid=False, set_g1=False, get_g1=False,
-            want_index=False, want_sort=False, repeat=1):
+            want_index=False, want_sort=False, repeat=1, b=None):
         """Run trafo / adj / layout query of the reference on np_mesh[0] x np_mesh[1] virtual ranks.
 
         Arrays are global: x [M,3]; f_hat [N0,N1,N2c] complex; f [M] (complex, or real for c2r);
@@ -122,6 +123,8 @@ class RefLib:
         J.m = m
         J.pnfft_flags, J.precompute_flags, J.compute_flags = pnfft_flags, precompute_flags, compute_flags
         J.c2r, J.op, J.repeat, J.M = int(c2r), op, repeat, M
+        if b is not None:          # pnfft_set_b after the plan is made: other window shape parameters than the default
+            J.b_in[:] = [float(v) for v in b]
         keep = {}
         ftype = self.rdt if c2r else self.cdt
 
@@ -204,8 +207,8 @@ class RefLib:
         return P
 
     def probe(self, which, dim, arg, N, n=None, m=6, x_max=(0.5, 0.5, 0.5), pnfft_flags=0, c2r=False):
-        """which in {'psi','dpsi','inv_phi_hat','phi_hat'}; arg = x values or integer k values."""
-        code = {"psi": 0, "dpsi": 1, "inv_phi_hat": 2, "phi_hat": 3}[which]
+        """which in {'psi','dpsi','ddpsi','inv_phi_hat','phi_hat'}; arg = x values or integer k values."""
+        code = {"psi": 0, "dpsi": 1, "inv_phi_hat": 2, "phi_hat": 3, "ddpsi": 4}[which]
         a = np.ascontiguousarray(arg, dtype=self.rdt)
         out = np.zeros_like(a)
         fn = getattr(self.lib, self.pre + "probe")

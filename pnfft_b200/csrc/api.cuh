@@ -120,6 +120,7 @@ void PNX(set_b)(RT b0, RT b1, RT b2, PNX(plan) ths) {
   // reference api/api-basic.c:587-596: new shape parameters, window tables recomputed
   PlanT *p = AS_PLAN(ths);
   p->b[0] = b0; p->b[1] = b1; p->b[2] = b2;
+  p->win_gen++;   // node-table rows cached for unchanged coordinates hold window values of the old shape
   CoreT::upload_window_tables(p);
 }
 CT *PNX(get_f)(const PNX(nodes) nodes) { return (CT *)AS_NODES(nodes)->f; }
@@ -209,24 +210,34 @@ RT PNX(phi_hat)(const PNX(plan) ths, int dim, INT k) {
   const PlanT *p = AS_PLAN(ths);
   return pnb::phi_hat_any<RT>(pnb::window_hat_kind(p->pnfft_flags), (long)k, (long)p->L.n[dim], p->b[dim], p->L.m, false);
 }
-// psi(x), dpsi(x): window at offset x (reference kernel/ndft-parallel.c:2288-2316)
+// psi(x), dpsi(x), ddpsi(x): the window and its derivatives at offset x (reference kernel/ndft-parallel.c:2288-2336), by the
+// formulas the kernels, the Hessian path and the PNFFT_PRE_*_PSI tables use (window.h).  window_tap takes y = l - n x.
+static RT window_at(int kind, int which, RT n, RT b, int m, RT x) {
+  RT psi = 0, d = 0;
+  if (which == 0) {
+    if (kind == pnb::WIN_BSPLINE) return pnb::bspline<RT>(2 * m, n * x + (RT)m);
+    pnb::window_tap<RT>(kind, n * x, n, b, m, false, &psi, &d);
+    return psi;
+  }
+  if (which == 1) {
+    if (kind == pnb::WIN_BSPLINE) return n * (pnb::bspline<RT>(2 * m - 1, n * x + (RT)m) - pnb::bspline<RT>(2 * m - 1, n * x + (RT)m - (RT)1));
+    pnb::window_tap<RT>(kind, -(n * x), n, b, m, true, &psi, &d);
+    return d;
+  }
+  if (kind != pnb::WIN_BSPLINE) pnb::window_tap<RT>(kind, -(n * x), n, b, m, true, &psi, &d);
+  return pnb::window_ddtap<RT>(kind, -(n * x), n, b, m, psi, d);
+}
 RT PNX(psi)(const PNX(plan) ths, int dim, RT x) {
   const PlanT *p = AS_PLAN(ths);
-  const RT n = (RT)p->L.n[dim];
-  if (p->kind == pnb::WIN_BSPLINE) return pnb::bspline<RT>(2 * p->L.m, n * x + (RT)p->L.m);
-  RT psi, d;
-  pnb::window_tap<RT>(p->kind, n * x, n, p->b[dim], p->L.m, false, &psi, &d);
-  return psi;
+  return window_at(p->kind, 0, (RT)p->L.n[dim], p->b[dim], p->L.m, x);
 }
 RT PNX(dpsi)(const PNX(plan) ths, int dim, RT x) {
   const PlanT *p = AS_PLAN(ths);
-  const RT n = (RT)p->L.n[dim];
-  const int m = p->L.m;
-  if (p->kind == pnb::WIN_BSPLINE) return n * (pnb::bspline<RT>(2 * m - 1, n * x + (RT)m) - pnb::bspline<RT>(2 * m - 1, n * x + (RT)m - (RT)1));
-  RT psi, d;
-  // window_tap takes y = l - n x, i.e. z = -y = n x
-  pnb::window_tap<RT>(p->kind, -(n * x), n, p->b[dim], m, true, &psi, &d);
-  return d;
+  return window_at(p->kind, 1, (RT)p->L.n[dim], p->b[dim], p->L.m, x);
+}
+RT PNX(ddpsi)(const PNX(plan) ths, int dim, RT x) {
+  const PlanT *p = AS_PLAN(ths);
+  return window_at(p->kind, 2, (RT)p->L.n[dim], p->b[dim], p->L.m, x);
 }
 
 void PNX(vpr_complex)(CT *data, INT N, const char *name, MPI_Comm comm) {
@@ -322,10 +333,6 @@ void PNX(apr_complex_3d)(CT *data, INT *local_N, INT *local_N_start, unsigned, c
 void PNX(apr_real_3d)(RT *data, INT *local_N, INT *local_N_start, unsigned, const char *name, MPI_Comm comm) {
   apr_block(data, 1, local_N, local_N_start, name, comm);
 }
-RT PNX(ddpsi)(const PNX(plan), int, RT) {
-  fprintf(stderr, "pnfft-b200: second window derivatives (Hessian path) are not part of the accelerated path\n");
-  return (RT)0;
-}
 void PNX(get_args)(int argc, char **argv, const char *name, int neededArgs, unsigned type, void *parameter) {
   pfft_get_args(argc, argv, name, neededArgs, type, parameter);
 }
@@ -333,7 +340,7 @@ void PNX(get_args)(int argc, char **argv, const char *name, int neededArgs, unsi
 void PNX(check_init_parameters)(int argc, char **argv, INT *N, INT *n, INT *local_M, int *m, unsigned *pnfft_flags,
                                 unsigned *compute_flags, double *x_max, int *np, int *compare_direct, int *debug) {
   int window = 4, fast_gaussian = 0, intpol = -1, interlaced = 0, diff_ik = 0, tr_f_hat = 0;
-  int cf = 1, cg = 1, ch = 0;      // the Hessian is outside the accelerated path: off unless asked for
+  int cf = 1, cg = 1, ch = 1;      // the reference's defaults (api/api-basic.c:834-836)
   N[0] = N[1] = N[2] = 16; n[0] = n[1] = n[2] = 0; *local_M = 0; *m = 6;
   x_max[0] = x_max[1] = x_max[2] = 0.5;
   np[0] = np[1] = np[2] = 2;
@@ -495,6 +502,13 @@ void PNX(b200_kb_taps_host)(const double *x, INT M, const INT *n, const double *
         if (dpsi) dpsi[((size_t)j * 3 + t) * c + s] = d;
       }
     }
+}
+// ... and of the window itself: out[i] = psi (which = 0), dpsi (1) or ddpsi (2) at offset x[i], as pnfft_psi / pnfft_dpsi /
+// pnfft_ddpsi of a plan with these flags, sizes and shape parameter return them (b <= 0: the window's default shape)
+void PNX(b200_psi_host)(unsigned pnfft_flags, INT N, INT n, RT b, int m, int which, const RT *x, INT len, RT *out) {
+  const int kind = pnb::window_kind(pnfft_flags);
+  const RT bb = b > 0 ? b : pnb::window_shape<RT>(kind, m, (RT)n / (RT)N);
+  for (INT i = 0; i < len; i++) out[i] = window_at(kind, which, (RT)n, bb, m, x[i]);
 }
 // Host evaluation of the window's Fourier coefficients exactly as the D tables (Core::upload_window_tables) and
 // pnfft_phi_hat / pnfft_inv_phi_hat compute them: out[i] = phi_hat(k[i]) (inverse = 0) or 1 / phi_hat(k[i]) for the window

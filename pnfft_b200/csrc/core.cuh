@@ -1281,13 +1281,13 @@ template <class R> struct Core {
       const double need_gb = (double)na.M * (GRAD ? len_g : len_f) * sizeof(R) / 1073741824.0;
       if (need_gb <= cap_gb || p->b_phase != 3) {
         // one table for the whole node set, in the binning's own buffer
-        const bool reuse = cache_on && nd->binned && nd->rows_plan == (const void *)p && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
+        const bool reuse = cache_on && nd->binned && nd->rows_plan == (const void *)p && nd->rows_gen == p->win_gen && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
         int flavor = reuse ? nd->rows_flavor : (GRAD ? 1 : 0);
         if (!reuse && (p->b_phase & 1)) {
           ensure(&nd->d_rows, &nd->cap_rows, (size_t)na.M * (flavor ? len_g : len_f) + 64);
           if (flavor) launch_zm3_table<CPLX, M_, true>(p, g, na, nd->d_rows, 0);
           else launch_zm3_table<CPLX, M_, false>(p, g, na, nd->d_rows, 0);
-          nd->rows_flavor = flavor; nd->rows_plan = p;
+          nd->rows_flavor = flavor; nd->rows_plan = p; nd->rows_gen = p->win_gen;
         } else if (!reuse) {
           flavor = nd->rows_flavor;      // the table phase of this call ran earlier (side stream)
         }
@@ -1338,7 +1338,7 @@ template <class R> struct Core {
       const size_t len_g = ZmRowOf<R, Cfg, true, false, CPLX>::ROWLEN, len_f = ZmRowOf<R, Cfg, false, false, CPLX>::ROWLEN;
       const char *rc = getenv("PNFFT_B200_ROW_CACHE");
       const bool cache_on = !(rc && atoi(rc) == 0);
-      const bool reuse = cache_on && nd->binned && nd->rows_plan == (const void *)p && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
+      const bool reuse = cache_on && nd->binned && nd->rows_plan == (const void *)p && nd->rows_gen == p->win_gen && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
       flavor = reuse ? nd->rows_flavor : (GRAD ? 1 : 0);
       if (!reuse && (p->b_phase & 1)) {
         ensure(&nd->d_rows, &nd->cap_rows, (size_t)na.M * (flavor ? len_g : len_f) + 64);
@@ -1352,7 +1352,7 @@ template <class R> struct Core {
         };
         if (flavor) table(k_node_table2<R, M_, true, false, CPLX, Cfg>, ZmRowOf<R, Cfg, true, false, CPLX>::ROWBYTES);
         else table(k_node_table2<R, M_, false, false, CPLX, Cfg>, ZmRowOf<R, Cfg, false, false, CPLX>::ROWBYTES);
-        nd->rows_flavor = flavor; nd->rows_plan = p;
+        nd->rows_flavor = flavor; nd->rows_plan = p; nd->rows_gen = p->win_gen;
       } else if (!reuse) {
         flavor = nd->rows_flavor;      // the table phase of this call ran earlier (side stream)
       }
@@ -1401,7 +1401,7 @@ template <class R> struct Core {
       const size_t rowlen = ZmRowOf<R, Cfg, GRAD, false, CPLX>::ROWLEN;
       static const double cap_gb = getenv("PNFFT_B200_TABLE_GB") ? atof(getenv("PNFFT_B200_TABLE_GB")) : 24.0;
       const double need_gb = (double)na.M * rowlen * sizeof(R) / 1073741824.0;
-      const bool cached = nd->binned && nd->rows_plan == (const void *)p && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
+      const bool cached = nd->binned && nd->rows_plan == (const void *)p && nd->rows_gen == p->win_gen && nd->rows_flavor >= (GRAD ? 1 : 0) && nd->d_rows;
       if (need_gb <= cap_gb || p->b_phase != 3 || cached) {
         const int flavor = zm4_rows<CPLX, M_, GRAD>(p, nd, na);
         if (p->b_phase & 2) run(zg, (unsigned)(ncol * zg.nseg), nd->d_rows, flavor);
@@ -1710,21 +1710,6 @@ template <class R> struct Core {
 
   static void rec(P *p, int i) { PNB_CUDA(cudaEventRecord(p->ev[i], p->stream)); }
   static double ms(P *p, int a, int b) { float t = 0; cudaEventElapsedTime(&t, p->ev[a], p->ev[b]); return (double)t; }
-
-  // PNFFT_COMPUTE_HESSIAN_F is outside the accelerated path: say so once, and leave zeros like the reference's own
-  // zeroing of the output arrays (api/api-basic.c:210-222) instead of stale memory
-  static void hessian_unsupported(P *p, Nd *nd, unsigned cf) {
-    if (!(cf & C_HESSIAN_F)) return;
-    if (!p->warned_hessian) {
-      fprintf(stderr, "pnfft-b200: PNFFT_COMPUTE_HESSIAN_F is not part of the accelerated path; hessian_f is zero-filled\n");
-      p->warned_hessian = true;
-    }
-    if (nd && nd->hessian_f && !(cf & C_ACCUMULATED)) {
-      const size_t bytes = sizeof(R) * 6 * (p->L.c2r ? 1 : 2) * (size_t)nd->local_M;
-      if (is_device_ptr(nd->hessian_f)) PNB_CUDA(cudaMemsetAsync(nd->hessian_f, 0, bytes, p->stream));
-      else memset(nd->hessian_f, 0, bytes);
-    }
-  }
 
   // -------------------------------------------------------------------------------------------
   // trafo  (reference api/api-basic.c:170-244)

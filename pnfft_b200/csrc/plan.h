@@ -173,6 +173,7 @@ template <class R> struct Plan {
   unsigned pnfft_flags = 0, pfft_flags = 0;
   R x_max[3], sigma[3], b[3];
   int kind = WIN_KAISER_BESSEL;
+  unsigned win_gen = 0;          // bumped whenever the window shape b changes (pnfft_set_b): cached node-table rows carry it
 
   // user-visible f_hat (host or device pointer); owned iff PNFFT_MALLOC_F_HAT
   C *f_hat = nullptr;
@@ -253,6 +254,7 @@ template <class R> struct BinState {
   size_t cap_rows = 0;
   int rows_flavor = -1;            // -1: none, 0: psi sections only, 1: with the derivative sections
   const void *rows_plan = nullptr;
+  unsigned rows_gen = 0;           // Plan::win_gen the rows were evaluated with
 };
 
 template <class R> struct Nodes : BinState<R> {

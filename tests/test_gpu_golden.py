@@ -111,6 +111,34 @@ def test_intpol_golden(case, variant):
     assert rel_l2(fh, g["out_f_hat"]) <= 1e-13
 
 
+BCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "b_*.npz")))
+
+
+@pytest.mark.parametrize("variant", [0, 8, 1])
+@pytest.mark.parametrize("case", BCASES)
+def test_set_b_golden(case, variant):
+    """pnfft_set_b (reference api/api-basic.c:587-596): window shape parameters changed after the plan was made -- the D
+    tables, fast-Gaussian constants and interpolation tables are rebuilt.  A transform with the DEFAULT shape runs first on
+    the same node object, so that everything it leaves behind for unchanged coordinates (bins, the tensor-core kernels'
+    node-table rows) meets the new shape: pnfft_adj right after pnfft_set_b must not gather from rows of the old window."""
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    single, c2r = bool(g["single"]), bool(g["c2r"])
+    tol = 1e-5 if single else 1e-13
+    run = Run1(tuple(g["N"]), g["x"], m=int(g["m"]), flags=int(g["flags"]), c2r=c2r, single=single, variant=variant)
+    f_def, _ = run.trafo(g["f_hat"], F | G)
+    b = tuple(float(v) for v in g["b"])
+    run.plan.set_b(*b)
+    assert np.allclose(run.plan.get_b(), b, rtol=1e-6 if single else 0, atol=0)
+    fh = run.adj(g["f"], g["grad_f"], F | G)
+    f, gr = run.trafo(g["f_hat"], F | G)
+    run.close()
+    if not single:      # the default shape gives other values (the approximation error differs; in float both are at rounding)
+        assert rel_l2(f_def, g["out_f"]) > 1e-10
+    assert rel_l2(fh, g["out_f_hat"]) <= tol
+    assert rel_l2(f, g["out_f"]) <= tol
+    assert rel_l2(gr, g["out_grad_f"]) <= tol
+
+
 @pytest.mark.parametrize("win", ["kaiser_bessel", "gaussian"])
 def test_intpol_quadratic_vs_direct(win):
     """PNFFT_PRE_QUAD_PSI has no usable reference output (its flag bit doubles as PNFFT_REAL_F inside the reference's node
@@ -598,6 +626,12 @@ def test_reference_drivers():
         errs = [float(v) for v in re.findall(r"relative error =\s*([0-9.eE+-]+)", out)]
         assert errs, out[-2000:]
         assert max(errs) < 1e-7, out[-2000:]   # truncation error of the method at m=6 (f ~4e-11, AD gradient ~2e-8)
+    # the drivers' default (api/api-basic.c:834-836) asks for the Hessian too: f, 3 gradient and 6 Hessian components,
+    # each against the m + 2 transform (two more derivatives cost about five digits of the method's accuracy at m = 6)
+    out = _run_driver("check_trafo", ["-pnfft_np", "1", "1", "1", "-pnfft_N", "16", "16", "16"])
+    errs = [float(v) for v in re.findall(r"relative error =\s*([0-9.eE+-]+)", out)]
+    assert len(errs) == 10, out[-2000:]
+    assert max(errs) < 1e-3 and max(errs[:4]) < 1e-7, out[-2000:]
     out = _run_driver("check_vs_pfft", ["-pnfft_np", "1", "1", "1", "-pnfft_N", "16", "16", "16"])
     errs = [float(v) for v in re.findall(r"relative maximum error =\s*([0-9.eE+-]+)", out)]
     assert errs and max(errs) < 1e-10, out[-2000:]

@@ -197,6 +197,42 @@ def test_window_fourier_coefficients_match_reference(window, single):
         assert np.abs(trunc / plain - 1).max() > 1e-8
 
 
+@pytest.mark.parametrize("single", [False, True])
+@pytest.mark.parametrize("window", ["kaiser_bessel", "gaussian", "bspline", "sinc_power", "bessel_i0"])
+def test_window_point_values_match_reference(window, single):
+    """pnfft_psi / pnfft_dpsi / pnfft_ddpsi (reference kernel/ndft-parallel.c:2288-2336) as the product evaluates them
+    (csrc/api.cuh window_at -> window.h window_tap / window_ddtap, the formulas of the kernels, the Hessian path and the
+    interpolation tables), on the host through pnfft_b200_psi_host, against the compiled reference at random offsets inside
+    the support, at 0, near the edge of the support and on grid lines."""
+    import ctypes as C
+    from pnfft_b200 import api as A
+    if not refdrv.available(single):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    ref = refdrv.get(single)
+    flags = {"kaiser_bessel": 0, "gaussian": 1 << 13, "bspline": 1 << 14, "sinc_power": 1 << 15, "bessel_i0": 1 << 16}[window]
+    dt = np.float32 if single else np.float64
+    fn = getattr(A.lib(), ("pnfftf_" if single else "pnfft_") + "b200_psi_host")
+    fn.restype = None
+    fn.argtypes = [C.c_uint, C.c_ssize_t, C.c_ssize_t, C.c_float if single else C.c_double, C.c_int, C.c_int, C.c_void_p,
+                   C.c_ssize_t, C.c_void_p]
+    rng = np.random.default_rng(3)
+    for N, n, m in [((16, 16, 16), (32, 32, 32), 6), ((8, 12, 10), (16, 24, 20), 5), ((24, 32, 20), (48, 64, 40), 4)]:
+        dim = 1
+        x = (rng.uniform(-1, 1, 400) * (m / n[dim])).astype(dt)
+        x[:5] = np.array([0, m / n[dim] * 0.999, -m / n[dim] * 0.5, 1.0 / n[dim], -2.0 / n[dim]], dt)
+        for which, name in ((0, "psi"), (1, "dpsi"), (2, "ddpsi")):
+            # sinc-power derivatives: cot(w) - 1/w (and its square) cancel near w = 0 in the reference's own formula
+            # (:1897-1917, :2060-2075): the float reference is only good to ~1e-4 in dpsi and has no correct digit in ddpsi
+            # there, the double one to ~1e-10 in ddpsi
+            if window == "sinc_power" and single and which == 2:
+                continue
+            tol = (1e-5 if single else 1e-13) if not (window == "sinc_power" and which) else (2e-4 if single else 1e-9)
+            want = ref.probe(name, dim, x, N, n=n, m=m, pnfft_flags=flags)
+            got = np.zeros(len(x), dt)
+            fn(flags, N[dim], n[dim], 0.0, m, which, x.ctypes.data, len(x), got.ctypes.data)
+            assert np.abs(got - want).max() <= tol * np.abs(want).max(), (window, m, name)
+
+
 HCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "[hi]_*.npz")))
 
 
@@ -228,3 +264,30 @@ def test_hessian_intpol_fixtures_reproduce(case):
         for c, (a, b) in enumerate(pairs):
             direct = (-4 * np.pi ** 2 * K[a] * K[b] * ph * g["f_hat"]).sum((1, 2, 3))
             assert rel_l2(t["hessian_f"][:8, c], direct) <= (1e-3 if single else 1e-9)
+
+
+BCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "b_*.npz")))
+
+
+def test_set_b_golden_present():
+    assert len(BCASES) == 10
+
+
+@pytest.mark.parametrize("case", BCASES)
+def test_set_b_fixtures_reproduce(case):
+    """pnfft_set_b fixtures (tools/make_golden.py --set-b): the compiled reference, where it is available, reproduces them
+    bit for bit -- this pins the generator and the driver's b plumbing -- and the default shape gives other values."""
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    single = bool(g["single"])
+    if not refdrv.available(single):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    ref = refdrv.get(single)
+    kw = dict(m=int(g["m"]), pnfft_flags=int(g["flags"]), compute_flags=3, c2r=bool(g["c2r"]))
+    N = tuple(int(v) for v in g["N"])
+    t = ref.trafo(N, g["x"], g["f_hat"], b=tuple(g["b"]), **kw)
+    a = ref.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], b=tuple(g["b"]), **kw)
+    assert np.array_equal(t["f"], g["out_f"]) and np.array_equal(t["grad_f"], g["out_grad_f"])
+    assert np.array_equal(a["f_hat"], g["out_f_hat"])
+    if not single:      # (in float both shapes are accurate to rounding: nothing to tell apart in f)
+        t0 = ref.trafo(N, g["x"], g["f_hat"], **kw)
+        assert rel_l2(t0["f"], g["out_f"]) > 1e-10

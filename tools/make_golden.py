@@ -264,6 +264,37 @@ def gauss_t_cases(out):
     return names
 
 
+def set_b_cases(out):
+    """pnfft_set_b (api/api-basic.c:587-596): other window shape parameters than the plan's default, set after the plan is
+    made -- the reference recomputes 1/phi_hat, the fast-Gaussian constants and the interpolation tables."""
+    names = []
+    seed = 1700
+    for name, win, m, extra, c2r, single, b in [
+            ("b_kaiser_bessel_c2c_m6_d", "kaiser_bessel", 6, 0, False, False, (5.0, 5.2, 4.9)),
+            ("b_kaiser_bessel_c2c_m8_d", "kaiser_bessel", 8, 0, False, False, (4.0, 4.2, 5.2)),
+            ("b_kaiser_bessel_c2r_m4_d", "kaiser_bessel", 4, 0, True, False, (4.4, 4.5, 4.9)),
+            ("b_kaiser_bessel_c2c_m6_f", "kaiser_bessel", 6, 0, False, True, (5.0, 5.2, 4.9)),
+            ("b_kaiser_bessel_cub_c2c_m6_d", "kaiser_bessel", 6, 1 << 5, False, False, (5.0, 5.2, 4.9)),
+            ("b_gaussian_c2c_m5_d", "gaussian", 5, 0, False, False, (2.0, 2.3, 2.6)),
+            ("b_fast_gaussian_c2c_m5_d", "fast_gaussian", 5, 0, False, False, (2.0, 2.3, 2.6)),
+            ("b_gaussian_t_c2c_m5_d", "gaussian", 5, 1 << 17, False, False, (2.0, 2.3, 2.6)),
+            ("b_bessel_i0_c2c_m5_d", "bessel_i0", 5, 0, False, False, (4.5, 4.9, 5.1)),
+            ("b_sinc_power_ik_c2c_m5_d", "sinc_power", 5, DIFF_IK, False, False, (6.0, 6.5, 7.0))]:
+        ref = refdrv.get(single)
+        N, M = (8, 12, 10), 120
+        seed += 1
+        x, fh, f, g = inputs(N, M, seed, c2r, single)
+        flags = WIN[win] | extra
+        rt = ref.trafo(N, x, fh, m=m, pnfft_flags=flags, compute_flags=3, c2r=c2r, b=b)
+        ra = ref.adj(N, x, f=f, grad_f=g, m=m, pnfft_flags=flags, compute_flags=3, c2r=c2r, b=b)
+        assert tuple(rt["b"]) == tuple(np.asarray(b, np.float32 if single else np.float64).astype(np.float64))
+        np.savez_compressed(os.path.join(out, name + ".npz"), N=np.array(N), m=m, flags=flags, c2r=c2r, single=single, b=np.array(b),
+                            x=x, f_hat=fh, f=f, grad_f=g, out_f=rt["f"], out_grad_f=rt["grad_f"], out_f_hat=ra["f_hat"])
+        names.append(name)
+    print("wrote %d pnfft_set_b cases" % len(names))
+    return names
+
+
 if __name__ == "__main__":
     gold = os.path.join(ROOT, "tests", "golden")
     if len(sys.argv) > 1 and sys.argv[1] == "--hessian":       # round-2 additions: leave the other fixtures untouched
@@ -272,8 +303,11 @@ if __name__ == "__main__":
         intpol_cases(gold)
     elif len(sys.argv) > 1 and sys.argv[1] == "--gauss-t":
         gauss_t_cases(gold)
+    elif len(sys.argv) > 1 and sys.argv[1] == "--set-b":
+        set_b_cases(gold)
     else:
         main()
         hessian_cases(gold)
         intpol_cases(gold)
         gauss_t_cases(gold)
+        set_b_cases(gold)
