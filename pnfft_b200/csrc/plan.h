@@ -190,7 +190,6 @@ template <class R> struct Plan {
   bool x_via_copy_stream = false;       // set by trafo around prepare_nodes: ev_copy[0] marks where the x upload may start
   C *d_f_hat = nullptr;          // staging copy when the user's f_hat is a host pointer
   R *d_invphi[3] = {nullptr, nullptr, nullptr};  // 1/phi_hat tables incl. the (-1)^k fft-shift sign, [local_N[t]]
-  R *d_invphi_plain[3] = {nullptr, nullptr, nullptr};  // without the sign (for OMIT_FFT paths)
   R *d_exp_const = nullptr;      // [3][cutoff] for FAST_GAUSSIAN
   R *d_poly = nullptr;           // window polynomials (see GridGeom::poly)
   int intpol_order = -1;         // PNFFT_PRE_*_PSI interpolation order, -1: none
