@@ -111,6 +111,37 @@ def test_intpol_golden(case, variant):
     assert rel_l2(fh, g["out_f_hat"]) <= 1e-13
 
 
+CCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "c_*.npz")))
+
+
+@pytest.mark.parametrize("variant", [0, 1])   # the family the plan picks / the generic kernels
+@pytest.mark.parametrize("case", CCASES)
+def test_combination_golden(case, variant):
+    """Flag and size combinations against the compiled reference (tools/make_golden.py: combination_cases): Hessians with
+    interlacing / truncated torus / transposed f_hat, oversampling factors other than 2 and different per axis, cutoffs
+    m = 2, 3, 5, 7, 8, 10, PNFFT_PRE_PSI with interlacing / torus / transposed f_hat, three-flag mixes."""
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    single, c2r = bool(g["single"]), bool(g["c2r"])
+    tol = 1e-5 if single else 1e-13
+    N, n, x_max, _ = fixture_kwargs(g)
+    cf, pre, hess = int(g["cf"]), int(g["pre"]), "out_hessian_f" in g.files
+    run = Run1(N, g["x"], n=n, m=int(g["m"]), flags=int(g["flags"]), c2r=c2r, single=single, x_max=x_max, variant=variant)
+    if pre:
+        run.plan.precompute_psi(run.nodes, pre)
+    if hess:
+        f, gr, h = run.trafo_hessian(g["f_hat"], cf | A.COMPUTE_HESSIAN_F)
+    else:
+        f, gr = run.trafo(g["f_hat"], cf)
+    fh = run.adj(g["f"], g["grad_f"], cf)
+    run.close()
+    assert rel_l2(f, g["out_f"]) <= tol
+    if cf & G:
+        assert rel_l2(gr, g["out_grad_f"]) <= tol
+    if hess:
+        assert rel_l2(h, g["out_hessian_f"]) <= 10 * tol
+    assert rel_l2(fh, g["out_f_hat"]) <= tol
+
+
 BCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "b_*.npz")))
 
 

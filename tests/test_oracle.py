@@ -291,3 +291,37 @@ def test_set_b_fixtures_reproduce(case):
     if not single:      # (in float both shapes are accurate to rounding: nothing to tell apart in f)
         t0 = ref.trafo(N, g["x"], g["f_hat"], **kw)
         assert rel_l2(t0["f"], g["out_f"]) > 1e-10
+
+
+CCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "c_*.npz")))
+
+
+def test_combination_golden_present():
+    assert len(CCASES) == 28
+
+
+@pytest.mark.parametrize("case", CCASES)
+def test_combination_fixtures_reproduce(case):
+    """Combination fixtures (tools/make_golden.py --combinations): the compiled reference, where it is available, reproduces
+    them bit for bit; the clean-room port agrees with them where it covers the flags (no Hessian, no PRE_PSI tables)."""
+    from tests.util import fixture_kwargs
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    single, c2r = bool(g["single"]), bool(g["c2r"])
+    N, n, x_max, _ = fixture_kwargs(g)
+    cf, pre, hess = int(g["cf"]), int(g["pre"]), "out_hessian_f" in g.files
+    kw = dict(n=n, m=int(g["m"]), pnfft_flags=int(g["flags"]), c2r=c2r, x_max=x_max)
+    if refdrv.available(single):
+        ref = refdrv.get(single)
+        t = ref.trafo(N, g["x"], g["f_hat"], compute_flags=cf | (4 if hess else 0), precompute_flags=pre, **kw)
+        a = ref.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], compute_flags=cf, precompute_flags=pre, **kw)
+        assert np.array_equal(t["f"], g["out_f"]) and np.array_equal(a["f_hat"], g["out_f_hat"])
+        if hess:
+            assert np.array_equal(t["hessian_f"], g["out_hessian_f"])
+    tol = 1e-5 if single else 1e-13
+    po = checker.port(single)
+    t = po.trafo(N, g["x"], g["f_hat"], compute_flags=cf, **kw)
+    a = po.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], compute_flags=cf, **kw)
+    assert rel_l2(t["f"], g["out_f"]) <= tol
+    if cf & 2:
+        assert rel_l2(t["grad_f"], g["out_grad_f"]) <= tol
+    assert rel_l2(a["f_hat"], g["out_f_hat"]) <= tol

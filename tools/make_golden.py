@@ -295,6 +295,72 @@ def set_b_cases(out):
     return names
 
 
+def combination_cases(out):
+    """Flag / size combinations the other groups leave out: Hessians with interlacing, truncated torus and transposed
+    f_hat; oversampling factors other than 2 (n != 2N, different per axis); cutoffs m = 2, 3, 5, 7, 8, 10 against the
+    reference itself; PNFFT_PRE_PSI with interlacing / torus; three-flag mixes.  Optional keys: out_hessian_f (trafo ran
+    with PNFFT_COMPUTE_HESSIAN_F), pre (precompute flags), cf (compute flags of trafo and adj, default F | GRAD_F)."""
+    names = []
+    seed = 2000
+    Ns, Nt, nt, xm = (8, 12, 10), (24, 32, 20), (48, 64, 40), (0.3, 0.25, 0.5)
+    KB, GA, BS = 0, WIN["gaussian"], WIN["bspline"]
+    cases = [
+        # name, N, n, x_max, m, flags, c2r, single, hessian, pre, cf
+        ("c_hess_il_kaiser_bessel_c2c_m6_d", Ns, None, None, 6, KB | INTERLACED, False, False, True, 0, 3),
+        ("c_hess_il_ik_kaiser_bessel_c2c_m6_d", Ns, None, None, 6, KB | INTERLACED | DIFF_IK, False, False, True, 0, 3),
+        ("c_hess_torus_kaiser_bessel_c2c_m4_d", Nt, nt, xm, 4, KB, False, False, True, 0, 3),
+        ("c_hess_tr_gaussian_c2c_m5_d", Ns, None, None, 5, GA | TRANSPOSED, False, False, True, 0, 3),
+        ("c_hess_torus_bspline_c2r_m4_d", Nt, nt, xm, 4, BS, True, False, True, 0, 3),
+        ("c_sigma_kaiser_bessel_c2c_m4_d", Ns, (20, 18, 24), None, 4, KB, False, False, False, 0, 3),
+        ("c_sigma_kaiser_bessel_c2r_m4_d", Ns, (20, 18, 24), None, 4, KB, True, False, False, 0, 3),
+        ("c_sigma_kaiser_bessel_ik_c2c_m6_d", (12, 12, 12), (18, 32, 20), None, 6, KB | DIFF_IK, False, False, False, 0, 3),
+        ("c_sigma_bspline_c2c_m5_f", Ns, (20, 26, 24), None, 5, BS, False, True, False, 0, 3),
+        ("c_sigma_gaussian_il_c2c_m5_d", Ns, (24, 20, 28), None, 5, GA | INTERLACED, False, False, False, 0, 3),
+        ("c_il_torus_kaiser_bessel_c2r_m4_d", Nt, nt, xm, 4, KB | INTERLACED, True, False, False, 0, 3),
+        ("c_ik_torus_tr_kaiser_bessel_c2c_m4_d", Nt, nt, xm, 4, KB | DIFF_IK | TRANSPOSED, False, False, False, 0, 3),
+        ("c_fast_gaussian_il_c2r_m5_d", Ns, None, None, 5, WIN["fast_gaussian"] | INTERLACED, True, False, False, 0, 3),
+        ("c_bessel_i0_tr_ik_c2c_m5_d", Ns, None, None, 5, WIN["bessel_i0"] | TRANSPOSED | DIFF_IK, False, False, False, 0, 3),
+        ("c_sinc_power_torus_c2c_m4_d", Nt, nt, xm, 4, WIN["sinc_power"], False, False, False, 0, 3),
+        ("c_kaiser_bessel_c2c_m2_d", (16, 16, 16), None, None, 2, KB, False, False, False, 0, 3),
+        ("c_kaiser_bessel_c2c_m3_d", (16, 16, 16), None, None, 3, KB, False, False, False, 0, 3),
+        ("c_kaiser_bessel_c2c_m5_d", (16, 16, 16), None, None, 5, KB, False, False, False, 0, 3),
+        ("c_kaiser_bessel_c2c_m7_d", (16, 16, 16), None, None, 7, KB, False, False, False, 0, 3),
+        ("c_kaiser_bessel_c2r_m7_d", (16, 16, 16), None, None, 7, KB, True, False, False, 0, 3),
+        ("c_kaiser_bessel_c2c_m8_d", (16, 16, 16), None, None, 8, KB, False, False, False, 0, 3),
+        ("c_gaussian_c2r_m8_d", (16, 16, 16), None, None, 8, GA, True, False, False, 0, 3),
+        ("c_bspline_il_c2c_m8_d", (16, 16, 16), None, None, 8, BS | INTERLACED, False, False, False, 0, 3),
+        ("c_kaiser_bessel_c2c_m10_d", (16, 16, 16), None, None, 10, KB, False, False, False, 0, 3),
+        # (no float Kaiser-Bessel case at m = 8: the float reference returns NaN there -- I0(8 b)^-3 underflows in D while
+        # sinh(8 b)^3 overflows in B)
+        ("c_gaussian_c2c_m8_f", (16, 16, 16), None, None, 8, GA, False, True, False, 0, 3),
+        ("c_pre_il_kaiser_bessel_c2c_m6_d", Ns, None, None, 6, KB | INTERLACED, False, False, False, 2, 1),
+        ("c_pre_torus_gaussian_c2r_m4_d", Nt, nt, xm, 4, GA, True, False, False, 2, 1),
+        ("c_pre_tr_kaiser_bessel_c2c_m8_d", (16, 16, 16), None, None, 8, KB | TRANSPOSED, False, False, False, 2, 1),
+    ]
+    for name, N, n, x_max, m, flags, c2r, single, hess, pre, cf in cases:
+        ref = refdrv.get(single)
+        seed += 1
+        M = 150
+        x, fh, f, g = inputs(N, M, seed, c2r, single)
+        rdt = np.float32 if single else np.float64
+        x_max_ = tuple(x_max) if x_max is not None else (0.5, 0.5, 0.5)
+        x = (x * (2 * np.array(x_max_))).astype(rdt)
+        n_ = tuple(n) if n is not None else tuple(2 * v for v in N)
+        kw = dict(n=n_, m=m, pnfft_flags=flags, c2r=c2r, x_max=x_max_, precompute_flags=pre)
+        rt = ref.trafo(N, x, fh, compute_flags=cf | (4 if hess else 0), **kw)
+        ra = ref.adj(N, x, f=f, grad_f=g, compute_flags=cf, **kw)
+        extra = dict(out_hessian_f=rt["hessian_f"]) if hess else {}
+        for k in ("f", "grad_f"):
+            assert np.all(np.isfinite(rt[k])), (name, k)
+        assert np.all(np.isfinite(ra["f_hat"])), name
+        np.savez_compressed(os.path.join(out, name + ".npz"), N=np.array(N), n=np.array(n_), x_max=np.array(x_max_), m=m, flags=flags,
+                            c2r=c2r, single=single, pre=pre, cf=cf, x=x, f_hat=fh, f=f, grad_f=g, out_f=rt["f"],
+                            out_grad_f=rt["grad_f"], out_f_hat=ra["f_hat"], **extra)
+        names.append(name)
+    print("wrote %d combination cases" % len(names))
+    return names
+
+
 if __name__ == "__main__":
     gold = os.path.join(ROOT, "tests", "golden")
     if len(sys.argv) > 1 and sys.argv[1] == "--hessian":       # round-2 additions: leave the other fixtures untouched
@@ -305,9 +371,12 @@ if __name__ == "__main__":
         gauss_t_cases(gold)
     elif len(sys.argv) > 1 and sys.argv[1] == "--set-b":
         set_b_cases(gold)
+    elif len(sys.argv) > 1 and sys.argv[1] == "--combinations":
+        combination_cases(gold)
     else:
         main()
         hessian_cases(gold)
         intpol_cases(gold)
         gauss_t_cases(gold)
         set_b_cases(gold)
+        combination_cases(gold)
