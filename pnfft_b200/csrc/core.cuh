@@ -150,6 +150,10 @@ inline CUtensorMap make_grid_tmap(void *grid, const Layout &L, int ncomp, int bx
   return tm;
 }
 
+}  // namespace pnb
+#include "direct.cuh"
+namespace pnb {
+
 // ---------------------------------------------------------------------------------------------
 template <class R> struct Core {
   typedef Plan<R> P;
@@ -1717,7 +1721,12 @@ template <class R> struct Core {
   static void trafo(P *p, Nd *nd, unsigned cf) {
     if (!p) return;
     if (!nd && !(cf & C_OMIT_CONV)) return;
-    if (cf & C_DIRECT) { fprintf(stderr, "pnfft-b200: PNFFT_COMPUTE_DIRECT (slow NDFT) is not part of the accelerated path\n"); return; }
+    if (cf & C_DIRECT) {       // the slow NDFT (reference api/api-basic.c:224-231): csrc/direct.cuh
+      if (!nd) return;
+      if (!p->f_hat) { fprintf(stderr, "pnfft-b200: f_hat is not set\n"); return; }
+      Direct<R>::trafo(p, nd, cf);
+      return;
+    }
     cudaStream_t st = p->stream;
     const Layout &L = p->L;
     const size_t nloc = (size_t)local_N_total(p);
@@ -1899,7 +1908,16 @@ template <class R> struct Core {
   static void adj(P *p, Nd *nd, unsigned cf) {
     if (!p) return;
     if (!nd && !(cf & C_OMIT_CONV)) return;
-    if (cf & C_DIRECT) { fprintf(stderr, "pnfft-b200: PNFFT_COMPUTE_DIRECT (slow NDFT) is not part of the accelerated path\n"); return; }
+    if (cf & C_DIRECT) {       // the slow adjoint NDFT (reference api/api-basic.c:355-365): csrc/direct.cuh
+      if (!nd) return;
+      if (!p->f_hat) { fprintf(stderr, "pnfft-b200: f_hat is not set\n"); return; }
+      if (!(cf & C_ACCUMULATED)) {
+        const size_t bytes = sizeof(C) * (size_t)local_N_total(p);
+        if (is_device_ptr(p->f_hat)) PNB_CUDA(cudaMemset(p->f_hat, 0, bytes)); else memset(p->f_hat, 0, bytes);
+      }
+      Direct<R>::adj(p, nd, cf);
+      return;
+    }
     cudaStream_t st = p->stream;
     const Layout &L = p->L;
     const size_t nloc = (size_t)local_N_total(p);
@@ -1910,7 +1928,7 @@ template <class R> struct Core {
     const size_t M = nd ? (size_t)nd->local_M : 0;
     const int npass = (p->pnfft_flags & F_INTERLACED) ? 2 : 1;   // reference api-basic.c:367-374
     if ((cf & C_HESSIAN_F) && !p->warned_hessian) {
-      fprintf(stderr, "pnfft-b200: PNFFT_COMPUTE_HESSIAN_F is not part of the accelerated path; hessian_f is ignored\n");
+      fprintf(stderr, "pnfft-b200: pnfft_adj has no Hessian part (as in the reference); PNFFT_COMPUTE_HESSIAN_F is ignored\n");
       p->warned_hessian = true;
     }
     rec(p, 0);

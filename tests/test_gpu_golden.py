@@ -142,6 +142,42 @@ def test_combination_golden(case, variant):
     assert rel_l2(fh, g["out_f_hat"]) <= tol
 
 
+DCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "d_*.npz")))
+
+
+@pytest.mark.parametrize("case", DCASES)
+def test_direct_ndft_golden(case):
+    """PNFFT_COMPUTE_DIRECT (reference kernel/ndft-parallel.c:377-722, csrc/direct.cuh): the slow NDFT and its adjoint the
+    reference's drivers compare the fast transform with -- f, grad_f, hessian_f, c2c / c2r, transposed f_hat, float,
+    PNFFT_COMPUTE_ACCUMULATED (the direct trafo overwrites its outputs whatever the flag says, the adjoint adds to f_hat).
+    The c2r gradient of the reference's NDFT has the wrong sign (:517-519, :597); the product returns the derivative of
+    the direct f, so that comparison flips the fixture's sign (tests/test_oracle.py::test_direct_fixtures pins the algebra)."""
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    single, c2r = bool(g["single"]), bool(g["c2r"])
+    tol = 1e-5 if single else 1e-13
+    N, n, x_max, acc = fixture_kwargs(g)
+    D = A.COMPUTE_DIRECT
+    run = Run1(N, g["x"], n=n, m=int(g["m"]), flags=int(g["flags"]), c2r=c2r, single=single, x_max=x_max)
+    before = run.plan.kernel_launches()
+    if acc:
+        run.f[...] = g["f0"]; run.g[...] = g["grad_f0"]
+        f, gr, h = run.trafo_hessian(g["f_hat"], F | G | A.COMPUTE_HESSIAN_F | D | A.COMPUTE_ACCUMULATED)
+        fh = run.adj(g["f"], g["grad_f"], F | G | D | A.COMPUTE_ACCUMULATED, f_hat0=g["f_hat0"])
+    else:
+        f, gr, h = run.trafo_hessian(g["f_hat"], F | G | A.COMPUTE_HESSIAN_F | D)
+        fh = run.adj(g["f"], g["grad_f"], F | G | D)
+    assert run.plan.kernel_launches() - before == 3      # NDFT kernel + store, adjoint kernel: nothing of the fast path ran
+    # the fast transform of the same plan agrees with the slow one to the method's accuracy at m = 4
+    ff, _ = run.trafo(g["f_hat"], F)
+    run.close()
+    assert rel_l2(f, g["out_f"]) <= tol
+    assert rel_l2(gr, (-1 if c2r else 1) * g["out_grad_f"]) <= tol
+    assert rel_l2(h, g["out_hessian_f"]) <= tol
+    assert rel_l2(fh, g["out_f_hat"]) <= tol
+    if not c2r:      # (random half spectra are not Hermitian on the planes k2 = 0, -N2/2: the two c2r transforms read them differently)
+        assert rel_l2(ff, f) <= 1e-4
+
+
 BCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "b_*.npz")))
 
 

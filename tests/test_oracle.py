@@ -325,3 +325,70 @@ def test_combination_fixtures_reproduce(case):
     if cf & 2:
         assert rel_l2(t["grad_f"], g["out_grad_f"]) <= tol
     assert rel_l2(a["f_hat"], g["out_f_hat"]) <= tol
+
+
+DCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "d_*.npz")))
+
+
+def test_direct_golden_present():
+    assert len(DCASES) == 9
+
+
+@pytest.mark.parametrize("case", DCASES)
+def test_direct_fixtures(case):
+    """PNFFT_COMPUTE_DIRECT fixtures (tools/make_golden.py --direct).  (i) The compiled reference, where available, reproduces
+    them bit for bit.  (ii) The algebra csrc/direct.cuh implements, restated in numpy, agrees with them: plain sums for
+    c2c; for c2r the half spectrum k2 in [-N2/2, 0] with weight 2, the origin once, the self-conjugate / redundant
+    coefficients of the planes k2 = 0, -N2/2 left out by the reference's rule applied to the loop variables in MEMORY
+    order (kernel/ndft-parallel.c:356-374), outputs overwritten by the trafo, f_hat added to by the adjoint -- and the c2r
+    gradient with the sign of the derivative, which is MINUS the reference's (:517-519, :597)."""
+    from tests.util import fixture_kwargs
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    single, c2r = bool(g["single"]), bool(g["c2r"])
+    N, n, x_max, acc = fixture_kwargs(g)
+    flags = int(g["flags"])
+    if refdrv.available(single):
+        ref = refdrv.get(single)
+        kw = dict(n=n, m=int(g["m"]), pnfft_flags=flags, c2r=c2r, x_max=x_max)
+        if acc:
+            t = ref.trafo(N, g["x"], g["f_hat"], f=g["f0"], grad_f=g["grad_f0"], compute_flags=7 | 8 | 16, **kw)
+            a = ref.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], f_hat=g["f_hat0"], compute_flags=3 | 8 | 16, **kw)
+        else:
+            t = ref.trafo(N, g["x"], g["f_hat"], compute_flags=7 | 8, **kw)
+            a = ref.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], compute_flags=3 | 8, **kw)
+        assert np.array_equal(t["f"], g["out_f"]) and np.array_equal(t["grad_f"], g["out_grad_f"])
+        assert np.array_equal(t["hessian_f"], g["out_hessian_f"]) and np.array_equal(a["f_hat"], g["out_f_hat"])
+    x, fh = g["x"].astype(np.float64), g["f_hat"].astype(np.complex128)
+    k = [np.arange(-v // 2, v // 2) for v in N]
+    if c2r:
+        k[2] = np.arange(-N[2] // 2, 1)
+    K = np.meshgrid(*k, indexing="ij")
+    v = np.exp(-2j * np.pi * sum(x[:, t, None, None, None] * K[t] for t in range(3))) * fh
+    pairs = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+    if c2r:
+        ax = (1, 2, 0) if flags & (1 << 11) else (0, 1, 2)
+        L, Nn = [K[a] for a in ax], [N[a] for a in ax]
+        e = [(L[i] == 0) | (L[i] == -(Nn[i] // 2)) for i in range(3)]
+        w = np.full(K[0].shape, 2.0)
+        w[e[0] & e[1] & e[2]] = 0
+        w[e[2] & (L[1] > 0)] = 0
+        w[e[2] & e[1] & (L[0] > 0)] = 0
+        w[(K[0] == 0) & (K[1] == 0) & (K[2] == 0)] = 1
+        v = v * w
+        f = v.sum((1, 2, 3)).real
+        grad = np.stack([2 * np.pi * (K[t] * v).sum((1, 2, 3)).imag for t in range(3)], 1)
+        hess = np.stack([-4 * np.pi ** 2 * (K[a] * K[b] * v).sum((1, 2, 3)).real for a, b in pairs], 1)
+    else:
+        f = v.sum((1, 2, 3))
+        grad = np.stack([-2j * np.pi * (K[t] * v).sum((1, 2, 3)) for t in range(3)], 1)
+        hess = np.stack([-4 * np.pi ** 2 * (K[a] * K[b] * v).sum((1, 2, 3)) for a, b in pairs], 1)
+    ff, gg = g["f"].astype(np.complex128), g["grad_f"].astype(np.complex128)
+    wj = ff[:, None, None, None] + 2j * np.pi * sum(gg[:, t, None, None, None] * K[t] for t in range(3))
+    fa = (wj * np.exp(2j * np.pi * sum(x[:, t, None, None, None] * K[t] for t in range(3)))).sum(0)
+    if acc:
+        fa = fa + g["f_hat0"]
+    tol = 1e-5 if single else 1e-13
+    assert rel_l2(g["out_f"], f) <= tol
+    assert rel_l2(g["out_grad_f"], (-1 if c2r else 1) * grad) <= tol
+    assert rel_l2(g["out_hessian_f"], hess) <= tol
+    assert rel_l2(g["out_f_hat"], fa) <= tol

@@ -361,6 +361,48 @@ def combination_cases(out):
     return names
 
 
+def direct_cases(out):
+    """PNFFT_COMPUTE_DIRECT (reference kernel/ndft-parallel.c:377-722): the direct NDFT and its adjoint, f / grad_f / hessian_f,
+    c2c and c2r, transposed f_hat, float, PNFFT_COMPUTE_ACCUMULATED (ignored by the direct trafo, honoured by the adjoint)."""
+    names = []
+    seed = 2500
+    Ns, Nt, nt, xm = (8, 12, 10), (12, 16, 10), (24, 32, 20), (0.3, 0.25, 0.5)
+    for name, N, n, x_max, flags, c2r, single, acc in [
+            ("d_c2c_d", Ns, None, None, 0, False, False, False),
+            ("d_tr_c2c_d", Ns, None, None, TRANSPOSED, False, False, False),
+            ("d_c2r_d", Ns, None, None, 0, True, False, False),
+            ("d_tr_c2r_d", Ns, None, None, TRANSPOSED, True, False, False),
+            ("d_torus_c2c_d", Nt, nt, xm, 0, False, False, False),
+            ("d_acc_c2c_d", Ns, None, None, 0, False, False, True),
+            ("d_acc_c2r_d", Ns, None, None, 0, True, False, True),
+            ("d_c2c_f", Ns, None, None, 0, False, True, False),
+            ("d_c2r_f", Ns, None, None, 0, True, True, False)]:
+        ref = refdrv.get(single)
+        seed += 1
+        M = 60
+        x, fh, f, g = inputs(N, M, seed, c2r, single)
+        rdt = np.float32 if single else np.float64
+        x_max_ = tuple(x_max) if x_max is not None else (0.5, 0.5, 0.5)
+        x = (x * (2 * np.array(x_max_))).astype(rdt)
+        n_ = tuple(n) if n is not None else tuple(2 * v for v in N)
+        kw = dict(n=n_, m=4, pnfft_flags=flags, c2r=c2r, x_max=x_max_)
+        extra = {}
+        if acc:
+            f0 = (f[::-1] * 0.5).copy(); g0 = (g[::-1] * 0.25).copy(); fh0 = (fh[::-1, ::-1, ::-1] * 0.125).copy()
+            rt = ref.trafo(N, x, fh, f=f0, grad_f=g0, compute_flags=7 | 8 | ACC, **kw)
+            ra = ref.adj(N, x, f=f, grad_f=g, f_hat=fh0, compute_flags=3 | 8 | ACC, **kw)
+            extra = dict(acc=True, f0=f0, grad_f0=g0, f_hat0=fh0)
+        else:
+            rt = ref.trafo(N, x, fh, compute_flags=7 | 8, **kw)
+            ra = ref.adj(N, x, f=f, grad_f=g, compute_flags=3 | 8, **kw)
+        np.savez_compressed(os.path.join(out, name + ".npz"), N=np.array(N), n=np.array(n_), x_max=np.array(x_max_), m=4, flags=flags,
+                            c2r=c2r, single=single, x=x, f_hat=fh, f=f, grad_f=g, out_f=rt["f"], out_grad_f=rt["grad_f"],
+                            out_hessian_f=rt["hessian_f"], out_f_hat=ra["f_hat"], **extra)
+        names.append(name)
+    print("wrote %d direct NDFT cases" % len(names))
+    return names
+
+
 if __name__ == "__main__":
     gold = os.path.join(ROOT, "tests", "golden")
     if len(sys.argv) > 1 and sys.argv[1] == "--hessian":       # round-2 additions: leave the other fixtures untouched
@@ -373,6 +415,8 @@ if __name__ == "__main__":
         set_b_cases(gold)
     elif len(sys.argv) > 1 and sys.argv[1] == "--combinations":
         combination_cases(gold)
+    elif len(sys.argv) > 1 and sys.argv[1] == "--direct":
+        direct_cases(gold)
     else:
         main()
         hessian_cases(gold)
@@ -380,3 +424,4 @@ if __name__ == "__main__":
         gauss_t_cases(gold)
         set_b_cases(gold)
         combination_cases(gold)
+        direct_cases(gold)
