@@ -704,3 +704,24 @@ def test_reference_drivers():
     assert errs and max(errs) < 1e-10, out[-2000:]
     out = _run_driver("pnfft_test", [], rc_ok=(0, 1))   # takes no options: its 2x2x2 mesh is refused with one rank,
     assert "Procmesh" in out or "PNFFT Results" in out   # through pnfft_create_procmesh's non-zero return (util/util.c:23-40)
+
+
+def test_reference_ndft_drivers():
+    """The reference's NDFT comparison programs, unmodified, on the product library (PNFFT_COMPUTE_DIRECT, csrc/direct.cuh):
+    c2c NDFT against c2r NDFT on Hermitian input (tests/check_trafo_vs_ndft_c2r.c:157-175), the c2r adjoint NFFT against
+    the adjoint NDFT (tests/check_adj_vs_ndft_c2r.c:150-178 -- with the reference's own library this one exposes its c2r
+    spreading defect), the float and the transposed-f_hat NFFT against the NDFT."""
+    import re
+    out = _run_driver("check_trafo_vs_ndft_c2r", ["-pnfft_np", "1", "1", "-pnfft_N", "16", "16", "16"])
+    errs = [float(v) for v in re.findall(r"max error between c2c pndft and c2r pndft:\s*([0-9.eE+-]+)", out)]
+    assert errs and max(errs) < 1e-9, out[-2000:]
+    out = _run_driver("check_adj_vs_ndft_c2r", ["-pnfft_np", "1", "1", "-pnfft_N", "16", "16", "16"])
+    errs = [float(v) for v in re.findall(r"relative error =\s*([0-9.eE+-]+)", out)]
+    assert errs and max(errs) < 1e-7, out[-2000:]
+    out = _run_driver("check_trafo_vs_ndft_transposed_2d", ["-pnfft_np", "1", "1", "-pnfft_N", "16", "16", "16"])
+    errs = [float(v) for v in re.findall(r"relative error =\s*([0-9.eE+-]+)", out)]
+    assert errs and max(errs) < 1e-7, out[-2000:]
+    # (-pnfft_m 8: this driver's own default, a Gaussian with m = 18, is beyond the library's cutoff limit of 16; measured 2.8e-6)
+    out = _run_driver("check_trafo_vs_ndft_float", ["-pnfft_np", "1", "1", "1", "-pnfft_N", "16", "16", "16", "-pnfft_m", "8"])
+    errs = [float(v) for v in re.findall(r"relative error =\s*([0-9.eE+-]+)", out)]
+    assert errs and max(errs) < 1e-3, out[-2000:]
