@@ -199,6 +199,9 @@ typedef float pnfftf_complex[2];
   void PNX(b200_phi_hat_host)(unsigned pnfft_flags, ptrdiff_t N, ptrdiff_t n, R b, int m, const ptrdiff_t *k, ptrdiff_t len, int inverse, R *out); \
   /* host evaluation of pnfft_psi (which = 0), pnfft_dpsi (1), pnfft_ddpsi (2) at offsets x[len] for the window of pnfft_flags */ \
   void PNX(b200_psi_host)(unsigned pnfft_flags, ptrdiff_t N, ptrdiff_t n, R b, int m, int which, const R *x, ptrdiff_t len, R *out); \
+  /* host-only: the f_hat block of rank pid of a p0 x p1 mesh as the direct NDFT exchanges it, memory order:            \
+   * out12 = { len[3], start[3], axis[3], N_of_axis[3] } */                                                             \
+  void PNX(b200_direct_block)(const ptrdiff_t *N, const ptrdiff_t *n, int m, int p0, int p1, int pid, unsigned pnfft_flags, int c2r, int *out12); \
   /* host-only self check of the pencil FFT's composed "own chunk" maps for rank (c0, c1) of a p0 x p1 \
    * mesh: self transfers checked, -1 on a mismatch, -2 if one did not compose (no GPU needed) */       \
   int PNX(b200_check_self_maps)(const ptrdiff_t *N, const ptrdiff_t *n, int m, int p0, int p1, int c0, int c1, int c2r); \

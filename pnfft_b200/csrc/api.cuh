@@ -518,6 +518,15 @@ void PNX(b200_phi_hat_host)(unsigned pnfft_flags, INT N, INT n, RT b, int m, con
   const RT bb = b > 0 ? b : pnb::window_shape<RT>(kind, m, (RT)n / (RT)N);
   for (INT i = 0; i < len; i++) out[i] = pnb::phi_hat_any<RT>(hat, (long)k[i], (long)n, bb, m, inverse != 0);
 }
+// Host-only: the f_hat block the direct NDFT (csrc/direct.cuh) broadcasts for / reduces to rank pid of a p0 x p1 mesh, in
+// memory order: out = { len[3], start[3], axis[3], N_of_axis[3] }.  For the CPU test suite (against the golden layouts).
+void PNX(b200_direct_block)(const INT *N, const INT *n, int m, int p0, int p1, int pid, unsigned pnfft_flags, int c2r, int *out12) {
+  pnb::Mesh M;
+  M.np[0] = p0; M.np[1] = p1; M.size = p0 * p1;
+  const RT xm[3] = {(RT)0.5, (RT)0.5, (RT)0.5};
+  const pnb::DirectBlock B = pnb::Direct<RT>::block_of_mesh(M, N, n, xm, m, c2r != 0, pnfft_flags, pid);
+  for (int q = 0; q < 3; q++) { out12[q] = B.len[q]; out12[3 + q] = B.start[q]; out12[6 + q] = B.axis[q]; out12[9 + q] = B.Nax[q]; }
+}
 // Host-only check of the pencil FFT's composed self maps (fftpipe.cuh: compose_self_map) for one rank of a p0 x p1 mesh:
 // every re-distribution stage is emulated on index arrays, once through pack -> chunk -> unpack and once through the
 // composed map, forward and backward.  Returns the number of self transfers checked, -1 on a mismatch, -2 if a self

@@ -176,12 +176,16 @@ template <class R> struct Direct {
   typedef Plan<R> P;
   typedef Nodes<R> Nd;
 
+  // the f_hat block of rank pid of the mesh, in memory order (what that rank's plan holds: reference
+  // local_block_internal, kernel/ndft-parallel.c:416-419)
   static DirectBlock block_of(const P *p, int pid) {
-    Mesh mesh = p->mesh;
+    R xm[3] = {p->x_max[0], p->x_max[1], p->x_max[2]};
+    return block_of_mesh(p->mesh, p->L.N, p->L.n, xm, p->L.m, p->L.c2r, p->pnfft_flags, pid);
+  }
+  static DirectBlock block_of_mesh(Mesh mesh, const INT *N, const INT *n, const R *xm, int m, bool c2r, unsigned flags, int pid) {
     mesh.co[0] = pid / mesh.np[1]; mesh.co[1] = pid % mesh.np[1]; mesh.rank = pid;
     Layout L;
-    R xm[3] = {p->x_max[0], p->x_max[1], p->x_max[2]};
-    compute_layout<R>(L, mesh, p->L.N, p->L.n, xm, p->L.m, p->L.c2r, p->pnfft_flags);
+    compute_layout<R>(L, mesh, N, n, xm, m, c2r, flags);
     DirectBlock B;
     const int ax[3] = {L.transposed ? 1 : 0, L.transposed ? 2 : 1, L.transposed ? 0 : 2};
     for (int q = 0; q < 3; q++) {

@@ -161,3 +161,34 @@ def test_column_pieces_partition_the_column(dist, target):
                 assert max(pieces) <= total / want + per_chunk.max()       # equal counts up to one sub-chunk
             if want == 1:
                 assert pieces == [total]                                   # a light column stays whole
+
+
+def test_direct_ndft_blocks_match_golden_layouts():
+    """The direct NDFT (csrc/direct.cuh) walks over every rank's f_hat block: broadcast in pnfft_trafo, reduced to its owner in
+    pnfft_adj (reference kernel/ndft-parallel.c:413-424, 630-641).  The block geometry it derives for rank pid of a mesh --
+    host code, probed through pnfft_b200_direct_block -- equals the reference's local_N / local_N_start of that rank for
+    1x1 .. 2x4 meshes, even / ragged sizes, c2c / c2r, natural and PNFFT_TRANSPOSED_F_HAT order (memory order k1, k2, k0)."""
+    import ctypes as C
+    fn = A.lib().pnfft_b200_direct_block
+    fn.restype = None
+    I3 = C.c_ssize_t * 3
+    fn.argtypes = [I3, I3, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int * 12]
+    checked = 0
+    for fname in ("layouts.npz", "layouts_r2.npz"):
+        L = np.load(os.path.join(GOLD, fname))
+        for key in sorted(k[:-4] for k in L.files if k.endswith("_cfg")):
+            cfg = L[key + "_cfg"]
+            N, n, m, c2r, mesh = [int(v) for v in cfg[0:3]], [int(v) for v in cfg[3:6]], int(cfg[6]), int(cfg[7]), (int(cfg[8]), int(cfg[9]))
+            flags = int(cfg[10]) if len(cfg) > 10 else 0
+            ax = (1, 2, 0) if flags & A.TRANSPOSED_F_HAT else (0, 1, 2)
+            lN, lNs = L[key + "_local_N"].reshape(-1, 3), L[key + "_local_N_start"].reshape(-1, 3)
+            for pid in range(mesh[0] * mesh[1]):
+                out = (C.c_int * 12)()
+                fn(I3(*N), I3(*n), m, mesh[0], mesh[1], pid, flags, c2r, out)
+                o = list(out)
+                assert o[6:9] == list(ax), key
+                assert o[0:3] == [int(lN[pid][a]) for a in ax], (key, pid)
+                assert o[3:6] == [int(lNs[pid][a]) for a in ax], (key, pid)
+                assert o[9:12] == [N[a] for a in ax], key
+                checked += 1
+    assert checked >= 48 * 3
