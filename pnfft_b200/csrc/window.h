@@ -396,36 +396,34 @@ template <class R> PNB_HD R window_ddtap(int kind, R y, R n, R b, int m, R psi, 
 // vertical path t = a + i s,  erf(a + i c) = erf(a) + 2/sqrt(pi) * Int_0^c exp(s^2 - a^2) (sin(2 a s) + i cos(2 a s)) ds,
 // the real part integrated by composite 32-point Gauss-Legendre in long double (the integrand is entire; panels of at
 // most 0.5 in s and 8 rad in phase).  Even in c.
-inline const long double *gauss_legendre_32(bool weights) {
-  static long double xs[32], ws[32];
-  static const bool ready = [] {
+struct GaussLegendre32 {     // nodes and weights on [-1, 1]: Newton's iteration on the Legendre recurrence, once per process
+  long double x[32], w[32];
+  GaussLegendre32() {
     const int n = 32;
     const long double pi = 3.14159265358979323846264338327950288L;
     for (int i = 0; i < n; i++) {
-      long double x = cosl(pi * ((long double)i + 0.75L) / ((long double)n + 0.5L)), dp = 1.0L;
+      long double z = cosl(pi * ((long double)i + 0.75L) / ((long double)n + 0.5L)), dp = 1.0L;
       for (int it = 0; it < 100; it++) {
-        long double p0 = 1.0L, p1 = x;                     // Legendre recurrence up to P_n(x)
-        for (int k = 2; k <= n; k++) { const long double pk = (((long double)(2 * k - 1)) * x * p1 - ((long double)(k - 1)) * p0) / (long double)k; p0 = p1; p1 = pk; }
-        dp = (long double)n * (x * p1 - p0) / (x * x - 1.0L);
-        const long double dx = p1 / dp;
-        x -= dx;
-        if (fabsl(dx) < 1e-19L) break;
+        const long double pn = legendre(n, z, &dp);
+        const long double dz = pn / dp;
+        z -= dz;
+        if (fabsl(dz) < 1e-19L) break;
       }
-      {
-        long double p0 = 1.0L, p1 = x;
-        for (int k = 2; k <= n; k++) { const long double pk = (((long double)(2 * k - 1)) * x * p1 - ((long double)(k - 1)) * p0) / (long double)k; p0 = p1; p1 = pk; }
-        dp = (long double)n * (x * p1 - p0) / (x * x - 1.0L);
-      }
-      xs[i] = x;
-      ws[i] = 2.0L / ((1.0L - x * x) * dp * dp);
+      (void)legendre(n, z, &dp);
+      x[i] = z;
+      w[i] = 2.0L / ((1.0L - z * z) * dp * dp);
     }
-    return true;
-  }();
-  (void)ready;
-  return weights ? ws : xs;
-}
+  }
+  static long double legendre(int n, long double z, long double *deriv) {      // P_n(z) and P_n'(z)
+    long double p0 = 1.0L, p1 = z;
+    for (int k = 2; k <= n; k++) { const long double pk = (((long double)(2 * k - 1)) * z * p1 - ((long double)(k - 1)) * p0) / (long double)k; p0 = p1; p1 = pk; }
+    *deriv = (long double)n * (z * p1 - p0) / (z * z - 1.0L);
+    return p1;
+  }
+};
+inline const GaussLegendre32 &gauss_legendre_32() { static const GaussLegendre32 t; return t; }
 inline long double re_erf_complex(long double a, long double c) {
-  const long double *xs = gauss_legendre_32(false), *ws = gauss_legendre_32(true);
+  const long double *xs = gauss_legendre_32().x, *ws = gauss_legendre_32().w;
   const long double ac = fabsl(c);
   long panels_l = (long)ceill(ac / 0.5L), panels_p = (long)ceill(2.0L * fabsl(a) * ac / 8.0L);
   long panels = panels_l > panels_p ? panels_l : panels_p;
