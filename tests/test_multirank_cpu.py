@@ -45,6 +45,19 @@ def _worker(rank, world, mesh, port, q):
         b = (C.c_int * 1)(1234 if rank == 0 else 0)
         lib.pnb_MPI_Bcast(b, 1, 2, 0, comm)
         assert b[0] == 1234
+        # the exchange pattern of the direct NDFT across ranks (csrc/direct.cuh; reference kernel/ndft-parallel.c:424, 714):
+        # every rank in turn broadcasts a block of bytes / receives the sum of all ranks' doubles
+        for root in range(world):
+            blk = (C.c_ubyte * 37)(*([(7 * root + i) % 251 for i in range(37)] if rank == root else [0] * 37))
+            lib.pnb_MPI_Bcast(blk, 37, 8, root, comm)                 # MPI_BYTE
+            assert list(blk) == [(7 * root + i) % 251 for i in range(37)]
+            part = (C.c_double * 3)(rank + 0.5, root, -2.0 * rank)
+            tot = (C.c_double * 3)(-1.0, -1.0, -1.0)
+            lib.pnb_MPI_Reduce(part, tot, 3, 6, 1, root, comm)        # MPI_DOUBLE, MPI_SUM
+            if rank == root:
+                assert list(tot) == [world * (world - 1) / 2 + 0.5 * world, float(root * world), -float(world * (world - 1))]
+            else:
+                assert list(tot) == [-1.0, -1.0, -1.0]
         L = np.load(os.path.join(GOLD, "layouts.npz"))
         res = []
         for tag in ("even", "ragged", "torus"):
