@@ -104,8 +104,10 @@ class PortLib:
         fo = np.zeros(M, ft) if f is None else np.ascontiguousarray(f, ft).copy()
         go = np.zeros((M, 3), ft) if grad_f is None else np.ascontiguousarray(grad_f, ft).copy()
         c = self._cfg(N, n, m, x_max, pnfft_flags, c2r)
-        self._fn("trafo")(C.byref(c), INT(M), self._p(xs), self._p(fh), self._p(fo), self._p(go), C.c_uint(compute_flags))
-        return dict(f=fo, grad_f=go, timers=None)
+        ho = np.zeros((M, 6), ft) if (compute_flags & 4) else None     # PNFFT_COMPUTE_HESSIAN_F: xx, xy, xz, yy, yz, zz
+        self._fn("trafo_h")(C.byref(c), INT(M), self._p(xs), self._p(fh), self._p(fo), self._p(go),
+                            self._p(ho) if ho is not None else None, C.c_uint(compute_flags))
+        return dict(f=fo, grad_f=go, hessian_f=ho, timers=None)
 
     def adj(self, N, x, f=None, grad_f=None, n=None, m=6, np_mesh=(1, 1), x_max=(0.5, 0.5, 0.5), pnfft_flags=0,
             compute_flags=1, c2r=False, f_hat=None, **_):

@@ -244,9 +244,17 @@ def test_hessian_and_intpol_golden_present():
 def test_hessian_intpol_fixtures_reproduce(case):
     """Round-2 fixtures (PNFFT_COMPUTE_HESSIAN_F, PNFFT_PRE_*_PSI interpolation): where the compiled reference is available
     it reproduces them bit for bit (the fixtures are its own output; this pins the generator script and the driver's
-    hessian_f plumbing).  The clean-room port does not cover these two 'next' rows of SURVEY 8f."""
+    hessian_f plumbing).  The clean-room port restates the Hessian (analytic second derivatives of all windows and the ik
+    variant) and is pinned by the h_* fixtures here; it does not restate the interpolation tables."""
     g = np.load(os.path.join(GOLD, case + ".npz"))
     single = bool(g["single"])
+    if case.startswith("h_"):
+        po = checker.port(single)
+        t = po.trafo(tuple(int(v) for v in g["N"]), g["x"], g["f_hat"], m=int(g["m"]), pnfft_flags=int(g["flags"]), compute_flags=7,
+                     c2r=bool(g["c2r"]))
+        tol = 1e-5 if single else 1e-13
+        assert rel_l2(t["f"], g["out_f"]) <= tol and rel_l2(t["grad_f"], g["out_grad_f"]) <= (1e-4 if (single and "sinc_power" in case) else tol)
+        assert rel_l2(t["hessian_f"], g["out_hessian_f"]) <= (2e-4 if single else 1e-13)
     if not refdrv.available(single):
         pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
     ref = refdrv.get(single)
@@ -303,7 +311,7 @@ def test_combination_golden_present():
 @pytest.mark.parametrize("case", CCASES)
 def test_combination_fixtures_reproduce(case):
     """Combination fixtures (tools/make_golden.py --combinations): the compiled reference, where it is available, reproduces
-    them bit for bit; the clean-room port agrees with them where it covers the flags (no Hessian, no PRE_PSI tables)."""
+    them bit for bit; the clean-room port agrees with them too (it evaluates the windows on the fly where the reference read its PRE_PSI tables)."""
     from tests.util import fixture_kwargs
     g = np.load(os.path.join(GOLD, case + ".npz"))
     single, c2r = bool(g["single"]), bool(g["c2r"])
@@ -319,9 +327,11 @@ def test_combination_fixtures_reproduce(case):
             assert np.array_equal(t["hessian_f"], g["out_hessian_f"])
     tol = 1e-5 if single else 1e-13
     po = checker.port(single)
-    t = po.trafo(N, g["x"], g["f_hat"], compute_flags=cf, **kw)
+    t = po.trafo(N, g["x"], g["f_hat"], compute_flags=cf | (4 if hess else 0), **kw)
     a = po.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], compute_flags=cf, **kw)
     assert rel_l2(t["f"], g["out_f"]) <= tol
+    if hess:
+        assert rel_l2(t["hessian_f"], g["out_hessian_f"]) <= tol
     if cf & 2:
         assert rel_l2(t["grad_f"], g["out_grad_f"]) <= tol
     assert rel_l2(a["f_hat"], g["out_f_hat"]) <= tol
