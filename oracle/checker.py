@@ -18,7 +18,7 @@ INT = C.c_ssize_t
 
 class _Cfg(C.Structure):
     _fields_ = [("N", INT * 3), ("n", INT * 3), ("x_max", C.c_double * 3), ("m", C.c_int), ("flags", C.c_uint),
-                ("c2r", C.c_int)]
+                ("c2r", C.c_int), ("b", C.c_double * 3)]
 
 
 class PortLib:
@@ -42,8 +42,10 @@ class PortLib:
         f.restype = restype
         return f
 
-    def _cfg(self, N, n, m, x_max, pnfft_flags, c2r):
+    def _cfg(self, N, n, m, x_max, pnfft_flags, c2r, b=None):
         c = _Cfg()
+        if b is not None:          # pnfft_set_b
+            c.b[:] = [float(self.rdt(v)) for v in b]
         c.N[:] = [int(v) for v in N]
         c.n[:] = [int(v) for v in (n if n is not None else [2 * v for v in N])]
         c.x_max[:] = [float(v) for v in x_max]
@@ -96,21 +98,21 @@ class PortLib:
         return np.array([f(C.byref(c), int(dim), INT(int(k))) for k in np.atleast_1d(arg)], self.rdt)
 
     def trafo(self, N, x, f_hat, n=None, m=6, np_mesh=(1, 1), x_max=(0.5, 0.5, 0.5), pnfft_flags=0, compute_flags=1,
-              c2r=False, f=None, grad_f=None, **_):
+              c2r=False, f=None, grad_f=None, b=None, **_):
         xs = np.ascontiguousarray(x, self.rdt)
         M = xs.shape[0]
         ft = self.rdt if c2r else self.cdt
         fh = np.ascontiguousarray(f_hat, self.cdt)
         fo = np.zeros(M, ft) if f is None else np.ascontiguousarray(f, ft).copy()
         go = np.zeros((M, 3), ft) if grad_f is None else np.ascontiguousarray(grad_f, ft).copy()
-        c = self._cfg(N, n, m, x_max, pnfft_flags, c2r)
+        c = self._cfg(N, n, m, x_max, pnfft_flags, c2r, b=b)
         ho = np.zeros((M, 6), ft) if (compute_flags & 4) else None     # PNFFT_COMPUTE_HESSIAN_F: xx, xy, xz, yy, yz, zz
         self._fn("trafo_h")(C.byref(c), INT(M), self._p(xs), self._p(fh), self._p(fo), self._p(go),
                             self._p(ho) if ho is not None else None, C.c_uint(compute_flags))
         return dict(f=fo, grad_f=go, hessian_f=ho, timers=None)
 
     def adj(self, N, x, f=None, grad_f=None, n=None, m=6, np_mesh=(1, 1), x_max=(0.5, 0.5, 0.5), pnfft_flags=0,
-            compute_flags=1, c2r=False, f_hat=None, **_):
+            compute_flags=1, c2r=False, f_hat=None, b=None, **_):
         xs = np.ascontiguousarray(x, self.rdt)
         M = xs.shape[0]
         ft = self.rdt if c2r else self.cdt
@@ -119,7 +121,7 @@ class PortLib:
         fh = np.zeros(shape, self.cdt) if f_hat is None else np.ascontiguousarray(f_hat, self.cdt).reshape(shape).copy()
         fi = np.zeros(M, ft) if f is None else np.ascontiguousarray(f, ft)
         gi = np.zeros((M, 3), ft) if grad_f is None else np.ascontiguousarray(grad_f, ft)
-        c = self._cfg(N, n, m, x_max, pnfft_flags, c2r)
+        c = self._cfg(N, n, m, x_max, pnfft_flags, c2r, b=b)
         self._fn("adj")(C.byref(c), INT(M), self._p(xs), self._p(fi), self._p(gi), self._p(fh), C.c_uint(compute_flags))
         return dict(f_hat=fh, timers=None)
 

@@ -244,17 +244,20 @@ def test_hessian_and_intpol_golden_present():
 def test_hessian_intpol_fixtures_reproduce(case):
     """Round-2 fixtures (PNFFT_COMPUTE_HESSIAN_F, PNFFT_PRE_*_PSI interpolation): where the compiled reference is available
     it reproduces them bit for bit (the fixtures are its own output; this pins the generator script and the driver's
-    hessian_f plumbing).  The clean-room port restates the Hessian (analytic second derivatives of all windows and the ik
-    variant) and is pinned by the h_* fixtures here; it does not restate the interpolation tables."""
+    hessian_f plumbing).  The clean-room port restates both -- analytic second derivatives of all windows, the ik variant, the
+    interpolated window of PNFFT_PRE_{CONST,LIN,CUB}_PSI with the reference's flag promotion -- and is pinned by them here."""
     g = np.load(os.path.join(GOLD, case + ".npz"))
     single = bool(g["single"])
-    if case.startswith("h_"):
-        po = checker.port(single)
-        t = po.trafo(tuple(int(v) for v in g["N"]), g["x"], g["f_hat"], m=int(g["m"]), pnfft_flags=int(g["flags"]), compute_flags=7,
-                     c2r=bool(g["c2r"]))
-        tol = 1e-5 if single else 1e-13
-        assert rel_l2(t["f"], g["out_f"]) <= tol and rel_l2(t["grad_f"], g["out_grad_f"]) <= (1e-4 if (single and "sinc_power" in case) else tol)
-        assert rel_l2(t["hessian_f"], g["out_hessian_f"]) <= (2e-4 if single else 1e-13)
+    po = checker.port(single)
+    Np = tuple(int(v) for v in g["N"])
+    kwp = dict(m=int(g["m"]), pnfft_flags=int(g["flags"]), c2r=bool(g["c2r"]))
+    t = po.trafo(Np, g["x"], g["f_hat"], compute_flags=7, **kwp)
+    tol = 1e-5 if single else 1e-13
+    assert rel_l2(t["f"], g["out_f"]) <= tol and rel_l2(t["grad_f"], g["out_grad_f"]) <= (1e-4 if (single and "sinc_power" in case) else tol)
+    assert rel_l2(t["hessian_f"], g["out_hessian_f"]) <= (2e-4 if single else 1e-13)
+    if case.startswith("i_"):      # the interpolation fixtures also hold the adjoint
+        a = po.adj(Np, g["x"], f=g["f"], grad_f=g["grad_f"], compute_flags=3, **kwp)
+        assert rel_l2(a["f_hat"], g["out_f_hat"]) <= tol
     if not refdrv.available(single):
         pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
     ref = refdrv.get(single)
@@ -287,11 +290,16 @@ def test_set_b_fixtures_reproduce(case):
     bit for bit -- this pins the generator and the driver's b plumbing -- and the default shape gives other values."""
     g = np.load(os.path.join(GOLD, case + ".npz"))
     single = bool(g["single"])
+    kw = dict(m=int(g["m"]), pnfft_flags=int(g["flags"]), compute_flags=3, c2r=bool(g["c2r"]))
+    N = tuple(int(v) for v in g["N"])
+    po = checker.port(single)          # the clean-room port with the same shape parameters
+    tol = 1e-5 if single else 1e-13
+    t = po.trafo(N, g["x"], g["f_hat"], b=tuple(g["b"]), **kw)
+    a = po.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], b=tuple(g["b"]), **kw)
+    assert rel_l2(t["f"], g["out_f"]) <= tol and rel_l2(t["grad_f"], g["out_grad_f"]) <= tol and rel_l2(a["f_hat"], g["out_f_hat"]) <= tol
     if not refdrv.available(single):
         pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
     ref = refdrv.get(single)
-    kw = dict(m=int(g["m"]), pnfft_flags=int(g["flags"]), compute_flags=3, c2r=bool(g["c2r"]))
-    N = tuple(int(v) for v in g["N"])
     t = ref.trafo(N, g["x"], g["f_hat"], b=tuple(g["b"]), **kw)
     a = ref.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], b=tuple(g["b"]), **kw)
     assert np.array_equal(t["f"], g["out_f"]) and np.array_equal(t["grad_f"], g["out_grad_f"])
