@@ -376,6 +376,17 @@ def test_direct_fixtures(case):
             a = ref.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], compute_flags=3 | 8, **kw)
         assert np.array_equal(t["f"], g["out_f"]) and np.array_equal(t["grad_f"], g["out_grad_f"])
         assert np.array_equal(t["hessian_f"], g["out_hessian_f"]) and np.array_equal(a["f_hat"], g["out_f_hat"])
+    # (iii) the clean-room port (oracle/pnfft_oracle.c: direct_trafo / direct_adj) -- the same algebra in C
+    po, sg, tolp = checker.port(single), (-1 if c2r else 1), (1e-5 if single else 1e-13)
+    kwp = dict(n=n, m=int(g["m"]), pnfft_flags=flags, c2r=c2r, x_max=x_max)
+    if acc:
+        tp = po.trafo(N, g["x"], g["f_hat"], f=g["f0"], grad_f=g["grad_f0"], compute_flags=7 | 8 | 16, **kwp)
+        ap = po.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], f_hat=g["f_hat0"], compute_flags=3 | 8 | 16, **kwp)
+    else:
+        tp = po.trafo(N, g["x"], g["f_hat"], compute_flags=7 | 8, **kwp)
+        ap = po.adj(N, g["x"], f=g["f"], grad_f=g["grad_f"], compute_flags=3 | 8, **kwp)
+    assert rel_l2(tp["f"], g["out_f"]) <= tolp and rel_l2(tp["grad_f"], sg * g["out_grad_f"]) <= tolp
+    assert rel_l2(tp["hessian_f"], g["out_hessian_f"]) <= tolp and rel_l2(ap["f_hat"], g["out_f_hat"]) <= tolp
     x, fh = g["x"].astype(np.float64), g["f_hat"].astype(np.complex128)
     k = [np.arange(-v // 2, v // 2) for v in N]
     if c2r:
