@@ -257,7 +257,8 @@ void PNX(vpr_real)(RT *data, INT N, const char *name, MPI_Comm comm) {
 
 double *PNX(get_timer_trafo)(PNX(plan) ths) { return PNX(timer_copy)(AS_PLAN(ths)->timer_trafo); }
 double *PNX(get_timer_adj)(PNX(plan) ths) { return PNX(timer_copy)(AS_PLAN(ths)->timer_adj); }
-void PNX(timer_average)(double *t) { if (t[0] > 0) for (int i = 1; i < PNFFT_TIMER_LENGTH; i++) t[i] /= t[0]; t[0] = t[0] > 0 ? 1 : 0; }
+// reference kernel/timer.c:57-66: the slots after the iteration count are divided by it; the count itself stays
+void PNX(timer_average)(double *t) { if (t[0] < 1.0) return; for (int i = 1; i < PNFFT_TIMER_LENGTH; i++) t[i] /= t[0]; }
 double *PNX(timer_copy)(const double *orig) {
   double *c = (double *)malloc(sizeof(double) * PNFFT_TIMER_LENGTH);
   for (int i = 0; i < PNFFT_TIMER_LENGTH; i++) c[i] = orig[i];

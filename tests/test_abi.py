@@ -192,3 +192,48 @@ def test_direct_ndft_blocks_match_golden_layouts():
                 assert o[9:12] == [N[a] for a in ax], key
                 checked += 1
     assert checked >= 48 * 3
+
+
+def test_input_generators_match_reference():
+    """pnfft_init_x_3d, pnfft_init_x_3d_adv and pnfft_init_f (reference api/api-basic.c:681-718, api/api-adv.c:35-85) draw from
+    rand(): with the same seed the product's host generators return the compiled reference's arrays bit for bit (the reference's
+    drivers seed with srand(myrank) and compare transforms on these inputs)."""
+    import ctypes as C
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libpnfft_ref.so")
+    if not os.path.exists(ref_so):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    libc, ref, L = C.CDLL("libc.so.6"), C.CDLL(ref_so), A.lib()
+    M = 1000
+    D3 = C.c_double * 3
+    lo, up, xm = D3(-0.3, -0.25, 0.1), D3(0.0, 0.25, 0.5), D3(0.3, 0.25, 0.5)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    for seed, call in [(5, lambda lib, out: lib.pnfft_init_x_3d(lo, up, C.c_ssize_t(M), P(out))),
+                       (7, lambda lib, out: lib.pnfft_init_x_3d_adv(lo, up, xm, C.c_ssize_t(M), P(out))),
+                       (9, lambda lib, out: lib.pnfft_init_f(C.c_ssize_t(M), P(out)))]:
+        a, b = np.zeros((M, 3)), np.zeros((M, 3))
+        libc.srand(seed); call(L, a)
+        libc.srand(seed); call(ref, b)
+        assert a.any() and np.array_equal(a, b)
+
+
+def test_timer_utilities_match_reference():
+    """pnfft_timer_add / _copy / _average (reference kernel/timer.c:57-110): same arrays as the compiled reference, including
+    the iteration count left in slot 0 by the average and the untouched array when nothing was counted."""
+    import ctypes as C
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libpnfft_ref.so")
+    if not os.path.exists(ref_so):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    D = C.c_double * 10
+    res = []
+    for lib in (A.lib(), C.CDLL(ref_so)):
+        lib.pnfft_timer_add.restype = C.POINTER(C.c_double)
+        lib.pnfft_timer_copy.restype = C.POINTER(C.c_double)
+        a, b = D(3, 1.5, 0.25, 7, 8, 9, 1, 2, 3, 4), D(2, 0.5, 0.75, 1, 1, 1, 1, 1, 1, 1)
+        s, c = lib.pnfft_timer_add(a, b), lib.pnfft_timer_copy(b)
+        out = [s[i] for i in range(10)] + [c[i] for i in range(10)]
+        lib.pnfft_timer_average(a)
+        z = D(*([0.0] * 10)); z[3] = 5.0
+        lib.pnfft_timer_average(z)
+        res.append(out + list(a) + list(z))
+    assert res[0] == res[1]
+    assert res[0][20] == 3.0 and res[0][21] == 0.5
