@@ -240,19 +240,38 @@ RT PNX(ddpsi)(const PNX(plan) ths, int dim, RT x) {
   return window_at(p->kind, 2, (RT)p->L.n[dim], p->b[dim], p->L.m, x);
 }
 
+// every rank prints its own vector in turn (reference api/api-basic.c:705-780: formats, "Rank r, name" header, nothing for N < 1)
 void PNX(vpr_complex)(CT *data, INT N, const char *name, MPI_Comm comm) {
-  int rank = 0; MPI_Comm_rank(comm, &rank);
-  if (rank) return;
-  printf("%s:", name);
-  for (INT k = 0; k < N; k++) { if (k % 4 == 0) printf("\n%4td.", k / 4); printf(" %.2e+%.2ei,", (double)data[k][0], (double)data[k][1]); }
-  printf("\n");
+  if (N < 1) return;
+  int rank = 0, size = 1;
+  MPI_Comm_size(comm, &size); MPI_Comm_rank(comm, &rank);
+  fflush(stdout);
+  MPI_Barrier(comm);
+  for (int t = 0; t < size; t++) {
+    if (t == rank) {
+      printf("\nRank %d, %s", rank, name);
+      for (INT k = 0; k < N; k++) { if (k % 4 == 0) printf("\n%4td.", k / 4); printf(" %.2e+%.2ei,", (double)data[k][0], (double)data[k][1]); }
+      printf("\n");
+      fflush(stdout);
+    }
+    MPI_Barrier(comm);
+  }
 }
 void PNX(vpr_real)(RT *data, INT N, const char *name, MPI_Comm comm) {
-  int rank = 0; MPI_Comm_rank(comm, &rank);
-  if (rank) return;
-  printf("%s:", name);
-  for (INT k = 0; k < N; k++) { if (k % 8 == 0) printf("\n%4td.", k / 8); printf(" %.2e,", (double)data[k]); }
-  printf("\n");
+  if (N < 1) return;
+  int rank = 0, size = 1;
+  MPI_Comm_size(comm, &size); MPI_Comm_rank(comm, &rank);
+  fflush(stdout);
+  MPI_Barrier(comm);
+  for (int t = 0; t < size; t++) {
+    if (t == rank) {
+      printf("\nRank %d, %s", rank, name);
+      for (INT k = 0; k < N; k++) { if (k % 8 == 0) printf("\n%4td.", k / 8); printf(" %e,", (double)data[k]); }
+      printf("\n");
+      fflush(stdout);
+    }
+    MPI_Barrier(comm);
+  }
 }
 
 double *PNX(get_timer_trafo)(PNX(plan) ths) { return PNX(timer_copy)(AS_PLAN(ths)->timer_trafo); }
@@ -328,11 +347,19 @@ static void apr_block(const RT *data, int ncomp, const INT *local_N, const INT *
     MPI_Barrier(comm);
   }
 }
-void PNX(apr_complex_3d)(CT *data, INT *local_N, INT *local_N_start, unsigned, const char *name, MPI_Comm comm) {
-  apr_block((const RT *)data, 2, local_N, local_N_start, name, comm);
+// with PNFFT_TRANSPOSED_F_HAT the block is stored (k1, k2, k0): extents and starts are rotated into memory order before the
+// walk (reference apr_3d, api/api-basic.c:783-800; the element format is PFFT's there, which is not available)
+static void apr_rotated(const RT *data, int ncomp, const INT *local_N, const INT *local_N_start, unsigned pnfft_flags, const char *name, MPI_Comm comm) {
+  const int shift = (pnfft_flags & PNFFT_TRANSPOSED_F_HAT) ? 1 : 0;
+  INT lN[3], lNs[3];
+  for (int t = 0; t < 3; t++) { lN[t] = local_N[(t + shift) % 3]; lNs[t] = local_N_start[(t + shift) % 3]; }
+  apr_block(data, ncomp, lN, lNs, name, comm);
 }
-void PNX(apr_real_3d)(RT *data, INT *local_N, INT *local_N_start, unsigned, const char *name, MPI_Comm comm) {
-  apr_block(data, 1, local_N, local_N_start, name, comm);
+void PNX(apr_complex_3d)(CT *data, INT *local_N, INT *local_N_start, unsigned pnfft_flags, const char *name, MPI_Comm comm) {
+  apr_rotated((const RT *)data, 2, local_N, local_N_start, pnfft_flags, name, comm);
+}
+void PNX(apr_real_3d)(RT *data, INT *local_N, INT *local_N_start, unsigned pnfft_flags, const char *name, MPI_Comm comm) {
+  apr_rotated(data, 1, local_N, local_N_start, pnfft_flags, name, comm);
 }
 void PNX(get_args)(int argc, char **argv, const char *name, int neededArgs, unsigned type, void *parameter) {
   pfft_get_args(argc, argv, name, neededArgs, type, parameter);

@@ -237,3 +237,76 @@ def test_timer_utilities_match_reference():
         res.append(out + list(a) + list(z))
     assert res[0] == res[1]
     assert res[0][20] == 3.0 and res[0][21] == 0.5
+
+
+@pytest.mark.parametrize("args", [
+    "",
+    "-pnfft_N 8 12 10 -pnfft_m 4 -pnfft_window 0 -pnfft_np 1 2 1",
+    "-pnfft_window 5 -pnfft_intpol 3 -pnfft_interlaced 1 -pnfft_diff_ik 1 -pnfft_tr_f_hat 1 -pnfft_x_max 0.3 0.25 0.5 -pnfft_local_M 77 -pnfft_n 20 30 24",
+    "-pnfft_window 2 -pnfft_fast_gaussian 1 -pnfft_intpol 1 -pnfft_compute_f 0 -pnfft_compute_hessian_f 0 -pnfft_compare_direct 1 -pnfft_debug 1",
+    "-pnfft_window 1 -pnfft_intpol 0 -pnfft_compute_grad_f 0",
+    "-pnfft_window 7 -pnfft_intpol 9"])
+def test_check_init_parameters_matches_reference(args):
+    """pnfft_check_init_parameters (reference api/api-basic.c:820-938), the option parser of the reference's test programs: same
+    sizes, cutoff, plan flags, compute flags, x_max, process mesh and switches as the compiled reference for the same argv,
+    defaults included (window 4 = Kaiser-Bessel, f + grad_f + hessian_f on)."""
+    import ctypes as C
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libpnfft_ref.so")
+    if not os.path.exists(ref_so):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    words = args.split()
+    res = []
+    for lib in (A.lib(), C.CDLL(ref_so)):
+        argv = (C.c_char_p * (len(words) + 1))(b"prog", *[w.encode() for w in words])
+        N, n, lM, m = (C.c_ssize_t * 3)(), (C.c_ssize_t * 3)(), C.c_ssize_t(), C.c_int()
+        pf, cf, xm, mesh, cd, dbg = C.c_uint(), C.c_uint(), (C.c_double * 3)(), (C.c_int * 3)(), C.c_int(0), C.c_int(0)
+        lib.pnfft_check_init_parameters(len(words) + 1, argv, N, n, C.byref(lM), C.byref(m), C.byref(pf), C.byref(cf), xm, mesh,
+                                        C.byref(cd), C.byref(dbg))
+        res.append((list(N), list(n), lM.value, m.value, pf.value, cf.value, list(xm), list(mesh), cd.value, dbg.value))
+    assert res[0] == res[1]
+
+
+def test_print_helpers_follow_reference_formats():
+    """pnfft_vpr_complex / pnfft_vpr_real (reference api/api-basic.c:705-780): every rank prints "Rank r, name" and its vector,
+    four complex numbers as %.2e+%.2ei or eight reals as %e per numbered line, nothing at all for N < 1;
+    pnfft_apr_complex_3d walks a PNFFT_TRANSPOSED_F_HAT block in its memory order (k1, k2, k0) (:783-800).  Host only, one rank."""
+    import subprocess
+    import sys
+    code = r"""
+import ctypes as C, sys
+import numpy as np
+sys.path.insert(0, %r)
+from pnfft_b200 import api as A
+lib = A.lib()
+z = (np.arange(6) * 1.5 + 1j * (np.arange(6) - 3.25)).astype(np.complex128)
+r = (np.arange(11) * 0.375 - 1).astype(np.float64)
+P = lambda a: a.ctypes.data_as(C.c_void_p)
+lib.pnfft_vpr_complex(P(z), C.c_ssize_t(6), b"cv", 1)
+lib.pnfft_vpr_real(P(r), C.c_ssize_t(11), b"rv", 1)
+lib.pnfft_vpr_real(P(r), C.c_ssize_t(0), b"never", 1)
+lN, lNs = (C.c_ssize_t * 3)(3, 1, 2), (C.c_ssize_t * 3)(-1, 0, -2)
+lib.pnfft_apr_complex_3d(P(z), lN, lNs, C.c_uint(1 << 11), b"tr", 1)
+C.CDLL("libc.so.6").fflush(None)
+""" % ROOT
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120,
+                         env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    z = np.arange(6) * 1.5 + 1j * (np.arange(6) - 3.25)
+    r = np.arange(11) * 0.375 - 1
+    want = "\nRank 0, cv"
+    for k in range(6):
+        if k % 4 == 0:
+            want += "\n%4d." % (k // 4)
+        want += " %.2e+%.2ei," % (z[k].real, z[k].imag)
+    want += "\n\nRank 0, rv"
+    for k in range(11):
+        if k % 8 == 0:
+            want += "\n%4d." % (k // 8)
+        want += " %e," % r[k]
+    want += "\n"
+    assert out.stdout.startswith(want), out.stdout
+    rest = out.stdout[len(want):]
+    assert "never" not in rest
+    # transposed block local_N = (3, 1, 2), starts (-1, 0, -2): memory order (k1, k2, k0) = extents (1, 2, 3), starts (0, -2, -1)
+    idx = re.findall(r"\[(-?\d+),(-?\d+),(-?\d+)\]", rest)
+    assert [tuple(int(v) for v in t) for t in idx] == [(0, a, b) for a in (-2, -1) for b in (-1, 0, 1)]
