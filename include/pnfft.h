@@ -202,6 +202,9 @@ typedef float pnfftf_complex[2];
   /* host-only: the f_hat block of rank pid of a p0 x p1 mesh as the direct NDFT exchanges it, memory order:            \
    * out12 = { len[3], start[3], axis[3], N_of_axis[3] } */                                                             \
   void PNX(b200_direct_block)(const ptrdiff_t *N, const ptrdiff_t *n, int m, int p0, int p1, int pid, unsigned pnfft_flags, int c2r, int *out12); \
+  /* host-only: append the report of pnfft_write_average_timer (adv = 0) / _adv (adv != 0) for the given plan data to `name` */ \
+  void PNX(b200_timer_report_host)(const char *name, unsigned pnfft_flags, const ptrdiff_t *N, const ptrdiff_t *n, int m,      \
+                                   const int *np3, const double *timer_trafo, const double *timer_adj, int adv, MPI_Comm comm); \
   /* host-only self check of the pencil FFT's composed "own chunk" maps for rank (c0, c1) of a p0 x p1 \
    * mesh: self transfers checked, -1 on a mismatch, -2 if one did not compose (no GPU needed) */       \
   int PNX(b200_check_self_maps)(const ptrdiff_t *N, const ptrdiff_t *n, int m, int p0, int p1, int c0, int c1, int c2r); \

@@ -298,33 +298,105 @@ void PNX(reset_timer)(PNX(plan) ths) {
   memset(AS_PLAN(ths)->timer_trafo, 0, sizeof(double) * PNFFT_TIMER_LENGTH);
   memset(AS_PLAN(ths)->timer_adj, 0, sizeof(double) * PNFFT_TIMER_LENGTH);
 }
-void PNX(print_average_timer)(const PNX(plan) ths, MPI_Comm comm) {
-  static const char *names[] = {"iter", "whole", "loop_b", "sort_nodes", "gcells", "matrix_b", "matrix_f", "matrix_d", "shift_input", "shift_output"};
-  for (int dir = 0; dir < 2; dir++) {
-    double t[PNFFT_TIMER_LENGTH], mx[PNFFT_TIMER_LENGTH];
-    for (int i = 0; i < PNFFT_TIMER_LENGTH; i++) t[i] = dir ? AS_PLAN(ths)->timer_adj[i] : AS_PLAN(ths)->timer_trafo[i];
-    PNX(timer_average)(t);
-    MPI_Reduce(t, mx, PNFFT_TIMER_LENGTH, MPI_DOUBLE, MPI_MAX, 0, comm);
-    int rank = 0; MPI_Comm_rank(comm, &rank);
-    if (rank == 0) for (int i = 1; i < 8; i++) printf("pnfft_%s_%s = %.3e;\n", dir ? "adj" : "trafo", names[i], mx[i]);
-  }
+// ---- timer reports in the reference's Octave-readable format (kernel/timer.c:139-367): rank 0 writes a legend, one line
+// with the plan's flags and sizes, and the averaged maxima over the ranks under the prefixes pnfft_trf / pnfft_adj, all
+// indexed by log2(procs) + 1.  (The reference appends PFFT's and the ghost-cell plan's own reports in the _adv variants;
+// there is no PFFT here.)
+struct TimerReport {
+  unsigned flags; INT N[3], n[3]; int m, np[3];
+  const double *trafo, *adj;
+};
+static void timer_report_legend(FILE *f) {
+  fprintf(f, "%% N  - NFFT size\n%% n  - FFT size\n%% np - process grid\n%% procs - number of processes\n"
+             "%% pnfft - PNFFT runtime\n%% pfft  - PFFT runtime\n%% index(i) = log(procs(i)) + 1\n");
 }
-void PNX(print_average_timer_adv)(const PNX(plan) ths, MPI_Comm comm) { PNX(print_average_timer)(ths, comm); }
-// same averages appended to a file by rank 0 (reference kernel/timer.c write_average_timer*)
-void PNX(write_average_timer)(const PNX(plan) ths, const char *name, MPI_Comm comm) {
-  static const char *names[] = {"iter", "whole", "loop_b", "sort_nodes", "gcells", "matrix_b", "matrix_f", "matrix_d", "shift_input", "shift_output"};
-  int rank = 0; MPI_Comm_rank(comm, &rank);
-  FILE *fp = rank == 0 ? fopen(name, "a") : nullptr;
-  for (int dir = 0; dir < 2; dir++) {
-    double t[PNFFT_TIMER_LENGTH], mx[PNFFT_TIMER_LENGTH];
-    for (int i = 0; i < PNFFT_TIMER_LENGTH; i++) t[i] = dir ? AS_PLAN(ths)->timer_adj[i] : AS_PLAN(ths)->timer_trafo[i];
-    PNX(timer_average)(t);
-    MPI_Reduce(t, mx, PNFFT_TIMER_LENGTH, MPI_DOUBLE, MPI_MAX, 0, comm);
-    if (fp) for (int i = 1; i < 8; i++) fprintf(fp, "pnfft_%s_%s = %.3e;\n", dir ? "adj" : "trafo", names[i], mx[i]);
-  }
-  if (fp) fclose(fp);
+static void timer_report_run(FILE *f, const TimerReport &r, int size, int idx) {
+  const unsigned fl = r.flags;
+  fprintf(f, "%% pnfft_flags == %s", (fl & PNFFT_WINDOW_GAUSSIAN) ? "PNFFT_WINDOW_GAUSSIAN" : (fl & PNFFT_WINDOW_BSPLINE) ? "PNFFT_WINDOW_BSPLINE" :
+          (fl & PNFFT_WINDOW_SINC_POWER) ? "PNFFT_WINDOW_SINC_POWER" : (fl & PNFFT_WINDOW_BESSEL_I0) ? "PNFFT_WINDOW_BESSEL_I0" : "PNFFT_WINDOW_KAISER_BESSEL");
+  const struct { unsigned bit; const char *on, *off; } tab[] = {
+    {PNFFT_PRE_PHI_HAT, " | PNFFT_PRE_PHI_HAT", ""}, {PNFFT_FAST_GAUSSIAN, " | PNFFT_FAST_GAUSSIAN", ""},
+    {PNFFT_PRE_CONST_PSI, " | PNFFT_PRE_CONST_PSI", ""}, {PNFFT_PRE_LIN_PSI, " | PNFFT_PRE_LIN_PSI", ""},
+    {PNFFT_PRE_QUAD_PSI, " | PNFFT_PRE_QUAD_PSI", ""}, {PNFFT_PRE_CUB_PSI, " | PNFFT_PRE_CUB_PSI", ""},
+    {PNFFT_FFT_IN_PLACE, " | PNFFT_FFT_IN_PLACE", " | PNFFT_FFT_OUT_OF_PLACE"}, {PNFFT_SORT_NODES, " | PNFFT_SORT_NODES", ""},
+    {PNFFT_INTERLACED, " | PNFFT_INTERLACED", ""}, {PNFFT_SHIFTED_F_HAT, " | PNFFT_SHIFTED_F_HAT", ""},
+    {PNFFT_SHIFTED_X, " | PNFFT_SHIFTED_X", ""}, {PNFFT_TRANSPOSED_F_HAT, " | PNFFT_TRANSPOSED_F_HAT", ""},
+    {PNFFT_DIFF_IK, " | PNFFT_DIFF_IK", " | PNFFT_DIFF_AD"}, {PNFFT_REAL_F, " | PNFFT_REAL_F", ""},
+    {PNFFT_MALLOC_F_HAT, " | PNFFT_MALLOC_F_HAT", ""}};
+  for (const auto &t : tab) fputs((fl & t.bit) ? t.on : t.off, f);
+  fprintf(f, "\nindex(%d) = %d;  procs(%d) = %d;  np_pnfft(%d, 1:3) = [%d %d %d];  ", idx, idx, idx, size, idx, r.np[0], r.np[1], r.np[2]);
+  fprintf(f, "N_pnfft(%d, 1:3) = [%td %td %td ];  n_pnfft(%d, 1:3) = [%td %td %td ];  m_pnfft(%d) = %d;\n", idx, r.N[0], r.N[1], r.N[2],
+          idx, r.n[0], r.n[1], r.n[2], idx, r.m);
 }
-void PNX(write_average_timer_adv)(const PNX(plan) ths, const char *name, MPI_Comm comm) { PNX(write_average_timer)(ths, name, comm); }
+// one direction: maxima over the ranks, averaged over the iterations; the iteration count printed is the caller's own
+static void timer_report_block(FILE *f, MPI_Comm comm, const char *prefix, const double *timer, bool adv, int idx) {
+  double *mt = PNX(timer_reduce_max)(comm, const_cast<double *>(timer));
+  PNX(timer_average)(mt);
+  if (f) {
+    if (!adv) {
+      fprintf(f, "%s_iter(%d)    = %d;  %s(%d)   = %.3e;\n", prefix, idx, (int)timer[PNFFT_TIMER_ITER], prefix, idx, mt[PNFFT_TIMER_WHOLE]);
+    } else {
+      fprintf(f, "%s_matrix_D(%d)   = %.3e;  %s_matrix_F(%d)   = %.3e;\n", prefix, idx, mt[PNFFT_TIMER_MATRIX_D], prefix, idx, mt[PNFFT_TIMER_MATRIX_F]);
+      fprintf(f, "%s_matrix_B(%d)   = %.3e;  %s_gcells(%d)     = %.3e;\n", prefix, idx, mt[PNFFT_TIMER_MATRIX_B], prefix, idx, mt[PNFFT_TIMER_GCELLS]);
+      fprintf(f, "%s_sort_nodes(%d) = %.3e;  %s_loop_B(%d)     = %.3e;\n", prefix, idx, mt[PNFFT_TIMER_SORT_NODES], prefix, idx, mt[PNFFT_TIMER_LOOP_B]);
+      fprintf(f, "%s_shift_in(%d)   = %.3e;  %s_shift_out(%d)  = %.3e;\n", prefix, idx, mt[PNFFT_TIMER_SHIFT_INPUT], prefix, idx, mt[PNFFT_TIMER_SHIFT_OUTPUT]);
+    }
+  }
+  free(mt);
+}
+// f is the destination on rank 0 and NULL elsewhere (the other ranks only take part in the reductions)
+static void timer_report(FILE *f, MPI_Comm comm, const TimerReport &r, bool legend, bool basic, bool adv) {
+  int size = 1;
+  MPI_Comm_size(comm, &size);
+  const int idx = (int)lrint(round(log((double)size) / log(2.0))) + 1;
+  if (f && legend) timer_report_legend(f);
+  if (f && basic) timer_report_run(f, r, size, idx);
+  if (basic) { timer_report_block(f, comm, "pnfft_trf", r.trafo, false, idx); timer_report_block(f, comm, "pnfft_adj", r.adj, false, idx); }
+  if (adv) { timer_report_block(f, comm, "pnfft_trf", r.trafo, true, idx); timer_report_block(f, comm, "pnfft_adj", r.adj, true, idx); }
+  if (f) fflush(f);
+}
+static TimerReport timer_report_of(const PlanT *p) {
+  TimerReport r;
+  r.flags = p->pnfft_flags; r.m = p->L.m;
+  for (int t = 0; t < 3; t++) { r.N[t] = p->L.N[t]; r.n[t] = p->L.n[t]; }
+  r.np[0] = p->mesh.np[0]; r.np[1] = p->mesh.np[1]; r.np[2] = 1;
+  r.trafo = p->timer_trafo; r.adj = p->timer_adj;
+  return r;
+}
+static FILE *timer_report_file(const char *name, MPI_Comm comm, bool *is_new) {
+  int rank = 0;
+  MPI_Comm_rank(comm, &rank);
+  if (rank) return nullptr;
+  FILE *probe = fopen(name, "r");
+  *is_new = probe == nullptr;
+  if (probe) fclose(probe);
+  FILE *f = fopen(name, "a+");
+  if (!f) { fprintf(stderr, "Error: Cannot open file %s.\n", name); exit(1); }
+  return f;
+}
+static void timer_report_to(const TimerReport &r, const char *name, MPI_Comm comm, bool adv) {
+  int rank = 0;
+  MPI_Comm_rank(comm, &rank);
+  if (!name) { timer_report(rank ? nullptr : stdout, comm, r, true, true, adv); return; }
+  bool is_new = false;
+  FILE *f = timer_report_file(name, comm, &is_new);
+  timer_report(f, comm, r, is_new, true, adv);
+  if (f) fclose(f);
+}
+void PNX(print_average_timer)(const PNX(plan) ths, MPI_Comm comm) { timer_report_to(timer_report_of(AS_PLAN(ths)), nullptr, comm, false); }
+void PNX(print_average_timer_adv)(const PNX(plan) ths, MPI_Comm comm) { timer_report_to(timer_report_of(AS_PLAN(ths)), nullptr, comm, true); }
+void PNX(write_average_timer)(const PNX(plan) ths, const char *name, MPI_Comm comm) { timer_report_to(timer_report_of(AS_PLAN(ths)), name, comm, false); }
+void PNX(write_average_timer_adv)(const PNX(plan) ths, const char *name, MPI_Comm comm) { timer_report_to(timer_report_of(AS_PLAN(ths)), name, comm, true); }
+// host-only: the report pnfft_write_average_timer(_adv) would append to `name` for a plan with these flags, sizes, process mesh
+// and timer arrays (no plan, no GPU; for the CPU test suite)
+void PNX(b200_timer_report_host)(const char *name, unsigned pnfft_flags, const INT *N, const INT *n, int m, const int *np3,
+                                 const double *timer_trafo, const double *timer_adj, int adv, MPI_Comm comm) {
+  TimerReport r;
+  r.flags = pnfft_flags; r.m = m;
+  for (int t = 0; t < 3; t++) { r.N[t] = N[t]; r.n[t] = n[t]; r.np[t] = np3[t]; }
+  r.trafo = timer_trafo; r.adj = timer_adj;
+  timer_report_to(r, name, comm, adv != 0);
+}
 
 // every rank in turn prints its block; k_t = local_N_start[t] + i_t (reference api/pnfft.h:233-238)
 static void apr_block(const RT *data, int ncomp, const INT *local_N, const INT *local_N_start, const char *name, MPI_Comm comm) {

@@ -310,3 +310,40 @@ C.CDLL("libc.so.6").fflush(None)
     # transposed block local_N = (3, 1, 2), starts (-1, 0, -2): memory order (k1, k2, k0) = extents (1, 2, 3), starts (0, -2, -1)
     idx = re.findall(r"\[(-?\d+),(-?\d+),(-?\d+)\]", rest)
     assert [tuple(int(v) for v in t) for t in idx] == [(0, a, b) for a in (-2, -1) for b in (-1, 0, 1)]
+
+
+def test_timer_report_follows_reference_format(tmp_path):
+    """pnfft_write_average_timer / _adv (reference kernel/timer.c:139-367): the Octave-readable report -- legend once per new
+    file, one comment line with the plan's flags, index / procs / np / N / n / m, then pnfft_trf / pnfft_adj iteration
+    counts and per-iteration maxima, the stage breakdown in the _adv variant -- through the host probe of the same code."""
+    import ctypes as C
+    comm = A.create_procmesh_2d(1, 1)
+    fn = A.lib().pnfft_b200_timer_report_host
+    I3, D = C.c_ssize_t * 3, C.c_double * 10
+    fn.argtypes = [C.c_char_p, C.c_uint, I3, I3, C.c_int, C.c_int * 3, D, D, C.c_int, C.c_int]
+    fn.restype = None
+    path = str(tmp_path / "timer.m")
+    tr, ad = D(4, 2.0, 0.5, 0.1, 0.2, 0.8, 0.9, 0.3, 0, 0), D(2, 1.0, 0.25, 0.05, 0.1, 0.4, 0.45, 0.15, 0, 0)
+    fn(path.encode(), (1 << 13) | (1 << 1) | (1 << 6) | (1 << 12), I3(16, 16, 16), I3(32, 32, 32), 6, (C.c_int * 3)(1, 1, 1), tr, ad, 0, comm)
+    fn(path.encode(), 1 << 11, I3(8, 12, 10), I3(16, 24, 20), 4, (C.c_int * 3)(1, 1, 1), tr, ad, 1, comm)
+    legend = ("%% N  - NFFT size\n%% n  - FFT size\n%% np - process grid\n%% procs - number of processes\n%% pnfft - PNFFT runtime\n"
+              "%% pfft  - PFFT runtime\n%% index(i) = log(procs(i)) + 1\n").replace("%%", "%")
+
+    def run(flagtext, N, n, m):
+        return ("%% pnfft_flags == %s\n" % flagtext).replace("%%", "%") + \
+            "index(1) = 1;  procs(1) = 1;  np_pnfft(1, 1:3) = [1 1 1];  N_pnfft(1, 1:3) = [%d %d %d ];  n_pnfft(1, 1:3) = [%d %d %d ];  m_pnfft(1) = %d;\n" % (N + n + (m,))
+
+    def basic(prefix, t):
+        return "%s_iter(1)    = %d;  %s(1)   = %.3e;\n" % (prefix, int(t[0]), prefix, t[1] / t[0])
+
+    def adv(prefix, t):
+        a = [v / t[0] for v in t]
+        return ("%s_matrix_D(1)   = %.3e;  %s_matrix_F(1)   = %.3e;\n%s_matrix_B(1)   = %.3e;  %s_gcells(1)     = %.3e;\n"
+                "%s_sort_nodes(1) = %.3e;  %s_loop_B(1)     = %.3e;\n%s_shift_in(1)   = %.3e;  %s_shift_out(1)  = %.3e;\n"
+                % (prefix, a[7], prefix, a[6], prefix, a[5], prefix, a[4], prefix, a[3], prefix, a[2], prefix, a[8], prefix, a[9]))
+
+    want = legend + run("PNFFT_WINDOW_GAUSSIAN | PNFFT_FAST_GAUSSIAN | PNFFT_FFT_OUT_OF_PLACE | PNFFT_DIFF_IK | PNFFT_MALLOC_F_HAT",
+                        (16, 16, 16), (32, 32, 32), 6) + basic("pnfft_trf", list(tr)) + basic("pnfft_adj", list(ad))
+    want += run("PNFFT_WINDOW_KAISER_BESSEL | PNFFT_FFT_OUT_OF_PLACE | PNFFT_TRANSPOSED_F_HAT | PNFFT_DIFF_AD", (8, 12, 10), (16, 24, 20), 4)
+    want += basic("pnfft_trf", list(tr)) + basic("pnfft_adj", list(ad)) + adv("pnfft_trf", list(tr)) + adv("pnfft_adj", list(ad))
+    assert open(path).read() == want
