@@ -347,3 +347,17 @@ def test_timer_report_follows_reference_format(tmp_path):
     want += run("PNFFT_WINDOW_KAISER_BESSEL | PNFFT_FFT_OUT_OF_PLACE | PNFFT_TRANSPOSED_F_HAT | PNFFT_DIFF_AD", (8, 12, 10), (16, 24, 20), 4)
     want += basic("pnfft_trf", list(tr)) + basic("pnfft_adj", list(ad)) + adv("pnfft_trf", list(tr)) + adv("pnfft_adj", list(ad))
     assert open(path).read() == want
+
+
+def test_init_f_hat_3d_is_the_reference_drivers_formula():
+    """pnfft_init_f_hat_3d forwards to PFFT's generator in the reference (api/api-basic.c:663-679), which is not available; the
+    product uses the in-tree formula of the reference's own check program (tests/check_vs_pfft.c:167-181):
+    data[k] = 1000 / (2 g + 1) + i 1000 / (2 g + 2) with g the row-major index of k + N/2."""
+    import ctypes as C
+    N, lN, lNs = (6, 4, 8), (3, 4, 5), (-1, -2, -3)
+    out = np.zeros(lN, np.complex128)
+    I3 = C.c_ssize_t * 3
+    A.lib().pnfft_init_f_hat_3d(I3(*N), I3(*lN), I3(*lNs), C.c_uint(0), out.ctypes.data_as(C.c_void_p))
+    k = np.meshgrid(*[np.arange(lNs[t], lNs[t] + lN[t]) for t in range(3)], indexing="ij")
+    g = ((k[0] + N[0] // 2) * N[1] + (k[1] + N[1] // 2)) * N[2] + (k[2] + N[2] // 2)
+    assert np.array_equal(out, 1000.0 / (2 * g + 1) + 1j * (1000.0 / (2 * g + 2)))
