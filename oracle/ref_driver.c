@@ -245,7 +245,7 @@ static PNX(plan) probe_plan(const DRV(probe_cfg) *P, MPI_Comm *comm)
                 : PNX(init_guru)(3, P->N, P->n, x_max, P->m, P->pnfft_flags, PFFT_ESTIMATE, *comm);
 }
 
-/* which: 0 psi, 1 dpsi, 2 inv_phi_hat, 3 phi_hat, 4 ddpsi.  arg: x (real) for 0/1/4, k (as R) for 2/3 */
+/* which: 0 psi, 1 dpsi, 2 inv_phi_hat, 3 phi_hat, 4 ddpsi, 5 pnfft_get_pnfft_flags.  arg: x (real) for 0/1/4, k (as R) for 2/3 */
 void DRV(probe)(const DRV(probe_cfg) *P, int which, int dim, INT count, const R *arg, R *out)
 {
   MPI_Comm comm;
@@ -256,6 +256,7 @@ void DRV(probe)(const DRV(probe_cfg) *P, int which, int dim, INT count, const R 
       case 1: out[i] = PNX(dpsi)(ths, dim, arg[i]); break;
       case 2: out[i] = PNX(inv_phi_hat)(ths, dim, (INT)arg[i]); break;
       case 4: out[i] = PNX(ddpsi)(ths, dim, arg[i]); break;
+      case 5: out[i] = (R)PNX(get_pnfft_flags)(ths); break;
       default: out[i] = PNX(phi_hat)(ths, dim, (INT)arg[i]); break;
     }
   }

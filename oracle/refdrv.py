@@ -208,7 +208,7 @@ class RefLib:
 
     def probe(self, which, dim, arg, N, n=None, m=6, x_max=(0.5, 0.5, 0.5), pnfft_flags=0, c2r=False):
         """which in {'psi','dpsi','ddpsi','inv_phi_hat','phi_hat'}; arg = x values or integer k values."""
-        code = {"psi": 0, "dpsi": 1, "inv_phi_hat": 2, "phi_hat": 3, "ddpsi": 4}[which]
+        code = {"psi": 0, "dpsi": 1, "inv_phi_hat": 2, "phi_hat": 3, "ddpsi": 4, "plan_flags": 5}[which]
         a = np.ascontiguousarray(arg, dtype=self.rdt)
         out = np.zeros_like(a)
         fn = getattr(self.lib, self.pre + "probe")

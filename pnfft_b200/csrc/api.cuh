@@ -137,7 +137,17 @@ int PNX(get_m)(const PNX(plan) ths) { return AS_PLAN(ths)->L.m; }
 void PNX(get_x_max)(const PNX(plan) ths, RT *x_max) { for (int t = 0; t < 3; t++) x_max[t] = AS_PLAN(ths)->x_max[t]; }
 void PNX(get_N)(const PNX(plan) ths, INT *N) { for (int t = 0; t < 3; t++) N[t] = AS_PLAN(ths)->L.N[t]; }
 void PNX(get_n)(const PNX(plan) ths, INT *n) { for (int t = 0; t < 3; t++) n[t] = AS_PLAN(ths)->L.n[t]; }
-unsigned PNX(get_pnfft_flags)(const PNX(plan) ths) { return AS_PLAN(ths)->pnfft_flags; }
+// The reference's planner tests the plan flags against precompute-namespace constants (api/api-guru.c:150-155:
+// PNFFT_PRE_HESSIAN_PSI = 1 << 3 sets PNFFT_PRE_GRAD_PSI = 1 << 2, which sets PNFFT_PRE_PSI = 1 << 1), so a plan made with
+// PNFFT_PRE_LIN_PSI reports PNFFT_PRE_CONST_PSI and PNFFT_FAST_GAUSSIAN as well, one made with PNFFT_PRE_CONST_PSI reports
+// PNFFT_FAST_GAUSSIAN: what pnfft_get_pnfft_flags and the timer reports show (the plan itself keeps the caller's flags; the
+// interpolation order already follows the promotion, Core::init).
+static unsigned reference_plan_flags(unsigned fl) {
+  if (fl & (1u << 3)) fl |= 1u << 2;
+  if (fl & (1u << 2)) fl |= 1u << 1;
+  return fl;
+}
+unsigned PNX(get_pnfft_flags)(const PNX(plan) ths) { return reference_plan_flags(AS_PLAN(ths)->pnfft_flags); }
 unsigned PNX(get_pfft_flags)(const PNX(plan) ths) { return AS_PLAN(ths)->pfft_flags; }
 void PNX(get_b)(const PNX(plan) ths, RT *b0, RT *b1, RT *b2) { *b0 = AS_PLAN(ths)->b[0]; *b1 = AS_PLAN(ths)->b[1]; *b2 = AS_PLAN(ths)->b[2]; }
 
@@ -311,7 +321,7 @@ static void timer_report_legend(FILE *f) {
              "%% pnfft - PNFFT runtime\n%% pfft  - PFFT runtime\n%% index(i) = log(procs(i)) + 1\n");
 }
 static void timer_report_run(FILE *f, const TimerReport &r, int size, int idx) {
-  const unsigned fl = r.flags;
+  const unsigned fl = reference_plan_flags(r.flags);
   fprintf(f, "%% pnfft_flags == %s", (fl & PNFFT_WINDOW_GAUSSIAN) ? "PNFFT_WINDOW_GAUSSIAN" : (fl & PNFFT_WINDOW_BSPLINE) ? "PNFFT_WINDOW_BSPLINE" :
           (fl & PNFFT_WINDOW_SINC_POWER) ? "PNFFT_WINDOW_SINC_POWER" : (fl & PNFFT_WINDOW_BESSEL_I0) ? "PNFFT_WINDOW_BESSEL_I0" : "PNFFT_WINDOW_KAISER_BESSEL");
   const struct { unsigned bit; const char *on, *off; } tab[] = {

@@ -347,6 +347,16 @@ def test_timer_report_follows_reference_format(tmp_path):
     want += run("PNFFT_WINDOW_KAISER_BESSEL | PNFFT_FFT_OUT_OF_PLACE | PNFFT_TRANSPOSED_F_HAT | PNFFT_DIFF_AD", (8, 12, 10), (16, 24, 20), 4)
     want += basic("pnfft_trf", list(tr)) + basic("pnfft_adj", list(ad)) + adv("pnfft_trf", list(tr)) + adv("pnfft_adj", list(ad))
     assert open(path).read() == want
+    # the flags shown are the reference plan's after its planner promoted them (api/api-guru.c:150-155; probed from the
+    # compiled reference: PRE_LIN_PSI -> + PRE_CONST_PSI + FAST_GAUSSIAN), as pnfft_get_pnfft_flags returns them
+    path2 = str(tmp_path / "timer2.m")
+    fn(path2.encode(), 1 << 3, I3(8, 12, 10), I3(16, 24, 20), 4, (C.c_int * 3)(1, 1, 1), tr, ad, 0, comm)
+    assert "% pnfft_flags == PNFFT_WINDOW_KAISER_BESSEL | PNFFT_FAST_GAUSSIAN | PNFFT_PRE_CONST_PSI | PNFFT_PRE_LIN_PSI | " in open(path2).read()
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libpnfft_ref.so")
+    if os.path.exists(ref_so):
+        from oracle import refdrv
+        got = refdrv.get(False).probe("plan_flags", 0, np.zeros(1), (16, 16, 16), m=4, pnfft_flags=1 << 3)
+        assert int(got[0]) == (1 << 3) | (1 << 2) | (1 << 1)
 
 
 def test_init_f_hat_3d_is_the_reference_drivers_formula():
